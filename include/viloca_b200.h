@@ -1,0 +1,168 @@
+/*
+ * viloca_b200.h — C ABI of the B200-native CAVI engine for VILOCA's local haplotype inference.
+ *
+ * This is the drop-in boundary for ONE path of cbg-ethz/VILOCA: the coordinate-ascent
+ * variational inference loop of
+ *   viloca/local_haplotype_inference/use_quality_scores/cavi.py:70-210   (run_cavi)
+ *   viloca/local_haplotype_inference/learn_error_params/cavi.py:71-255   (run_cavi)
+ * together with the update equations (update_eqs.py), the ELBO (elbo_eqs.py) and the
+ * finishing contraction of analyze_results.py:74-80.  The reference has no FFI for this
+ * path (it is NumPy); the seam this library replaces is the Python call
+ *   cavi.run_cavi(n_cluster, alpha0, alphabet, reference_binary, reads_seq_binary,
+ *                 reads_weights, reads_log_error_proba, start_id, output_dir,
+ *                 convergence_threshold, record_history, rng, seed_number)
+ * (use_quality_scores/cavi.py:70-84) batched over all windows of a genome and all random
+ * restarts.  Conventions follow the reference's existing native module libshorah
+ * (lib/src/bindings.cpp:13-34): plain scalars and pointers in, int return, 0 = success.
+ * Unlike libshorah there is NO process-global state: every call takes a batch handle and
+ * handles are independent (one per GPU / host thread).
+ *
+ * Soft CAVI exits ("ELBO converged.", "Error: ELBO is decreasing.", "Error: ELBO is nan.",
+ * use_quality_scores/cavi.py:155-165) are per-restart status codes, never error returns.
+ * A non-zero return means a hard error (bad argument, CUDA failure); vl_last_error() gives
+ * the message for the calling thread.
+ *
+ * Memory: the caller owns every buffer.  Host pointers are read/written synchronously with
+ * respect to the call that takes them.  The device workspace is allocated by the caller
+ * (PyTorch owns it in the Python host layer) and must outlive the batch.
+ */
+#ifndef VILOCA_B200_H
+#define VILOCA_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VL_ABI_VERSION 1
+#define VL_N_BASES 5          /* alphabet "ACGT-" (shotgun.py:197, run_dpm_mfa.py:26) */
+#define VL_CODE_N 255         /* read / reference character outside the alphabet      */
+#define VL_MAX_CLUSTERS 128   /* K = --n_max_haplotypes (cli.py:179-181), default 100  */
+
+/* inference mode: which reference package the numbers must match */
+#define VL_MODE_UQS 0         /* use_quality_scores  */
+#define VL_MODE_LEP 1         /* learn_error_params  */
+
+/* per-restart exit state (exit_message of run_cavi) */
+#define VL_STATUS_RUNNING    0
+#define VL_STATUS_CONVERGED  1  /* "ELBO converged."            cavi.py:163-165 */
+#define VL_STATUS_DECREASING 2  /* "Error: ELBO is decreasing." cavi.py:160-162 */
+#define VL_STATUS_NAN        3  /* "Error: ELBO is nan."        cavi.py:155-159 */
+#define VL_STATUS_MAXITER    4  /* iteration cap hit (the reference has no cap) */
+
+/* layout of the per-restart scalar blocks (doubles) */
+#define VL_INIT_STRIDE 8      /* a0, b0, mean_log_gamma[0], mean_log_gamma[1], c0, d0, mean_log_theta[0], mean_log_theta[1] */
+#define VL_SCALAR_STRIDE 16   /* see vl_scalar_index */
+enum vl_scalar_index {
+  VL_S_ELBO = 0, VL_S_GAMMA_A, VL_S_GAMMA_B, VL_S_MLG0, VL_S_MLG1,
+  VL_S_THETA_C, VL_S_THETA_D, VL_S_MLT0, VL_S_MLT1,
+  VL_S_DSUM_ALPHA, VL_S_DSUM_AB, VL_S_DSUM_CD,
+  VL_S_TERM_DATA, VL_S_TERM_PI, VL_S_TERM_CLUSTER, VL_S_TERM_HAPLO
+};
+
+/*
+ * One window = one call of run_dpm_mfa.main (use_quality_scores/run_dpm_mfa.py:18-31).
+ * Row order of the reads is the first-seen order of preparation.py:56-76 — it defines
+ * which row of init_cluster belongs to which read.
+ */
+typedef struct vl_window_desc {
+  int32_t mode;          /* VL_MODE_*                                                    */
+  int32_t n_reads;       /* N: unique reads (rows)                                       */
+  int32_t length;        /* L: window length                                             */
+  int32_t n_clusters;    /* K                                                            */
+  int32_t n_starts;      /* R: random restarts (cavi.py:26-67)                           */
+  int32_t max_iter;      /* iteration cap per restart, > 0                               */
+  double alpha0;         /* Dirichlet concentration (cli.py:112-114)                     */
+  double conv_thres;     /* |dELBO| threshold, uqs only (cli.py:183-185); lep uses 1e-3  */
+  const uint8_t* codes;        /* [N*L] 0..4 = "ACGT-", VL_CODE_N otherwise (one-hot row of zeros) */
+  const double* log_hit;       /* uqs: [N*L] log theta_nl               (preparation.py:123-157)   */
+  const double* log_off;       /* uqs: [N*L] log((1-theta_nl)/(B-1)); both NULL for lep            */
+  const double* weights;       /* [N] read multiplicities (reads_weights)                          */
+  const uint8_t* ref_codes;    /* [L] reference, same coding                                       */
+  const double* init_cluster;  /* [R*N*K] initial mean_cluster (initialization.py:46-54)           */
+  const double* init_scalars;  /* [R*VL_INIT_STRIDE]                                               */
+} vl_window_desc;
+
+/* Caller-allocated result buffers of one window; any pointer may be NULL to skip it. */
+typedef struct vl_window_result {
+  double* elbo;            /* [R] final ELBO                                             */
+  int32_t* n_iterations;   /* [R] `iter` as reported in dict_result["n_iterations"]      */
+  int32_t* n_updates;      /* [R] number of update() calls actually performed            */
+  int32_t* status;         /* [R] VL_STATUS_*                                            */
+  int32_t* converged;      /* [R] the sticky `converged` flag                            */
+  int32_t* history_len;    /* [R]                                                        */
+  double* history;         /* [R*history_stride] history_elbo                            */
+  int32_t history_stride;
+  int32_t state_restart;   /* in: restart whose state to copy, or -1 = best ELBO         */
+  int32_t best_restart;    /* out: argmax ELBO, first on ties (run_dpm_mfa.py:83-95)     */
+  double* mean_haplo;      /* [K*L*B]  mean_haplo of state_restart, C order (K,L,B)      */
+  double* mean_cluster;    /* [N*K]                                                      */
+  double* alpha;           /* [K]                                                        */
+  double* mean_log_pi;     /* [K]                                                        */
+  double* scalars;         /* [VL_SCALAR_STRIDE]                                         */
+} vl_window_result;
+
+typedef struct vl_batch vl_batch;
+
+int vl_abi_version(void);
+const char* vl_last_error(void);
+
+/* Number of CUDA devices visible, or a negative value if the runtime is unusable. */
+int vl_device_count(void);
+
+/* Device bytes a batch over these windows needs (host pointers in the descs are not read). */
+int vl_batch_workspace_bytes(const vl_window_desc* windows, int32_t n_windows, size_t* bytes_out);
+
+/*
+ * Create a batch on `device` inside a caller-owned device workspace.  `stream` is a
+ * cudaStream_t (NULL = the legacy default stream).  Host pointers in the descs are not read
+ * here; the shapes are.
+ */
+int vl_batch_create(vl_batch** out, int32_t device, const vl_window_desc* windows,
+                    int32_t n_windows, void* dev_workspace, size_t dev_bytes, void* stream);
+void vl_batch_destroy(vl_batch* batch);
+
+/* Host -> device copy of every window's inputs and initial state; resets all restarts. */
+int vl_batch_upload(vl_batch* batch, const vl_window_desc* windows, int32_t n_windows);
+
+/*
+ * Run CAVI for every (window, restart) until each has left its loop (the `while` of
+ * cavi.py:120).  Device-resident; returns after the stream has drained.  `n_launches_out`
+ * (optional) receives the number of kernels launched.
+ */
+int vl_batch_run(vl_batch* batch, int64_t* n_launches_out);
+
+/* Run exactly `n_updates` more update()+ELBO iterations on every still-running restart. */
+int vl_batch_step(vl_batch* batch, int32_t n_updates, int64_t* n_launches_out);
+
+/* Device -> host copy of results. */
+int vl_batch_fetch(vl_batch* batch, vl_window_result* results, int32_t n_windows);
+
+/*
+ * Teacher forcing for parity tests: overwrite the running state of one restart with a state
+ * of the reference (the keys update_eqs.update reads, update_eqs.py:9-19) and set the loop
+ * counter, so that one vl_batch_step reproduces exactly one reference iteration.
+ * scalars: [VL_SCALAR_STRIDE], entries MLG0/1, MLT0/1, DSUM_* are read.
+ */
+int vl_batch_set_state(vl_batch* batch, int32_t window, int32_t restart,
+                       const double* mean_cluster, const double* mean_log_pi,
+                       const double* scalars, int32_t iter);
+
+/*
+ * Finishing contraction (analyze_results.py:65-80): merge the clusters of `restart` with
+ * group_of[k] in [0, n_groups) and recompute mean_haplo for the merged responsibilities.
+ * merged_cluster_out [N*n_groups] and merged_haplo_out [n_groups*L*B] are host buffers.
+ */
+int vl_batch_merge_haplo(vl_batch* batch, int32_t window, int32_t restart,
+                         const int32_t* group_of, int32_t n_groups,
+                         double* merged_cluster_out, double* merged_haplo_out);
+
+/* Milliseconds the last vl_batch_run / vl_batch_step spent on the device (CUDA events). */
+double vl_batch_last_device_ms(const vl_batch* batch);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VILOCA_B200_H */

@@ -1,0 +1,297 @@
+"""Batched CAVI on one GPU: the Python face of the C ABI.
+
+A :class:`Window` carries the tensors the reference's ``run_cavi`` receives
+(use_quality_scores/cavi.py:70-84) in compact form plus the seeded initial states of its
+restarts; :class:`CaviBatch` runs all (window, restart) problems of a list of windows on one
+device.  PyTorch is used only to own the device workspace and pinned host buffers.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass, field
+from typing import Optional, Sequence
+
+import numpy as np
+import torch
+
+from . import _capi as capi
+
+DEFAULT_MAX_ITER = 5000
+
+
+@dataclass
+class Window:
+    """One inference window (one call of ``run_dpm_mfa.main`` in the reference)."""
+    mode: str                      # "uqs" = use_quality_scores, "lep" = learn_error_params
+    codes: np.ndarray              # (N, L) uint8, 0..4 = "ACGT-", 255 otherwise
+    weights: np.ndarray            # (N,) read multiplicities
+    ref_codes: np.ndarray          # (L,) uint8
+    init_cluster: np.ndarray       # (R, N, K) initial mean_cluster per restart
+    init_scalars: np.ndarray       # (R, 8) a0, b0, log g0, log(1-g0), c0, d0, log t0, log(1-t0)
+    alpha0: float
+    log_hit: Optional[np.ndarray] = None   # (N, L) log theta              (uqs)
+    log_off: Optional[np.ndarray] = None   # (N, L) log((1-theta)/(B-1))   (uqs)
+    conv_thres: float = 1e-3
+    max_iter: int = DEFAULT_MAX_ITER
+    name: str = ""
+
+    def __post_init__(self):
+        self.codes = np.ascontiguousarray(self.codes, dtype=np.uint8)
+        self.weights = np.ascontiguousarray(self.weights, dtype=np.float64)
+        self.ref_codes = np.ascontiguousarray(self.ref_codes, dtype=np.uint8)
+        self.init_cluster = np.ascontiguousarray(self.init_cluster, dtype=np.float64)
+        self.init_scalars = np.ascontiguousarray(self.init_scalars, dtype=np.float64)
+        if self.init_cluster.ndim == 2:
+            self.init_cluster = self.init_cluster[None]
+        if self.init_scalars.ndim == 1:
+            self.init_scalars = self.init_scalars[None]
+        if self.mode not in ("uqs", "lep"):
+            raise ValueError(f"mode must be 'uqs' or 'lep', got {self.mode!r}")
+        n, l = self.codes.shape
+        if self.weights.shape != (n,) or self.ref_codes.shape != (l,):
+            raise ValueError("weights / ref_codes do not match codes")
+        r = self.init_cluster.shape[0]
+        if self.init_cluster.shape[1] != n or self.init_scalars.shape != (r, capi.INIT_STRIDE):
+            raise ValueError("init_cluster must be (R, N, K) and init_scalars (R, 8)")
+        if self.mode == "uqs":
+            if self.log_hit is None or self.log_off is None:
+                raise ValueError("uqs window needs log_hit and log_off")
+            self.log_hit = np.ascontiguousarray(self.log_hit, dtype=np.float64)
+            self.log_off = np.ascontiguousarray(self.log_off, dtype=np.float64)
+            if self.log_hit.shape != (n, l) or self.log_off.shape != (n, l):
+                raise ValueError("log_hit / log_off must be (N, L)")
+
+    @property
+    def n_reads(self) -> int:
+        return self.codes.shape[0]
+
+    @property
+    def length(self) -> int:
+        return self.codes.shape[1]
+
+    @property
+    def n_clusters(self) -> int:
+        return self.init_cluster.shape[2]
+
+    @property
+    def n_starts(self) -> int:
+        return self.init_cluster.shape[0]
+
+    def cost(self) -> float:
+        """Relative cost estimate used by the longest-first scheduler."""
+        return float(self.n_reads) * self.length * self.n_clusters * self.n_starts
+
+    def input_bytes(self) -> int:
+        b = self.codes.nbytes + self.weights.nbytes + self.ref_codes.nbytes
+        b += self.init_cluster.nbytes + self.init_scalars.nbytes
+        if self.mode == "uqs":
+            b += self.log_hit.nbytes + self.log_off.nbytes
+        return b
+
+    def desc(self) -> capi.WindowDesc:
+        d = capi.WindowDesc()
+        d.mode = capi.MODE_UQS if self.mode == "uqs" else capi.MODE_LEP
+        d.n_reads, d.length = self.n_reads, self.length
+        d.n_clusters, d.n_starts = self.n_clusters, self.n_starts
+        d.max_iter = int(self.max_iter)
+        d.alpha0, d.conv_thres = float(self.alpha0), float(self.conv_thres)
+        d.codes = capi.u8_ptr(self.codes)
+        d.log_hit = capi.f64_ptr(self.log_hit if self.mode == "uqs" else None)
+        d.log_off = capi.f64_ptr(self.log_off if self.mode == "uqs" else None)
+        d.weights = capi.f64_ptr(self.weights)
+        d.ref_codes = capi.u8_ptr(self.ref_codes)
+        d.init_cluster = capi.f64_ptr(self.init_cluster)
+        d.init_scalars = capi.f64_ptr(self.init_scalars)
+        return d
+
+
+@dataclass
+class RestartOutcome:
+    """``dict_result`` of one ``run_cavi`` call (use_quality_scores/cavi.py:190-206)."""
+    elbo: float
+    n_iterations: int
+    n_updates: int
+    status: int
+    converged: bool
+    history_elbo: np.ndarray
+
+    @property
+    def exit_message(self) -> str:
+        return capi.STATUS_MESSAGE[self.status]
+
+
+@dataclass
+class WindowOutcome:
+    restarts: list
+    best_restart: int
+    state_restart: int
+    state: dict = field(default_factory=dict)   # keys of state_curr_dict for state_restart
+
+
+class CaviBatch:
+    """All (window, restart) problems of ``windows`` on one device."""
+
+    def __init__(self, windows: Sequence[Window], device: int = 0, stream: Optional[int] = None):
+        if not windows:
+            raise ValueError("empty batch")
+        self.windows = list(windows)
+        self.device = int(device)
+        self._descs = (capi.WindowDesc * len(self.windows))(*[w.desc() for w in self.windows])
+        nbytes = C.c_size_t(0)
+        capi.check(capi.lib.vl_batch_workspace_bytes(self._descs, len(self.windows), C.byref(nbytes)))
+        self.workspace_bytes = int(nbytes.value)
+        if not torch.cuda.is_available():
+            raise capi.EngineError("no CUDA device: the CAVI engine has no CPU fallback")
+        self._workspace = torch.empty(self.workspace_bytes + 256, dtype=torch.uint8,
+                                      device=torch.device("cuda", self.device))
+        ptr = (self._workspace.data_ptr() + 255) // 256 * 256
+        self._handle = C.c_void_p()
+        capi.check(capi.lib.vl_batch_create(C.byref(self._handle), self.device, self._descs,
+                                            len(self.windows), C.c_void_p(ptr),
+                                            self.workspace_bytes, C.c_void_p(stream or 0)))
+        self.n_problems = sum(w.n_starts for w in self.windows)
+        self.launches = 0
+
+    # -- lifetime ------------------------------------------------------------------------
+    def close(self) -> None:
+        if getattr(self, "_handle", None) is not None and self._handle.value:
+            capi.lib.vl_batch_destroy(self._handle)
+            self._handle = C.c_void_p()
+        self._workspace = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    # -- data path -----------------------------------------------------------------------
+    def input_bytes(self) -> int:
+        return sum(w.input_bytes() for w in self.windows)
+
+    def upload(self) -> None:
+        capi.check(capi.lib.vl_batch_upload(self._handle, self._descs, len(self.windows)))
+
+    def run(self) -> int:
+        n = C.c_int64(0)
+        capi.check(capi.lib.vl_batch_run(self._handle, C.byref(n)))
+        self.launches += int(n.value)
+        return int(n.value)
+
+    def step(self, n_updates: int = 1) -> int:
+        n = C.c_int64(0)
+        capi.check(capi.lib.vl_batch_step(self._handle, int(n_updates), C.byref(n)))
+        self.launches += int(n.value)
+        return int(n.value)
+
+    def last_device_ms(self) -> float:
+        return float(capi.lib.vl_batch_last_device_ms(self._handle))
+
+    def set_state(self, window: int, restart: int, mean_cluster, mean_log_pi, scalars, it: int) -> None:
+        mc = np.ascontiguousarray(mean_cluster, dtype=np.float64)
+        lp = np.ascontiguousarray(mean_log_pi, dtype=np.float64)
+        sc = np.ascontiguousarray(scalars, dtype=np.float64)
+        assert sc.shape == (capi.SCALAR_STRIDE,)
+        capi.check(capi.lib.vl_batch_set_state(self._handle, window, restart, capi.f64_ptr(mc),
+                                               capi.f64_ptr(lp), capi.f64_ptr(sc), int(it)))
+
+    def merge_haplo(self, window: int, restart: int, group_of: np.ndarray, n_groups: int):
+        """analyze_results.py:65-80 on the device: merged responsibilities (N, G) and the
+        haplotype table (G, L, B) recomputed from them."""
+        w = self.windows[window]
+        g = np.ascontiguousarray(group_of, dtype=np.int32)
+        zc = np.empty((w.n_reads, n_groups), dtype=np.float64)
+        hm = np.empty((n_groups, w.length, capi.N_BASES), dtype=np.float64)
+        capi.check(capi.lib.vl_batch_merge_haplo(self._handle, window, restart, capi.i32_ptr(g),
+                                                 int(n_groups), capi.f64_ptr(zc), capi.f64_ptr(hm)))
+        return zc, hm
+
+    def fetch(self, state: str | int = "best", want_cluster: bool = True, want_haplo: bool = True,
+              want_history: bool = True) -> list:
+        """Copy results to the host.  ``state`` = "best" (max-ELBO restart), "none", or a
+        restart index."""
+        nw = len(self.windows)
+        res = (capi.WindowResult * nw)()
+        keep = []
+        for i, w in enumerate(self.windows):
+            r_ = w.n_starts
+            bufs = {
+                "elbo": np.empty(r_, np.float64), "n_iterations": np.empty(r_, np.int32),
+                "n_updates": np.empty(r_, np.int32), "status": np.empty(r_, np.int32),
+                "converged": np.empty(r_, np.int32), "history_len": np.empty(r_, np.int32),
+            }
+            res[i].elbo = capi.f64_ptr(bufs["elbo"])
+            for key in ("n_iterations", "n_updates", "status", "converged", "history_len"):
+                setattr(res[i], key, capi.i32_ptr(bufs[key]))
+            if want_history:
+                bufs["history"] = np.zeros((r_, w.max_iter), np.float64)
+                res[i].history = capi.f64_ptr(bufs["history"])
+                res[i].history_stride = w.max_iter
+            if state == "none":
+                res[i].state_restart = -1
+            else:
+                res[i].state_restart = -1 if state == "best" else int(state)
+                k, l, n = w.n_clusters, w.length, w.n_reads
+                if want_haplo:
+                    bufs["mean_haplo"] = np.empty((k, l, capi.N_BASES), np.float64)
+                    res[i].mean_haplo = capi.f64_ptr(bufs["mean_haplo"])
+                if want_cluster:
+                    bufs["mean_cluster"] = np.empty((n, k), np.float64)
+                    res[i].mean_cluster = capi.f64_ptr(bufs["mean_cluster"])
+                bufs["alpha"] = np.empty(k, np.float64)
+                bufs["mean_log_pi"] = np.empty(k, np.float64)
+                bufs["scalars"] = np.empty(capi.SCALAR_STRIDE, np.float64)
+                res[i].alpha = capi.f64_ptr(bufs["alpha"])
+                res[i].mean_log_pi = capi.f64_ptr(bufs["mean_log_pi"])
+                res[i].scalars = capi.f64_ptr(bufs["scalars"])
+            keep.append(bufs)
+        capi.check(capi.lib.vl_batch_fetch(self._handle, res, nw))
+        out = []
+        for i, w in enumerate(self.windows):
+            b = keep[i]
+            restarts = []
+            for r in range(w.n_starts):
+                hl = int(b["history_len"][r])
+                hist = b["history"][r, :hl].copy() if want_history else np.empty(0)
+                restarts.append(RestartOutcome(
+                    elbo=float(b["elbo"][r]), n_iterations=int(b["n_iterations"][r]),
+                    n_updates=int(b["n_updates"][r]), status=int(b["status"][r]),
+                    converged=bool(b["converged"][r]), history_elbo=hist))
+            best = int(res[i].best_restart)
+            sr = best if state in ("best", "none") else int(state)
+            st = {}
+            if state != "none":
+                sc = b["scalars"]
+                st = {
+                    "alpha": b["alpha"], "mean_log_pi": b["mean_log_pi"],
+                    "gamma_a": sc[capi.S_GAMMA_A], "gamma_b": sc[capi.S_GAMMA_B],
+                    "mean_log_gamma": (sc[capi.S_MLG0], sc[capi.S_MLG1]),
+                    "digamma_alpha_sum": sc[capi.S_DSUM_ALPHA], "digamma_a_b_sum": sc[capi.S_DSUM_AB],
+                    "elbo": sc[capi.S_ELBO],
+                    "elbo_terms": (sc[capi.S_TERM_DATA], sc[capi.S_TERM_PI], sc[capi.S_TERM_CLUSTER],
+                                   sc[capi.S_TERM_HAPLO]),
+                }
+                if w.mode == "lep":
+                    st.update({"theta_c": sc[capi.S_THETA_C], "theta_d": sc[capi.S_THETA_D],
+                               "mean_log_theta": (sc[capi.S_MLT0], sc[capi.S_MLT1]),
+                               "digamma_c_d_sum": sc[capi.S_DSUM_CD]})
+                if want_haplo:
+                    st["mean_haplo"] = b["mean_haplo"]
+                if want_cluster:
+                    st["mean_cluster"] = b["mean_cluster"]
+            out.append(WindowOutcome(restarts=restarts, best_restart=best, state_restart=sr, state=st))
+        return out
+
+
+def run_windows(windows: Sequence[Window], device: int = 0) -> list:
+    """upload + run + fetch of one batch: the end-to-end call with host buffers."""
+    with CaviBatch(windows, device=device) as batch:
+        batch.upload()
+        batch.run()
+        return batch.fetch()

@@ -1,0 +1,356 @@
+#!/usr/bin/env python3
+"""Benchmark of the CAVI hot path (BASELINE.json: CAVI windows/sec at 1/2/4/8 B200 vs the
+host-CPU reference).
+
+A *step* is one pass of the hot path over one batch of synthetic input: every window of one
+synthetic genome per GPU (workload ``hiv5k_uqs`` = BASELINE configs[1]: HIV-1 9.7 kb, window
+201, 5,000x coverage, 5 haplotypes, use_quality_scores, K = 100 -> 145 windows), each run to
+the end of its CAVI loop.
+
+  value   windows (x restarts) per second with the window tensors already resident in HBM:
+          only the device time of the iteration loop (CUDA events) is counted
+  e2e     the same through the host-buffer API: pinned host -> device copy of all inputs, the
+          loop, device -> host copy of the results, every step
+  roofline  the dominant kernel's algorithmic FP64 flop rate, timed live with CUDA events,
+          against the FP64 tensor (DMMA) ceiling measured on this pool
+  cpu_baseline  the NumPy oracle port (same einsum calls as the reference) on one host core,
+          bounded sample, extrapolated with the iteration counts the GPU run took
+
+``--impl reference`` times the reference's CPU algorithm (the oracle port; the reference is
+pure Python/NumPy and cannot be shipped to the GPU box) with its own parallelism: a
+multiprocessing Pool over windows with cpu_count()-1 single-threaded workers
+(viloca/shotgun.py:527-538).
+
+Multi-GPU: one process per GPU (torchrun), windows sharded by the host-side longest-first
+scheduler, no data-path collective; weak scaling (one synthetic genome per GPU).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "cavi_windows_per_sec"
+UNIT = "windows/s"
+ITER_TABLE = os.path.join(ROOT, "profiles", "bench_iterations.json")
+FP64_PEAK_FILE = os.path.join(ROOT, "profiles", "r01_fp64_peak.json")
+TRAFFIC_FILE = os.path.join(ROOT, "profiles", "dram_traffic.json")
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="hiv5k_uqs")
+    ap.add_argument("--windows", type=int, default=None, help="windows per synthetic genome (default: all)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--record-iterations", action="store_true", help="write profiles/bench_iterations.json")
+    return ap.parse_args()
+
+
+def dist_env():
+    return int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
+
+
+def shard_items(spec, n_windows, world):
+    """Global work list of a weak-scaling job: one synthetic genome per GPU, every window an
+    independent item; longest-first partition over the ranks (no collective)."""
+    from viloca_b200 import scheduler
+    items = [(sample, w) for sample in range(world) for w in range(n_windows)]
+    costs = [float(spec.coverage) * spec.window_length * spec.n_clusters * spec.n_starts] * len(items)
+    return items, scheduler.lpt_partition(costs, world)
+
+
+def algorithmic_flops_per_contraction(windows):
+    """2*N*K*L*B per (window, restart) with N = unique reads, B = 5, unpadded."""
+    return sum(2.0 * w.n_reads * w.n_clusters * w.length * 5 * w.n_starts for w in windows)
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+             "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device):
+        self.device, self.rows, self.proc = device, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits",
+                                          "-lms", "200", "-i", str(self.device)], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except subprocess.TimeoutExpired:
+                self.proc.kill()
+        sm, smax, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); smax.append(float(r[2]))
+            except (ValueError, IndexError):
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(smax), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------
+# CPU legs (the only places that may execute oracle/)
+# ------------------------------------------------------------------------------------------
+
+def _oracle_window_iterations(win, n_iter):
+    """Seconds for n_iter oracle iterations (update + ELBO, exactly the reference's per-iteration
+    work incl. its redundant einsums) on one window, single thread."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import _bridge as br
+    w, ref, data = br.dense_inputs(win)
+    init = br.oracle_init(win)
+    t0 = time.perf_counter()
+    traj = br.orc.run(win.mode, w, ref, data, init, convergence_threshold=win.conv_thres, max_iterations=n_iter)
+    return time.perf_counter() - t0, traj.n_updates
+
+
+def _pool_worker(arg):
+    name, index, n_iter = arg
+    os.environ["OMP_NUM_THREADS"] = "1"
+    from viloca_b200 import synthetic
+    win = synthetic.make_window(synthetic.WORKLOADS[name], index)
+    dt, n = _oracle_window_iterations(win, n_iter)
+    return dt, n, win.n_reads
+
+
+def load_iteration_table(name):
+    try:
+        return json.load(open(ITER_TABLE))[name]
+    except (OSError, KeyError, ValueError):
+        return None
+
+
+def cpu_baseline_single_core(name, windows, n_updates, budget_s=20.0):
+    """One core, bounded: a few dozen oracle iterations on the first windows, extrapolated to the
+    whole workload with the iteration counts the GPU run actually took (cost/iteration is
+    linear in N_unique)."""
+    spent, read_iters, sample = 0.0, 0.0, []
+    n_iter = 12
+    for i, win in enumerate(windows[:3]):
+        dt, n = _oracle_window_iterations(win, n_iter)
+        spent += dt
+        read_iters += n * win.n_reads
+        sample.append(f"w{i}:{n}it")
+        if spent > budget_s:
+            break
+    sec_per_read_iter = spent / read_iters
+    total = sum(u * w.n_reads for w, u in zip(windows, n_updates)) * sec_per_read_iter
+    return {"value": len(windows) / total, "unit": UNIT, "cores": 1, "kind": "port",
+            "sample": f"oracle port, {'+'.join(sample)} of {name} ({spent:.1f}s), extrapolated with the GPU run's "
+                      f"per-window iteration counts", "sec_per_read_iteration": sec_per_read_iter}
+
+
+def run_reference_arm(args):
+    rank, world, _ = dist_env()
+    if rank != 0:
+        return
+    import multiprocessing as mp
+    from viloca_b200 import synthetic
+    spec = synthetic.WORKLOADS[args.workload]
+    procs = max((os.cpu_count() or 2) - 1, 1)          # shotgun.py:527
+    n_iter = 10
+    table = load_iteration_table(args.workload)
+    mean_updates = float(np.mean(table["n_updates"])) if table else 300.0
+    mean_reads = float(np.mean(table["n_reads"])) if table else None
+    per_step = []
+    ctx = mp.get_context("fork")
+    with ctx.Pool(processes=procs) as pool:
+        for step in range(args.warmup + args.steps):
+            jobs = [(args.workload, (step * procs + i) % spec.n_windows, n_iter) for i in range(procs)]
+            t0 = time.perf_counter()
+            out = pool.map(_pool_worker, jobs)
+            dt = time.perf_counter() - t0
+            if step >= args.warmup:
+                # windows/s = (window-iterations done / iterations a window needs) / time, corrected
+                # for the sampled windows' size relative to the workload mean
+                scale = 1.0
+                if mean_reads:
+                    scale = float(np.mean([o[2] for o in out])) / mean_reads
+                per_step.append(sum(o[1] for o in out) / mean_updates * scale / dt)
+    value = float(np.mean(per_step))
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": None, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": args.workload, "n_windows": spec.n_windows, "coverage": spec.coverage,
+                   "window_length": spec.window_length, "n_clusters": spec.n_clusters, "mode": spec.mode},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": procs, "kind": "port",
+                         "sample": f"Pool({procs}) x {n_iter} iterations per window per step; converted with "
+                                   f"mean iterations/window = {mean_updates:.1f} "
+                                   f"({'profiles/bench_iterations.json' if table else 'assumed'})"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------
+# GPU arm
+# ------------------------------------------------------------------------------------------
+
+def run_b200_arm(args):
+    import torch
+    import torch.distributed as dist
+    from viloca_b200 import engine, synthetic
+
+    rank, world, local_rank = dist_env()
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    device = local_rank
+    torch.cuda.set_device(device)
+    spec = synthetic.WORKLOADS[args.workload]
+    n_windows = args.windows or spec.n_windows
+    items, parts = shard_items(spec, n_windows, world)
+    mine = [items[i] for i in parts[rank]]
+    windows = [synthetic.make_window(spec, w, master_seed=sample).pin() for sample, w in mine]
+    n_problems = sum(w.n_starts for w in windows)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    batch = engine.CaviBatch(windows, device=device)
+    h2d = batch.input_bytes()
+    d2h = 0
+    launches = 0
+    outcomes = None
+    for _ in range(args.warmup):
+        batch.upload(); batch.run(); outcomes = batch.fetch()
+    sampler = ClockSampler(device)
+    sampler.start()
+    barrier()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    run_ms = 0.0
+    ev0.record()
+    for _ in range(args.steps):
+        batch.upload()
+        launches += len(windows) + 1                    # mcount per window + init
+        launches += batch.run()
+        run_ms += batch.last_device_ms()
+        outcomes = batch.fetch()
+        launches += len(windows)                        # mean_haplo export per window
+    ev1.record()
+    barrier()
+    e2e_ms = ev0.elapsed_time(ev1)
+    clocks = sampler.stop()
+    for o, w in zip(outcomes, windows):
+        d2h += w.n_clusters * w.length * 5 * 8 + w.n_reads * w.n_clusters * 8 + 2 * w.n_clusters * 8 + 128
+        d2h += sum(len(r.history_elbo) for r in o.restarts) * 8
+
+    # per-kernel roofline numbers, measured live (all restarts are still running in the first 10 updates)
+    batch.upload()
+    prof = batch.profile_step(8)
+    flops = algorithmic_flops_per_contraction(windows)
+    n_updates = [o.restarts[o.best_restart].n_updates for o in outcomes]
+    all_updates = [r.n_updates for o in outcomes for r in o.restarts]
+    read_iters = sum(r.n_updates * w.n_reads for o, w in zip(outcomes, windows) for r in o.restarts)
+    raw_read_iters = sum(r.n_updates * getattr(w, "n_raw", w.n_reads) for o, w in zip(outcomes, windows) for r in o.restarts)
+
+    t = torch.tensor([run_ms, e2e_ms, float(n_problems), float(read_iters), float(raw_read_iters), float(launches),
+                      float(h2d), float(d2h)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        tmax = t.clone(); dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        tsum = t.clone(); dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
+    else:
+        tmax = tsum = t
+    run_ms_max, e2e_ms_max = float(tmax[0]), float(tmax[1])
+    total_problems = float(tsum[2])
+
+    if args.record_iterations and rank == 0:
+        os.makedirs(os.path.dirname(ITER_TABLE), exist_ok=True)
+        table = {}
+        if os.path.exists(ITER_TABLE):
+            table = json.load(open(ITER_TABLE))
+        table[args.workload] = {"n_updates": all_updates, "n_reads": [w.n_reads for w in windows],
+                                "n_raw": [getattr(w, "n_raw", w.n_reads) for w in windows]}
+        json.dump(table, open(ITER_TABLE, "w"))
+
+    if rank == 0:
+        dom = "cluster" if prof["cluster"][0] >= prof["haplo"][0] else "haplo"
+        dom_ms = prof[dom][0] / max(prof[dom][1], 1)
+        try:
+            peak = max(r["tflops"] for r in json.load(open(FP64_PEAK_FILE))["results"] if r["kind"] == "dmma884")
+            peak_src = "measured on this pool: DMMA m8n8k4 register loop, profiles/r01_fp64_peak.json (MEASURED_PEAKS.json has no FP64 entry)"
+        except (OSError, ValueError, KeyError):
+            peak, peak_src = 37.0, "fallback: nominal B200 FP64 tensor peak"
+        traffic = None
+        try:
+            traffic = json.load(open(TRAFFIC_FILE)).get(args.workload, {}).get(dom)
+        except (OSError, ValueError):
+            pass
+        achieved = flops / (dom_ms * 1e-3) * 1e-12
+        line = {
+            "metric": METRIC, "value": total_problems * args.steps / (run_ms_max * 1e-3), "unit": UNIT,
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": run_ms_max / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": args.workload, "mode": spec.mode, "genome_length": spec.genome_length,
+                       "window_length": spec.window_length, "windows_per_gpu": len(windows), "coverage": spec.coverage,
+                       "n_unique_mean": float(np.mean([w.n_reads for w in windows])), "n_clusters": spec.n_clusters,
+                       "n_starts": spec.n_starts, "haplotypes": spec.n_haplotypes, "parallelism": f"windows x{world}",
+                       "l2": "inputs larger than L2 (working set %.0f MB per GPU, re-uploaded every step)" % (batch.workspace_bytes / 1e6)},
+            "e2e": {"value": total_problems * args.steps / (e2e_ms_max * 1e-3), "unit": UNIT,
+                    "h2d_bytes_per_step": int(float(tsum[6])), "d2h_bytes_per_step": int(float(tsum[7])),
+                    "ms_per_step": e2e_ms_max / args.steps},
+            "gpu_launches": int(float(tsum[5])),
+            "read_iterations_per_sec": float(tsum[3]) * args.steps / (run_ms_max * 1e-3),
+            "raw_read_iterations_per_sec": float(tsum[4]) * args.steps / (run_ms_max * 1e-3),
+            "iterations": {"mean": float(np.mean(all_updates)), "max": int(max(all_updates)), "min": int(min(all_updates))},
+            "clocks": clocks,
+            "roofline": {"bound": "tensor", "kernel": f"vl_{dom}_kernel", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
+                         "frac": achieved / peak, "traffic": traffic, "flops_per_launch": flops,
+                         "ms_per_launch": dom_ms, "peak_source": peak_src,
+                         "other_kernels_ms_per_launch": {k: v[0] / max(v[1], 1) for k, v in prof.items() if k != dom},
+                         "convention": "algorithmic 2*N_unique*K*L*B flops per contraction (B = 5, unpadded), all restarts active"},
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline_single_core(args.workload, windows, n_updates)
+        print(json.dumps(line), flush=True)
+    batch.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference_arm(args)
+    else:
+        run_b200_arm(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -159,6 +159,14 @@ int vl_batch_merge_haplo(vl_batch* batch, int32_t window, int32_t restart,
                          const int32_t* group_of, int32_t n_groups,
                          double* merged_cluster_out, double* merged_haplo_out);
 
+/*
+ * Like vl_batch_step, but brackets every launch with CUDA events on the launching stream and
+ * returns the summed device time per kernel (ms) and the launch counts:
+ * ms[0]/n[0] haplotype update, ms[1]/n[1] responsibility update, ms[2]/n[2] scalar update.
+ * Used by bench.py for the live roofline numbers; not a fast path.
+ */
+int vl_batch_profile_step(vl_batch* batch, int32_t n_updates, double* ms_out, int64_t* n_out);
+
 /* Milliseconds the last vl_batch_run / vl_batch_step spent on the device (CUDA events). */
 double vl_batch_last_device_ms(const vl_batch* batch);
 

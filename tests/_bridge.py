@@ -15,8 +15,10 @@ from oracle import cavi_oracle as orc  # noqa: E402
 
 def dense_inputs(win):
     """(weights, ref_onehot, data) with data = E for uqs, float one-hot reads for lep."""
-    reads = orc.onehot_from_codes(win.codes)
-    ref = orc.onehot_from_codes(win.ref_codes)
+    # one-hot dtypes as in the reference pipeline (int8 for uqs, float64 for lep)
+    dt = np.int8 if win.mode == "uqs" else np.float64
+    reads = orc.onehot_from_codes(win.codes, dtype=dt)
+    ref = orc.onehot_from_codes(win.ref_codes, dtype=dt)
     if win.mode == "uqs":
         E = np.where(reads > 0, win.log_hit[:, :, None], win.log_off[:, :, None])
         E[win.codes == 255] = 0

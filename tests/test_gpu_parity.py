@@ -1,0 +1,313 @@
+"""Parity of the CUDA path (through the C ABI) with the reference.
+
+Tolerances (BASELINE.json north_star): responsibilities and ELBO within 1e-6 relative per
+iteration in FP64, identical haplotype sequences.  The engine is checked at the much tighter
+ENG_TOL as well, which is what a pure summation-order difference in FP64 produces.
+"""
+import dataclasses
+import json
+import os
+
+import numpy as np
+import pytest
+
+import _bridge as br
+from oracle import cavi_oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+SPEC_TOL = 1e-6     # the stated bar
+ENG_TOL = 1e-9      # what we actually hold
+
+
+def _engine():
+    from viloca_b200 import engine
+    return engine
+
+
+def _window_from_golden(g, mode, restarts_init, conv_thres=1e-3, max_iter=5000):
+    from viloca_b200 import tensors
+    engine = _engine()
+    kw = {}
+    if mode == "uqs":
+        kw["log_hit"], kw["log_off"] = tensors.log_error_terms(g["qualities"])
+    zs = np.stack([r[0] for r in restarts_init])
+    scs = np.stack([r[1] for r in restarts_init])
+    return engine.Window(mode=mode, codes=g["codes"], weights=g["weights"].astype(np.float64),
+                         ref_codes=g["ref_codes"], init_cluster=zs, init_scalars=scs,
+                         alpha0=float(g["alpha0"]), conv_thres=conv_thres, max_iter=max_iter, **kw)
+
+
+def _assert_state_close(st, ref_state, mode, tol):
+    assert np.array_equal(st["mean_cluster"] == 0, ref_state["mean_cluster"] == 0), "zero pattern of mean_cluster"
+    assert br.rel_err(st["mean_cluster"], ref_state["mean_cluster"]) < tol
+    assert br.rel_err(st["mean_haplo"], ref_state["mean_haplo"]) < tol
+    assert br.rel_err(st["alpha"], ref_state["alpha"]) < tol
+    assert br.rel_err(st["mean_log_pi"], ref_state["mean_log_pi"]) < tol
+    assert br.rel_err(st["gamma_a"], ref_state["gamma_a"]) < tol
+    assert br.rel_err(st["gamma_b"], ref_state["gamma_b"]) < tol
+    assert br.rel_err(np.array(st["mean_log_gamma"]), np.array(ref_state["mean_log_gamma"])) < tol
+    if mode == "lep":
+        assert br.rel_err(st["theta_c"], ref_state["theta_c"]) < tol
+        assert br.rel_err(st["theta_d"], ref_state["theta_d"]) < tol
+        assert br.rel_err(np.array(st["mean_log_theta"]), np.array(ref_state["mean_log_theta"])) < tol
+
+
+@pytest.mark.parametrize("mode", ["uqs", "lep"])
+def test_teacher_forced_against_reference_vectors(golden_dir, mode):
+    """State t of the REFERENCE in -> one device iteration -> compare with the reference's
+    state t+1 and its ELBO (terms included)."""
+    engine = _engine()
+    g = np.load(os.path.join(golden_dir, f"{mode}_steps.npz"), allow_pickle=True)
+    sc0 = np.zeros(8)
+    sc0[0], sc0[1] = g["init_gamma_a"], g["init_gamma_b"]
+    sc0[2:4] = g["init_mean_log_gamma"]
+    sc0[4:6] = 1.0
+    if mode == "lep":
+        sc0[4], sc0[5] = g["init_theta_c"], g["init_theta_d"]
+        sc0[6:8] = g["init_mean_log_theta"]
+    win = _window_from_golden(g, mode, [(g["init_mean_cluster"], sc0)])
+    n_iter = len(g["elbo"])
+    with engine.CaviBatch([win]) as b:
+        b.upload()
+        for it in range(n_iter):
+            if it == 0:
+                z_in, lp_in = g["init_mean_cluster"], g["init_mean_log_pi"]
+                mlg, mlt = g["init_mean_log_gamma"], (g["init_mean_log_theta"] if mode == "lep" else (0, 0))
+            else:
+                z_in, lp_in = g["mean_cluster"][it - 1], g["mean_log_pi"][it - 1]
+                mlg, mlt = g["mean_log_gamma"][it - 1], (g["mean_log_theta"][it - 1] if mode == "lep" else (0, 0))
+            sc = np.zeros(16)
+            sc[3], sc[4] = mlg
+            sc[7], sc[8] = mlt
+            sc[9], sc[10] = g["in_digamma_alpha_sum"][it], g["in_digamma_a_b_sum"][it]
+            if mode == "lep":
+                sc[11] = g["in_digamma_c_d_sum"][it]
+            b.set_state(0, 0, z_in, lp_in, sc, it)
+            b.step(1)
+            st = b.fetch(state=0)[0].state
+            ref_state = {k: g[k][it] for k in ("mean_cluster", "mean_haplo", "alpha", "mean_log_pi", "gamma_a",
+                                               "gamma_b", "mean_log_gamma")}
+            if mode == "lep":
+                ref_state.update({k: g[k][it] for k in ("theta_c", "theta_d", "mean_log_theta")})
+            _assert_state_close(st, ref_state, mode, SPEC_TOL)
+            _assert_state_close(st, ref_state, mode, ENG_TOL)
+            assert abs(st["elbo"] - g["elbo"][it]) < ENG_TOL * abs(g["elbo"][it])
+            got_terms = np.array(st["elbo_terms"])
+            assert br.rel_err(got_terms, g["terms"][it][:4]) < ENG_TOL
+
+
+def test_free_running_against_reference_run_cavi(golden_dir):
+    """Whole trajectories of the reference's cavi.run_cavi: iteration counts, exit messages
+    (including the soft failure 'ELBO is decreasing'), ELBO history, final haplotypes; the
+    three restarts of case b run as one multi-restart window."""
+    from viloca_b200 import init_state, tensors
+    engine = _engine()
+    g = np.load(os.path.join(golden_dir, "uqs_run.npz"), allow_pickle=True)
+    wins, keys = [], []
+    for name in ("a", "b", "c"):
+        seeds = [int(s) for s in g[f"{name}_seeds"]]
+        K = int(g[f"{name}_K"])
+        n = g[f"{name}_codes"].shape[0]
+        inits = [init_state.draw("uqs", K, 1e-4, n, np.random.default_rng(s)) for s in seeds]
+        lh, lo = tensors.log_error_terms(g[f"{name}_qualities"])
+        wins.append(engine.Window(mode="uqs", codes=g[f"{name}_codes"], weights=g[f"{name}_weights"].astype(float),
+                                  ref_codes=g[f"{name}_ref_codes"], init_cluster=np.stack([i[0] for i in inits]),
+                                  init_scalars=np.stack([i[1] for i in inits]), alpha0=1e-4, log_hit=lh, log_off=lo,
+                                  conv_thres=float(g[f"{name}_thr"])))
+        keys.append([f"{name}_s{s}" for s in seeds])
+    with engine.CaviBatch(wins) as b:
+        b.upload()
+        b.run()
+        for wi, ks in enumerate(keys):
+            elbos = []
+            for r, key in enumerate(ks):
+                out = b.fetch(state=[r if i == wi else "none" for i in range(len(wins))])[wi]
+                rr = out.restarts[r]
+                assert rr.n_iterations == int(g[key + "_n_iterations"]), key
+                assert rr.exit_message == str(g[key + "_exit_message"]), key
+                assert rr.converged == bool(g[key + "_converged"]), key
+                assert br.rel_err(rr.history_elbo, g[key + "_history"]) < ENG_TOL
+                assert orc.haplotype_strings(out.state["mean_haplo"]) == orc.haplotype_strings(g[key + "_mean_haplo"])
+                assert br.rel_err(out.state["mean_cluster"], g[key + "_mean_cluster"]) < SPEC_TOL
+                elbos.append(float(g[key + "_elbo"]))
+            # best-run selection of run_dpm_mfa.py:83-95
+            assert b.fetch(state="none")[wi].best_restart == int(np.argmax(elbos))
+
+
+def _parse_support(path):
+    from viloca_b200 import fasta
+    import re
+    out = []
+    for rec in fasta.parse(path):
+        m = re.search(r"posterior=(.*)\s*ave_reads=(.*)", rec.description)   # shorah_snv.py:224-236
+        out.append((rec.id, rec.seq, float(m.group(1)), int(m.group(2))))
+    return out
+
+
+def test_data4_window_files_end_to_end(golden_dir, tmp_path):
+    """The reference's fixture window through the drop-in entry point: same haplotypes, same
+    ave_reads, posteriors equal to 1e-9, identical corrected-reads file."""
+    from viloca_b200.local_haplotype_inference.use_quality_scores import run_dpm_mfa
+    d = os.path.join(golden_dir, "data4")
+    stem = "w-HXB2-2335-2535"
+    out_dir = str(tmp_path) + "/"
+    run_dpm_mfa.main(os.path.join(d, stem + ".reads.fas"), os.path.join(d, stem + ".ref.fas"),
+                     os.path.join(d, stem + ".qualities.npy"), out_dir, 1, 100, 0.0001, seed=42)
+    got = _parse_support(out_dir + stem + ".reads-support.fas")
+    exp = _parse_support(os.path.join(d, "expected_seed42.reads-support.fas"))
+    assert [(i, s, w) for i, s, _, w in got] == [(i, s, w) for i, s, _, w in exp]
+    for (_, _, pg, _), (_, _, pe, _) in zip(got, exp):
+        assert abs(pg - pe) <= ENG_TOL * abs(pe)
+        assert (pg >= 0.9) == (pe >= 0.9)          # the threshold shorah_snv applies (-p 0.9)
+    assert open(out_dir + stem + ".reads-cor.fas").read() == \
+        open(os.path.join(d, "expected_seed42.reads-cor.fas")).read()
+
+
+def _spec(mode, K, called):
+    from viloca_b200 import synthetic
+    base = synthetic.WORKLOADS["hiv5k_uqs"]
+    return dataclasses.replace(base, mode=mode, n_clusters=K, called_length=called)
+
+
+@pytest.mark.parametrize("mode,n_raw,L,K", [("uqs", 400, 201, 100), ("lep", 400, 201, 100), ("uqs", 250, 90, 24),
+                                            ("lep", 250, 90, 50), ("uqs", 200, 130, 128)])
+def test_free_running_against_oracle(mode, n_raw, L, K):
+    from viloca_b200 import synthetic
+    engine = _engine()
+    win = synthetic.make_window(_spec(mode, K, int(L * 0.75)), 3, n_reads=n_raw, length=L)
+    traj = br.oracle_run(win)
+    out = engine.run_windows([win])[0]
+    r = out.restarts[0]
+    assert (r.n_iterations, r.n_updates, r.exit_message) == (traj.n_iterations, traj.n_updates, traj.exit_message)
+    assert br.rel_err(r.history_elbo, np.array(traj.history_elbo)) < ENG_TOL
+    assert orc.haplotype_strings(out.state["mean_haplo"]) == orc.haplotype_strings(traj.state["mean_haplo"])
+    assert br.rel_err(out.state["mean_cluster"], traj.state["mean_cluster"]) < SPEC_TOL
+
+
+def test_ragged_mixed_batch_equals_single_window_runs():
+    """Windows of different N, L, K and mode in one batch give bit-identical results to
+    running each alone (problems are independent; the reductions are order-fixed)."""
+    from viloca_b200 import synthetic
+    engine = _engine()
+    shapes = [("uqs", 300, 201, 100), ("lep", 120, 57, 10), ("uqs", 40, 16, 100), ("uqs", 500, 333, 30),
+              ("lep", 64, 201, 100), ("uqs", 1, 9, 5)]
+    wins = [synthetic.make_window(_spec(m, K, max(4, int(L * 0.8))), i, n_reads=n, length=L)
+            for i, (m, n, L, K) in enumerate(shapes)]
+    together = engine.run_windows(wins)
+    for w, o in zip(wins, together):
+        alone = engine.run_windows([w])[0]
+        assert alone.restarts[0].n_updates == o.restarts[0].n_updates
+        assert np.array_equal(alone.restarts[0].history_elbo, o.restarts[0].history_elbo)
+        assert np.array_equal(alone.state["mean_cluster"], o.state["mean_cluster"])
+        assert np.array_equal(alone.state["mean_haplo"], o.state["mean_haplo"])
+    # and the single-read window agrees with the oracle
+    traj = br.oracle_run(wins[-1])
+    assert together[-1].restarts[0].n_updates == traj.n_updates
+
+
+def test_edge_cases_all_N_columns_reference_N_and_iteration_cap():
+    from viloca_b200 import synthetic
+    engine = _engine()
+    win = synthetic.make_window(_spec("uqs", 16, 40), 9, n_reads=150, length=50)
+    win.codes[:, 7] = 255            # a column no read covers
+    win.codes[3, :] = 255            # a read that is all N
+    win.ref_codes[11] = 255          # N in the reference: all mass goes to gamma_b (update_eqs.py:103-112)
+    win.ref_codes[7] = 255
+    traj = br.oracle_run(win)
+    out = engine.run_windows([win])[0]
+    assert out.restarts[0].n_updates == traj.n_updates
+    assert br.rel_err(out.restarts[0].history_elbo, np.array(traj.history_elbo)) < ENG_TOL
+    assert br.rel_err(out.state["gamma_b"], traj.state["gamma_b"]) < ENG_TOL
+    capped = dataclasses.replace(win, max_iter=5)
+    out = engine.run_windows([capped])[0]
+    assert out.restarts[0].n_updates == 5 and out.restarts[0].status == 4 and not out.restarts[0].converged
+    t5 = br.oracle_run(win, max_iterations=5)
+    assert br.rel_err(out.restarts[0].history_elbo, np.array(t5.history_elbo)) < ENG_TOL
+
+
+def test_finishing_contraction_matches_oracle():
+    """analyze_results.py:65-80: merged responsibilities and the haplotype table recomputed
+    from them."""
+    from viloca_b200 import synthetic
+    engine = _engine()
+    win = synthetic.make_window(_spec("uqs", 40, 60), 4, n_reads=300, length=80)
+    w, ref, E = br.dense_inputs(win)
+    with engine.CaviBatch([win]) as b:
+        b.upload()
+        b.run()
+        st = b.fetch()[0].state
+        groups = orc.unique_haplotypes(st["mean_haplo"])
+        group_of = np.empty(win.n_clusters, dtype=np.int32)
+        for j, (_, members) in enumerate(groups):
+            group_of[members] = j
+        zc, hm = b.merge_haplo(0, 0, group_of, len(groups))
+    merged = orc.merge_clusters(st["mean_cluster"], groups)
+    assert np.array_equal(zc, merged)                       # same additions in the same order
+    h_ref = orc.uqs_update_mean_haplo(w, ref, E, merged, st["mean_log_gamma"])
+    assert br.rel_err(hm, h_ref) < ENG_TOL
+    post = orc.haplotype_posteriors(hm, groups)
+    post_ref = orc.haplotype_posteriors(h_ref, groups)
+    assert br.rel_err(np.array(post), np.array(post_ref)) < ENG_TOL
+
+
+def test_full_size_invariants_and_determinism():
+    """BASELINE config 2 at full size (N_raw = 5000, L = 201, K = 100): size-independent
+    properties of a CAVI fixed point, and run-to-run bit reproducibility."""
+    from viloca_b200 import synthetic
+    engine = _engine()
+    spec = synthetic.WORKLOADS["hiv5k_uqs"]
+    wins = [synthetic.make_window(spec, i) for i in range(2)]
+    res1 = engine.run_windows(wins)
+    res2 = engine.run_windows(wins)
+    for w, o, o2 in zip(wins, res1, res2):
+        st, r = o.state, o.restarts[0]
+        z, h = st["mean_cluster"], st["mean_haplo"]
+        np.testing.assert_allclose(z.sum(axis=1), 1.0, rtol=0, atol=1e-12)
+        np.testing.assert_allclose(h.sum(axis=2), 1.0, rtol=0, atol=1e-12)
+        assert (z >= 0).all() and (h >= 0).all()
+        # sum(alpha) = K*alpha0 + sum(w); a + b = a0 + b0 + K*L  (invariants of update_alpha / update_a_and_b)
+        assert abs(st["alpha"].sum() - (w.n_clusters * w.alpha0 + w.weights.sum())) < 1e-8 * w.weights.sum()
+        a0, b0 = w.init_scalars[0, 0], w.init_scalars[0, 1]
+        assert abs(st["gamma_a"] + st["gamma_b"] - (a0 + b0 + w.n_clusters * w.length)) < 1e-7
+        np.testing.assert_allclose(st["alpha"], w.alpha0 + (w.weights[:, None] * z).sum(axis=0), rtol=1e-12)
+        hist = r.history_elbo
+        assert r.status in (1, 2) and len(hist) == r.n_updates
+        if r.status == 1:
+            assert (np.diff(hist)[2:] > -1e-5).all()         # coordinate ascent: ELBO never drops by > 1e-5
+            assert abs(hist[-1] - hist[-2]) < 1e-3 or r.n_updates == 10
+        assert np.array_equal(hist, o2.restarts[0].history_elbo)
+        assert np.array_equal(z, o2.state["mean_cluster"]) and np.array_equal(h, o2.state["mean_haplo"])
+        # the dominant haplotypes are recovered
+        found = set(orc.haplotype_strings(h))
+        from viloca_b200 import tensors
+        assert tensors.decode(w.true_haplotypes[0]) in found
+
+
+def test_lep_entry_point_writes_outputs(golden_dir, tmp_path):
+    from viloca_b200.local_haplotype_inference.learn_error_params import run_dpm_mfa
+    d = os.path.join(golden_dir, "data4")
+    stem = "w-HXB2-2335-2535"
+    out_dir = str(tmp_path) + "/"
+    run_dpm_mfa.main(os.path.join(d, stem + ".reads.fas"), os.path.join(d, stem + ".ref.fas"), out_dir, 2, 100, 0.0001,
+                     seed=42)
+    sup = _parse_support(out_dir + stem + ".reads-support.fas")
+    assert len(sup) >= 1 and sum(w for *_, w in sup) >= 87          # ties may count a read twice
+    assert all(len(s) == 201 for _, s, _, _ in sup)
+    assert os.path.getsize(out_dir + stem + ".reads-cor.fas") > 0
+
+
+def test_reference_signature_run_cavi(golden_dir):
+    """cavi.run_cavi with the reference's dense arguments (use_quality_scores/cavi.py:70-84)."""
+    from viloca_b200.local_haplotype_inference.use_quality_scores import cavi
+    g = np.load(os.path.join(golden_dir, "uqs_run.npz"), allow_pickle=True)
+    reads = orc.onehot_from_codes(g["c_codes"], dtype=np.int8)
+    ref = orc.onehot_from_codes(g["c_ref_codes"], dtype=np.int8)
+    E = orc.reads_log_error_tensor(g["c_qualities"], reads)
+    state, res = cavi.run_cavi(int(g["c_K"]), 1e-4, "ACGT-", ref, reads, g["c_weights"], E, 0, "./",
+                               float(g["c_thr"]), False, np.random.default_rng(seed=42), 42)
+    assert res["n_iterations"] == int(g["c_s42_n_iterations"]) and res["exit_message"] == "ELBO converged."
+    assert br.rel_err(np.array(res["history_elbo"]), g["c_s42_history"]) < ENG_TOL
+    for key in ("alpha", "mean_log_pi", "gamma_a", "gamma_b", "mean_log_gamma", "mean_haplo", "mean_cluster", "elbo"):
+        assert key in state
+    assert br.rel_err(state["alpha"], g["c_s42_alpha"]) < ENG_TOL

@@ -1,0 +1,129 @@
+"""Host-side logic that needs no GPU: preparation (against vectors from the reference's
+preparation.py), FASTA conventions, the longest-first scheduler, synthetic generators."""
+import os
+
+import numpy as np
+import pytest
+
+from viloca_b200 import fasta, scheduler, synthetic, tensors
+from viloca_b200.local_haplotype_inference import _common
+from viloca_b200.local_haplotype_inference.learn_error_params import preparation as prep_lep
+from viloca_b200.local_haplotype_inference.use_quality_scores import preparation as prep_uqs
+
+STEM = "w-REF-1-24"
+
+
+@pytest.fixture(scope="module")
+def prep(golden_dir):
+    return np.load(os.path.join(golden_dir, "prep.npz"), allow_pickle=True), os.path.join(golden_dir, "prep_window")
+
+
+@pytest.mark.parametrize("unique", [True, False])
+def test_uqs_preparation_matches_reference(prep, unique):
+    g, d = prep
+    reads, w, q, mapping = prep_uqs.load_and_process_reads(os.path.join(d, STEM + ".reads.fas"),
+                                                           os.path.join(d, STEM + ".qualities.npy"), "ACGT-", unique)
+    tag = "unique" if unique else "nonunique"
+    assert np.array_equal(reads, g[f"uqs_{tag}_reads"])
+    assert np.array_equal(w, g[f"uqs_{tag}_weights"])
+    assert np.array_equal(q, g[f"uqs_{tag}_qualities"])          # running-mean qualities, Q==0 -> 2: exact
+    E = prep_uqs.compute_reads_log_error_proba(q, reads, 5)
+    assert np.array_equal(E, g[f"uqs_{tag}_E"])                   # bit-identical log-error tensor
+    if unique:
+        assert ["|".join(i for i, _ in v) for v in mapping.values()] == list(g["uqs_unique_ids"])
+        assert w.sum() == 40 and reads.shape[0] == 29
+    else:
+        assert [m[0] for m in mapping] == list(g["uqs_nonunique_ids"])
+
+
+def test_reference_sequence_loading(prep):
+    g, d = prep
+    ref, ref_id = prep_uqs.load_reference_seq(os.path.join(d, STEM + ".ref.fas"), "ACGT-")
+    assert np.array_equal(ref, g["uqs_ref"]) and ref_id == str(g["uqs_ref_id"])
+    seq, _ = prep_lep.load_reference_seq(os.path.join(d, STEM + ".ref.fas"))
+    assert np.array_equal(prep_lep.reference2binary(seq, "ACGT-"), g["lep_ref"])
+    # reference tests/test_fasta2binary.py:19-63 (hard asserts of the reference's own suite)
+    assert np.array_equal(prep_uqs.reference2binary("ACGT-", "ACGT-"), np.eye(5, dtype=np.int8))
+    assert np.array_equal(prep_uqs.reference2binary("ANNT", "ACGT-"),
+                          np.array([[1, 0, 0, 0, 0], [0] * 5, [0] * 5, [0, 0, 0, 1, 0]], dtype=np.int8))
+
+
+@pytest.mark.parametrize("unique", [True, False])
+def test_lep_preparation_matches_reference(prep, unique):
+    g, d = prep
+    rl = prep_lep.load_fasta2reads_list(os.path.join(d, STEM + ".reads.fas"), "ACGT-", unique)
+    reads, w = prep_lep.reads_list_to_array(rl)
+    tag = "unique" if unique else "nonunique"
+    assert np.array_equal(reads, g[f"lep_{tag}_reads"])
+    assert np.array_equal(w, g[f"lep_{tag}_weights"])
+    assert [r.id for r in rl] == list(g[f"lep_{tag}_ids"])
+    assert ["|".join(r.identical_reads) for r in rl] == list(g[f"lep_{tag}_identical"])
+
+
+def test_dedup_weights_and_averaged_qualities():
+    """The scenario of the reference's tests/test_fasta2binary.py:119-150: weights [1, 2] and
+    averaged qualities."""
+    ids, seqs = ["r1", "r2", "r3"], ["ACGT", "TTTT", "TTTT"]
+    q = np.array([[40] * 4, [30] * 4, [20] * 4])
+    p = _common.prepare_reads(ids, seqs, q, "ACGT-", True)
+    assert list(p.weights) == [1, 2]
+    assert np.array_equal(p.qualities, np.array([[40.0] * 4, [25.0] * 4]))
+    assert p.read_ids == [["r1"], ["r2", "r3"]]
+    p = _common.prepare_reads(ids, seqs, q, "ACGT-", False)
+    assert list(p.weights) == [1, 1, 1] and p.codes.shape == (3, 4)
+
+
+def test_synthetic_dedup_equals_host_preparation():
+    spec = synthetic.WORKLOADS["hiv5k_uqs"]
+    rng = np.random.default_rng(5)
+    ref, haps = synthetic.make_haplotypes(rng, 40, 3)
+    codes_raw, quals_raw = synthetic.sample_reads(rng, haps, np.array([0.5, 0.3, 0.2]), 200,
+                                                  synthetic.WorkloadSpec(**{**spec.__dict__, "called_length": 30}))
+    codes, w, q, _ = synthetic.dedup_reads(codes_raw, quals_raw)
+    seqs = [tensors.decode(r) for r in codes_raw]
+    p = _common.prepare_reads([str(i) for i in range(200)], seqs, quals_raw, "ACGT-", True)
+    assert np.array_equal(p.codes, codes) and np.array_equal(p.weights, w) and np.array_equal(p.qualities, q)
+
+
+def test_fasta_roundtrip_and_header_conventions(tmp_path):
+    path = str(tmp_path / "x.fas")
+    fasta.write([("haplotype0", "hap_0 | posterior=0.5 ave_reads=3", "A" * 130),
+                 ("read7", "|posterior=1", "ACGT")], path)
+    text = open(path).read().split("\n")
+    assert text[0] == ">haplotype0 hap_0 | posterior=0.5 ave_reads=3"
+    assert [len(x) for x in text[1:4]] == [60, 60, 10]
+    assert text[4] == ">read7 |posterior=1"
+    recs = list(fasta.parse(path))
+    assert recs[0].id == "haplotype0" and recs[0].seq == "A" * 130
+    assert recs[1].description == "read7 |posterior=1"
+
+
+def test_encode_decode():
+    codes = tensors.encode("ACGT-NacgtX")
+    assert list(codes) == [0, 1, 2, 3, 4, 255, 255, 255, 255, 255, 255]
+    assert tensors.decode(codes[:6]) == "ACGT-N"
+    oh = tensors.onehot(codes[:6])
+    assert oh.shape == (6, 5) and oh[5].sum() == 0 and np.array_equal(tensors.codes_from_onehot(oh), codes[:6])
+
+
+def test_lpt_partition_is_balanced_and_deterministic():
+    costs = [9, 7, 6, 5, 5, 4, 3, 2, 2, 1]
+    bins = scheduler.lpt_partition(costs, 3)
+    assert sorted(i for b in bins for i in b) == list(range(10))
+    loads = [sum(costs[i] for i in b) for b in bins]
+    assert max(loads) - min(loads) <= 2
+    assert bins == scheduler.lpt_partition(costs, 3)
+    assert scheduler.lpt_partition([], 2) == [[], []]
+    assert scheduler.shard_for_rank(costs, 1, 3) == bins[1]
+    with pytest.raises(ValueError):
+        scheduler.lpt_partition(costs, 0)
+
+
+def test_group_haplotypes_sorted_and_first_max_wins():
+    h = np.zeros((3, 2, 5))
+    h[0, 0, 1] = h[0, 0, 2] = 0.5            # tie -> first maximum ('C')
+    h[0, 1, 0] = 1.0
+    h[1] = h[0]
+    h[2, 0, 0] = 1.0; h[2, 1, 0] = 1.0
+    groups = _common.group_haplotypes(h)
+    assert groups == [("AA", [2]), ("CA", [0, 1])]

@@ -391,6 +391,42 @@ int vl_batch_step(vl_batch* b, int32_t n_updates, int64_t* n_launches_out) {
   return 0;
 }
 
+int vl_batch_profile_step(vl_batch* b, int32_t n_updates, double* ms_out, int64_t* n_out) {
+  if (!b) return fail("batch is NULL");
+  if (!b->uploaded) return fail("vl_batch_profile_step before vl_batch_upload");
+  if (!ms_out || !n_out || n_updates < 0) return fail("bad argument");
+  VL_CUDA(cudaSetDevice(b->device));
+  for (int i = 0; i < 3; ++i) { ms_out[i] = 0.0; n_out[i] = 0; }
+  cudaEvent_t ev[4];
+  for (auto& e : ev) VL_CUDA(cudaEventCreate(&e));
+  const Layout& L = b->lay;
+  for (int it = 0; it < n_updates; ++it) {
+    for (const KernelClass& c : b->classes) {
+      VL_CUDA(cudaEventRecord(ev[0], b->stream));
+      VL_CUDA(vl_launch_contractions(c.kt, c.mode, b->d_probs(), b->dev<int2>(L.htiles) + c.h_off, (int)c.htiles.size(),
+                                     nullptr, 0, true, false, b->stream));
+      VL_CUDA(cudaEventRecord(ev[1], b->stream));
+      VL_CUDA(vl_launch_contractions(c.kt, c.mode, b->d_probs(), nullptr, 0, b->dev<int2>(L.ztiles) + c.z_off,
+                                     (int)c.ztiles.size(), false, true, b->stream));
+      VL_CUDA(cudaEventRecord(ev[2], b->stream));
+      VL_CUDA(cudaEventSynchronize(ev[2]));
+      float m0 = 0.f, m1 = 0.f;
+      VL_CUDA(cudaEventElapsedTime(&m0, ev[0], ev[1]));
+      VL_CUDA(cudaEventElapsedTime(&m1, ev[1], ev[2]));
+      ms_out[0] += m0; ms_out[1] += m1; n_out[0] += 1; n_out[1] += 1;
+    }
+    VL_CUDA(cudaEventRecord(ev[2], b->stream));
+    VL_CUDA(vl_launch_scalar(b->d_probs(), L.n_problems, b->d_done(), b->stream));
+    VL_CUDA(cudaEventRecord(ev[3], b->stream));
+    VL_CUDA(cudaEventSynchronize(ev[3]));
+    float m2 = 0.f;
+    VL_CUDA(cudaEventElapsedTime(&m2, ev[2], ev[3]));
+    ms_out[2] += m2; n_out[2] += 1;
+  }
+  for (auto& e : ev) cudaEventDestroy(e);
+  return 0;
+}
+
 static void fill_scalars(const VlState& S, double* out) {
   for (int i = 0; i < VL_SCALAR_STRIDE; ++i) out[i] = 0.0;
   out[VL_S_ELBO] = S.elbo; out[VL_S_GAMMA_A] = S.a; out[VL_S_GAMMA_B] = S.b;

@@ -16,7 +16,7 @@ import torch
 
 from . import _capi as capi
 
-DEFAULT_MAX_ITER = 5000
+DEFAULT_MAX_ITER = 50000   # safety cap; the reference's loop has none (cavi.py:120)
 
 
 @dataclass
@@ -76,6 +76,19 @@ class Window:
     @property
     def n_starts(self) -> int:
         return self.init_cluster.shape[0]
+
+    def pin(self) -> "Window":
+        """Re-home the host arrays in pinned memory (PyTorch owns it) so that the H2D copies
+        of vl_batch_upload are true asynchronous DMA transfers."""
+        self._pinned = []
+        for name in ("codes", "weights", "ref_codes", "init_cluster", "init_scalars", "log_hit", "log_off"):
+            a = getattr(self, name)
+            if a is None:
+                continue
+            t = torch.from_numpy(a).pin_memory()
+            self._pinned.append(t)
+            setattr(self, name, t.numpy())
+        return self
 
     def cost(self) -> float:
         """Relative cost estimate used by the longest-first scheduler."""
@@ -190,6 +203,15 @@ class CaviBatch:
         self.launches += int(n.value)
         return int(n.value)
 
+    def profile_step(self, n_updates: int):
+        """Per-kernel device time (ms) and launch counts over ``n_updates`` iterations:
+        {"haplo": (ms, n), "cluster": (ms, n), "scalar": (ms, n)}."""
+        ms = (C.c_double * 3)()
+        cnt = (C.c_int64 * 3)()
+        capi.check(capi.lib.vl_batch_profile_step(self._handle, int(n_updates), ms, cnt))
+        self.launches += int(sum(cnt))
+        return {k: (float(ms[i]), int(cnt[i])) for i, k in enumerate(("haplo", "cluster", "scalar"))}
+
     def last_device_ms(self) -> float:
         return float(capi.lib.vl_batch_last_device_ms(self._handle))
 
@@ -214,13 +236,15 @@ class CaviBatch:
 
     def fetch(self, state: str | int = "best", want_cluster: bool = True, want_haplo: bool = True,
               want_history: bool = True) -> list:
-        """Copy results to the host.  ``state`` = "best" (max-ELBO restart), "none", or a
-        restart index."""
+        """Copy results to the host.  ``state`` = "best" (max-ELBO restart), "none", a restart
+        index, or a per-window list of those."""
         nw = len(self.windows)
+        states = list(state) if isinstance(state, (list, tuple)) else [state] * nw
         res = (capi.WindowResult * nw)()
         keep = []
         for i, w in enumerate(self.windows):
             r_ = w.n_starts
+            state = states[i]
             bufs = {
                 "elbo": np.empty(r_, np.float64), "n_iterations": np.empty(r_, np.int32),
                 "n_updates": np.empty(r_, np.int32), "status": np.empty(r_, np.int32),
@@ -255,6 +279,7 @@ class CaviBatch:
         out = []
         for i, w in enumerate(self.windows):
             b = keep[i]
+            state = states[i]
             restarts = []
             for r in range(w.n_starts):
                 hl = int(b["history_len"][r])

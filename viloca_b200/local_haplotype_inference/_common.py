@@ -1,0 +1,320 @@
+"""Shared host logic of the two inference modes: window files -> compact tensors, the batched
+engine call, and the finishing steps that turn a converged state into the two FASTA files the
+rest of VILOCA parses (use_quality_scores/run_dpm_mfa.py:18-120,
+learn_error_params/run_dpm_mfa.py:33-110).
+
+Nothing here computes CAVI arithmetic on the CPU: the update equations, the ELBO and the
+finishing contraction all run in the CUDA engine (viloca_b200.engine).
+"""
+from __future__ import annotations
+
+import logging
+import os
+import pickle
+from dataclasses import dataclass, field
+from typing import Optional, Sequence
+
+import numpy as np
+
+from .. import fasta, init_state, tensors
+from .._consts import INIT_STRIDE
+
+ALPHABET = "ACGT-"
+
+
+# ---------------------------------------------------------------------------------------
+# window files -> tensors
+# ---------------------------------------------------------------------------------------
+
+@dataclass
+class PreparedWindow:
+    """The reads of one window after the reference's preparation step, in compact form."""
+    codes: np.ndarray                  # (N, L) uint8
+    weights: np.ndarray                # (N,) multiplicities (int64 for unique, float ones otherwise)
+    qualities: Optional[np.ndarray]    # (N, L) float64 (uqs) or None (lep)
+    read_ids: list                     # per row: ids of the raw reads collapsed into it, first-seen order
+    sequences: list                    # per row: the read string (keys of read_mapping)
+    n_raw: int = 0
+
+
+def read_window_fasta(path: str):
+    ids, seqs = [], []
+    for rec in fasta.parse(path):
+        ids.append(rec.id)
+        seqs.append(rec.seq)
+    return ids, seqs
+
+
+def prepare_reads(ids: Sequence[str], seqs: Sequence[str], qualities: Optional[np.ndarray],
+                  alphabet: str, unique_modus: bool) -> PreparedWindow:
+    """use_quality_scores/preparation.py:24-90 and learn_error_params/preparation.py:51-94.
+
+    unique: identical read strings collapse into the row of their first occurrence; weight =
+    multiplicity; quality = running mean (q*w + q_new)/(w + 1) in file order; afterwards
+    Q == 0 -> 2.  non-unique: one row per read, weight 1, Q == 0 -> 2.
+    The O(N^2) Hamming scan of the lep loader gives the same rows in the same order.
+    """
+    n_raw = len(seqs)
+    if n_raw == 0:
+        raise ValueError("window without reads")
+    length = len(seqs[0])
+    if unique_modus:
+        row_of = {}
+        rows, read_ids, weights = [], [], []
+        qual_rows = []
+        for i, s in enumerate(seqs):
+            r = row_of.get(s)
+            if r is None:
+                row_of[s] = len(rows)
+                rows.append(s)
+                read_ids.append([ids[i]])
+                weights.append(1)
+                if qualities is not None:
+                    qual_rows.append(qualities[i])
+            else:
+                if qualities is not None:
+                    qual_rows[r] = (qual_rows[r] * weights[r] + qualities[i]) / (weights[r] + 1)
+                weights[r] += 1
+                read_ids[r].append(ids[i])
+        w = np.asarray(weights, dtype=np.int64)
+    else:
+        rows = list(seqs)
+        read_ids = [[i] for i in ids]
+        w = np.ones(n_raw)
+        qual_rows = [qualities[i] for i in range(n_raw)] if qualities is not None else []
+    codes = np.empty((len(rows), length), dtype=np.uint8)
+    for r, s in enumerate(rows):
+        if len(s) != length:
+            raise ValueError("reads of one window must have equal length")
+        codes[r] = tensors.encode(s, alphabet)
+    q = None
+    if qualities is not None:
+        q = np.empty((len(rows), np.asarray(qualities).shape[1]), dtype=np.float64)
+        for r, row in enumerate(qual_rows):
+            q[r] = row
+        q = np.where(q == 0, 2, q)
+    return PreparedWindow(codes=codes, weights=w, qualities=q, read_ids=read_ids, sequences=rows, n_raw=n_raw)
+
+
+def load_reference(path: str, alphabet: str, upper: bool):
+    """First record of the reference FASTA -> (codes, id).  uqs upper-cases the sequence
+    (use_quality_scores/preparation.py:163-165); lep does not, so lower-case bases are outside
+    its alphabet (learn_error_params/preparation.py:97-108)."""
+    for rec in fasta.parse(path):
+        seq = rec.seq.upper() if upper else rec.seq
+        return tensors.encode(seq, alphabet), rec.id, rec.seq
+    raise ValueError(f"{path}: no sequence")
+
+
+# ---------------------------------------------------------------------------------------
+# running a batch of windows on the engine
+# ---------------------------------------------------------------------------------------
+
+@dataclass
+class WindowJob:
+    """One call of run_dpm_mfa.main, as data."""
+    mode: str
+    freads_in: str
+    fref_in: str
+    fname_qualities: Optional[str]
+    output_dir: str
+    n_starts: int
+    K: int
+    alpha0: float
+    alphabet: str = ALPHABET
+    unique_modus: bool = True
+    convergence_threshold: float = 1e-3
+    record_history: bool = False
+    seed: int = 27
+    max_iter: int = 50000
+    # filled by load()
+    prepared: Optional[PreparedWindow] = None
+    ref_codes: Optional[np.ndarray] = None
+    ref_seq: str = ""
+    window: object = None
+
+    @property
+    def output_name(self) -> str:
+        window_id = self.freads_in.split("/")[-1][:-4]      # run_dpm_mfa.py:33
+        return self.output_dir + window_id + "-"
+
+    def load(self):
+        from ..engine import Window
+        if self.alphabet != ALPHABET:
+            raise ValueError("the engine is built for the alphabet 'ACGT-' (B = 5)")
+        ids, seqs = read_window_fasta(self.freads_in)
+        quals = None
+        if self.mode == "uqs":
+            with open(self.fname_qualities, "rb") as fh:
+                quals = np.load(fh, allow_pickle=True)
+        self.prepared = prepare_reads(ids, seqs, quals, self.alphabet, self.unique_modus)
+        self.ref_codes, _, self.ref_seq = load_reference(self.fref_in, self.alphabet, upper=(self.mode == "uqs"))
+        p = self.prepared
+        n = p.codes.shape[0]
+        zs, scs = init_state.draw_restarts(self.mode, self.K, self.alpha0, n, self.n_starts, self.seed)
+        kw = {}
+        if self.mode == "uqs":
+            kw["log_hit"], kw["log_off"] = tensors.log_error_terms(p.qualities)
+        self.window = Window(mode=self.mode, codes=p.codes, weights=np.asarray(p.weights, dtype=np.float64),
+                             ref_codes=self.ref_codes, init_cluster=zs, init_scalars=scs, alpha0=self.alpha0,
+                             conv_thres=self.convergence_threshold, max_iter=self.max_iter,
+                             name=self.output_name, **kw)
+        return self
+
+
+def _result_dicts(job: WindowJob, outcome, restart: int, state: dict):
+    """(state_curr_dict, dict_result) in the shape run_cavi returns (cavi.py:171-210)."""
+    r = outcome.restarts[restart]
+    st = dict(state)
+    st["elbo"] = r.elbo
+    res = {"exit_message": r.exit_message, "n_iterations": r.n_iterations, "converged": r.converged,
+           "elbo": r.elbo, "history_elbo": list(r.history_elbo), "run_id": restart,
+           "n_reads": job.window.n_reads, "n_cluster": job.K, "alpha0": job.alpha0, "alphabet": job.alphabet}
+    res.update(st)
+    return st, res
+
+
+def group_haplotypes(mean_haplo: np.ndarray, alphabet: str = ALPHABET):
+    """get_unique_haplotypes (analyze_results.py:102-107, 144-157): per-position argmax (first
+    maximum wins), identical strings grouped, groups sorted lexicographically."""
+    idx = np.argmax(mean_haplo, axis=2)
+    table = np.array(list(alphabet))
+    groups = {}
+    for k in range(idx.shape[0]):
+        groups.setdefault("".join(table[idx[k]]), []).append(k)
+    return sorted(groups.items())
+
+
+def summarize(job: WindowJob, batch, window_index: int, restart: int, state: dict) -> dict:
+    """summarize_results (analyze_results.py:56-99): merged clusters, one more haplotype
+    update on them (on the device), posterior product, tie-aware read assignment."""
+    groups = group_haplotypes(state["mean_haplo"], job.alphabet)
+    group_of = np.empty(job.K, dtype=np.int32)
+    for j, (_, members) in enumerate(groups):
+        group_of[members] = j
+    merged_z, merged_h = batch.merge_haplo(window_index, restart, group_of, len(groups))
+    p = job.prepared
+    top = merged_z.max(axis=1, keepdims=True)
+    member = merged_z == top                       # (N, G): every cluster attaining the row maximum
+    mult = np.asarray(p.weights)
+    summary = {}
+    for j, (seq, _) in enumerate(groups):
+        base_idx = tensors.encode(seq, job.alphabet).astype(np.int64)
+        vals = merged_h[j, np.arange(len(seq)), base_idx]
+        posterior = np.cumprod(vals)[-1] if len(vals) else 1     # left-to-right product
+        rows = np.nonzero(member[:, j])[0]
+        assigned = [rid for n in rows for rid in p.read_ids[n]]
+        weight = mult[rows].sum()
+        weight = int(weight) if job.unique_modus else int(round(float(weight)))
+        summary.update({
+            "haplotype" + str(j): seq,
+            "approximatePosterior" + str(j): posterior,
+            "assignedUniqueReads" + str(j): list(assigned),
+            "assignedReads" + str(j): list(assigned),
+            "weight" + str(j): weight,
+        })
+    return summary
+
+
+def haplotypes_to_fasta(state: dict, path: str) -> None:
+    """analyze_results.py:26-53.  Haplotypes without supporting reads are skipped; if none has
+    support the file is not created (the reference only writes inside the loop)."""
+    n_hap = len([k for k in state if k.startswith("haplotype")])
+    records, wrote = [], False
+    for k in range(n_hap):
+        ave_reads = state["weight" + str(k)]
+        if ave_reads == 0:
+            continue
+        head = "hap_" + str(k) + " | posterior=" + str(state["approximatePosterior" + str(k)]) + \
+               " ave_reads=" + str(ave_reads)
+        records.append(("haplotype" + str(k), head, state["haplotype" + str(k)]))
+        wrote = True
+    if wrote:
+        fasta.write(records, path)
+
+
+def correct_reads(state: dict, path: str) -> None:
+    """analyze_results.py:9-23."""
+    n_hap = len([k for k in state if k.startswith("haplotype")])
+    if n_hap == 0:
+        return
+    records = []
+    for k in range(n_hap):
+        for read_id in state["assignedReads" + str(k)]:
+            records.append((read_id, "|posterior=1", state["haplotype" + str(k)]))
+    fasta.write(records, path)
+
+
+def _record_history_run(job: WindowJob, batch, window_index: int):
+    """record_history=True: the reference keeps alpha / mean_log_pi / mean_log_gamma /
+    mean_cluster after every even iteration (cavi.py:107-112, 146-150).  Here the batch is
+    stepped one update at a time and the state copied back each time (slow path, only on
+    request)."""
+    hist = {r: {"history_alpha": [], "history_mean_log_pi": [], "history_mean_log_gamma": [],
+                "history_mean_cluster": []} for r in range(job.n_starts)}
+    w = job.window
+    for r in range(job.n_starts):
+        sc = w.init_scalars[r]
+        hist[r]["history_alpha"].append(w.alpha0 * np.ones(w.n_clusters))
+        hist[r]["history_mean_log_gamma"].append((sc[2], sc[3]))
+        hist[r]["history_mean_cluster"].append(w.init_cluster[r].copy())
+    active = set(range(job.n_starts))
+    it = 0
+    while active and it < job.max_iter:
+        batch.step(1)
+        for r in sorted(active):
+            sel = [r if i == window_index else "none" for i in range(len(batch.windows))]
+            out = batch.fetch(state=sel, want_haplo=False)[window_index]
+            if it % 2 == 0:
+                hist[r]["history_mean_log_pi"].append(out.state["mean_log_pi"].copy())
+                hist[r]["history_mean_log_gamma"].append(out.state["mean_log_gamma"])
+                hist[r]["history_mean_cluster"].append(out.state["mean_cluster"].copy())
+            if out.restarts[r].status != 0:
+                active.discard(r)
+        it += 1
+    return hist
+
+
+def run_jobs(jobs: Sequence[WindowJob], device: int = 0) -> list:
+    """Load, run and finish a list of windows on one GPU; writes ``<output_name>support.fas``
+    and ``<output_name>cor.fas`` per window (run_dpm_mfa.py:119-120).  Returns the best
+    restart's state dict (with the summary merged in) per job."""
+    from ..engine import CaviBatch
+    for job in jobs:
+        os.makedirs(job.output_dir, exist_ok=True)
+        if job.window is None:
+            job.load()
+    finished = []
+    with CaviBatch([j.window for j in jobs], device=device) as batch:
+        batch.upload()
+        histories = {}
+        if any(j.record_history for j in jobs):
+            # slow path: single-step so that per-iteration states can be copied out
+            for i, job in enumerate(jobs):
+                if job.record_history:
+                    histories[i] = _record_history_run(job, batch, i)
+        batch.run()
+        outcomes = batch.fetch(state="best")
+        for i, (job, out) in enumerate(zip(jobs, outcomes)):
+            best = out.best_restart
+            logging.info("reference " + job.fref_in)
+            logging.info("reads " + job.freads_in)
+            logging.info("Maximal ELBO " + str(out.restarts[best].elbo) + "in run " + str(best))
+            logging.info("CAVI termination " + str(out.restarts[best].exit_message))
+            state, result = _result_dicts(job, out, best, out.state)
+            if job.record_history:
+                order = sorted(range(job.n_starts), key=lambda r: out.restarts[r].elbo, reverse=True)
+                per = []
+                for r in order:
+                    o_r = batch.fetch(state=[r if x == i else "none" for x in range(len(jobs))])[i]
+                    s_r, d_r = _result_dicts(job, o_r, r, o_r.state)
+                    d_r.update(histories.get(i, {}).get(r, {}))
+                    per.append((s_r, d_r))
+                with open(job.output_name + "all_results.pkl", "wb") as fh:
+                    pickle.dump(per, fh)
+                logging.info("Results dicts of all runs written to " + job.output_name + "all_results.pkl")
+            state.update(summarize(job, batch, i, best, state))
+            haplotypes_to_fasta(state, job.output_name + "support.fas")
+            correct_reads(state, job.output_name + "cor.fas")
+            finished.append((state, result))
+    return finished

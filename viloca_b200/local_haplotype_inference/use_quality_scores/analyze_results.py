@@ -1,0 +1,3 @@
+"""Finishing steps and writers (use_quality_scores/analyze_results.py)."""
+from .._common import correct_reads, group_haplotypes as get_unique_haplotypes, haplotypes_to_fasta  # noqa: F401
+from .._common import summarize as summarize_results  # noqa: F401

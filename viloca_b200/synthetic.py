@@ -108,7 +108,7 @@ def dedup_reads(codes_raw: np.ndarray, quals_raw: np.ndarray):
 
 
 def make_window(spec: WorkloadSpec, index: int, master_seed: int = 0, n_reads: int | None = None,
-                length: int | None = None, unique: bool = True, max_iter: int = 5000) -> Window:
+                length: int | None = None, unique: bool = True, max_iter: int = 50000) -> Window:
     """Window ``index`` of a workload: data from default_rng([master_seed, index]), initial
     states from default_rng(seed_init + s)."""
     rng = np.random.default_rng([master_seed, index])

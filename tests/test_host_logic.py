@@ -127,3 +127,18 @@ def test_group_haplotypes_sorted_and_first_max_wins():
     h[2, 0, 0] = 1.0; h[2, 1, 0] = 1.0
     groups = _common.group_haplotypes(h)
     assert groups == [("AA", [2]), ("CA", [0, 1])]
+
+
+def test_runlist_unpacking_matches_shotgun_run_dpm():
+    """The 10-tuple of shotgun.win_to_run (shotgun.py:326) -> window jobs with the file names
+    shotgun.run_dpm derives (shotgun.py:151-152)."""
+    from viloca_b200 import shotgun_hook
+    runlist = [("w-HXB2-1-201.reads.fas", 3000, 0.0001, np.array([42]), "use_quality_scores", 100, 3, True, 1e-3, False),
+               ("w-HXB2-68-268.reads.fas", 3000, 0.0001, 7, "learn_error_params", 50, 1, False, 1e-3, False)]
+    jobs = shotgun_hook.jobs_from_runlist(runlist)
+    assert jobs[0].mode == "uqs" and jobs[0].fref_in == "w-HXB2-1-201.ref.fas"
+    assert jobs[0].fname_qualities == "w-HXB2-1-201.qualities.npy" and jobs[0].seed == 42 and jobs[0].n_starts == 3
+    assert jobs[0].output_name == "./w-HXB2-1-201.reads-"
+    assert jobs[1].mode == "lep" and jobs[1].fname_qualities is None and jobs[1].K == 50 and not jobs[1].unique_modus
+    with pytest.raises(ValueError):
+        shotgun_hook.jobs_from_runlist([("x.reads.fas", 1, 0.1, 1, "shorah", 10, 1, True, 1e-3, False)])

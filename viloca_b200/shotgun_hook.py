@@ -1,0 +1,66 @@
+"""Batched replacement for ``Pool.map(run_dpm_wrapper, runlist)`` (viloca/shotgun.py:524-538).
+
+``runlist`` is what ``shotgun.win_to_run`` builds (shotgun.py:312-333): 10-tuples
+``(filein, j, a, seed, inference_type, n_max_haplotypes, n_mfa_starts, unique_modus,
+conv_thres, record_history)``.  All windows are loaded, sharded over the visible GPUs by the
+longest-first scheduler and run as one engine batch per GPU (one host thread per GPU; the C ABI
+releases the GIL).  Outputs are the per-window files the serial path writes into the CWD.
+"""
+from __future__ import annotations
+
+import logging
+import threading
+from typing import Optional, Sequence
+
+from . import scheduler
+from .local_haplotype_inference import _common
+
+MODES = {"use_quality_scores": "uqs", "learn_error_params": "lep"}
+
+
+def jobs_from_runlist(runlist) -> list:
+    jobs = []
+    for run_setting in runlist:
+        (filein, _j, a, seed, inference_type, n_max_haplotypes, n_mfa_starts, unique_modus,
+         conv_thres, record_history) = run_setting
+        if inference_type not in MODES:
+            raise ValueError(f"inference_type {inference_type!r} is not served by the CUDA engine")
+        mode = MODES[inference_type]
+        stem = filein.split(".reads.")[0]                       # shotgun.py:151-152
+        seed = int(seed[0]) if hasattr(seed, "__len__") else int(seed)   # shotgun.py:442-443 passes an array
+        jobs.append(_common.WindowJob(
+            mode=mode, freads_in=filein, fref_in=stem + ".ref.fas",
+            fname_qualities=(stem + ".qualities.npy") if mode == "uqs" else None,
+            output_dir="./", n_starts=int(n_mfa_starts), K=int(n_max_haplotypes), alpha0=float(a),
+            unique_modus=unique_modus, record_history=record_history, seed=seed,
+            convergence_threshold=conv_thres if mode == "uqs" else 1e-3))
+    return jobs
+
+
+def run_dpm_batch(runlist, devices: Optional[Sequence[int]] = None) -> None:
+    import torch
+    jobs = [j.load() for j in jobs_from_runlist(runlist)]
+    if not jobs:
+        return
+    if devices is None:
+        devices = list(range(torch.cuda.device_count()))
+    if not devices:
+        raise RuntimeError("no CUDA device: the CAVI engine has no CPU fallback")
+    parts = scheduler.lpt_partition([j.window.cost() for j in jobs], len(devices))
+    errors = []
+
+    def work(dev, idx):
+        try:
+            if idx:
+                _common.run_jobs([jobs[i] for i in idx], device=dev)
+        except Exception as exc:                                 # shotgun.py:137-143: log and re-raise
+            logging.error(f"Error in process for device {dev}: {exc}")
+            errors.append(exc)
+
+    threads = [threading.Thread(target=work, args=(dev, idx)) for dev, idx in zip(devices, parts)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    if errors:
+        raise errors[0]

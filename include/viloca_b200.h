@@ -36,7 +36,7 @@
 extern "C" {
 #endif
 
-#define VL_ABI_VERSION 1
+#define VL_ABI_VERSION 2
 #define VL_N_BASES 5          /* alphabet "ACGT-" (shotgun.py:197, run_dpm_mfa.py:26) */
 #define VL_CODE_N 255         /* read / reference character outside the alphabet      */
 #define VL_MAX_CLUSTERS 128   /* K = --n_max_haplotypes (cli.py:179-181), default 100  */
@@ -112,17 +112,32 @@ const char* vl_last_error(void);
 /* Number of CUDA devices visible, or a negative value if the runtime is unusable. */
 int vl_device_count(void);
 
-/* Device bytes a batch over these windows needs (host pointers in the descs are not read). */
+/*
+ * Device bytes a batch over these windows needs.  Of the host pointers in the descs only
+ * `codes` is read: the number of entries whose base differs from the most frequent base of
+ * their position sizes the batch's minority lists.  A later vl_batch_upload with other reads of
+ * the same shapes is accepted as long as it does not have more such entries.
+ */
 int vl_batch_workspace_bytes(const vl_window_desc* windows, int32_t n_windows, size_t* bytes_out);
 
 /*
  * Create a batch on `device` inside a caller-owned device workspace.  `stream` is a
- * cudaStream_t (NULL = the legacy default stream).  Host pointers in the descs are not read
- * here; the shapes are.
+ * cudaStream_t (NULL = the legacy default stream).  Shapes and `codes` are read here (see
+ * vl_batch_workspace_bytes); the other host pointers are not.
  */
 int vl_batch_create(vl_batch** out, int32_t device, const vl_window_desc* windows,
                     int32_t n_windows, void* dev_workspace, size_t dev_bytes, void* stream);
 void vl_batch_destroy(vl_batch* batch);
+
+/*
+ * Options, to be set before vl_batch_upload.
+ * VL_OPT_SKIP_DEAD (default 1): clusters whose responsibilities are exactly 0 for every read
+ * (exp underflow, the normal fate of most of the K clusters with alpha0 << 1) are taken out of
+ * the dense work and represented by one shared slot; the results are the ones the dense
+ * computation gives.  0 keeps all K clusters in every contraction.
+ */
+#define VL_OPT_SKIP_DEAD 1
+int vl_batch_set_option(vl_batch* batch, int32_t option, int32_t value);
 
 /* Host -> device copy of every window's inputs and initial state; resets all restarts. */
 int vl_batch_upload(vl_batch* batch, const vl_window_desc* windows, int32_t n_windows);
@@ -166,6 +181,13 @@ int vl_batch_merge_haplo(vl_batch* batch, int32_t window, int32_t restart,
  * Used by bench.py for the live roofline numbers; not a fast path.
  */
 int vl_batch_profile_step(vl_batch* batch, int32_t n_updates, double* ms_out, int64_t* n_out);
+
+/*
+ * Per (window, restart) problem, in batch order, four ints as of the last completed update:
+ * still running (0/1), 8-cluster tiles its contractions span, clusters in them (live + 1 shared
+ * slot for the dead ones), updates done.  out: [4 * n_problems].
+ */
+int vl_batch_problem_stats(vl_batch* batch, int32_t* out, int32_t n_problems);
 
 /* Milliseconds the last vl_batch_run / vl_batch_step spent on the device (CUDA events). */
 double vl_batch_last_device_ms(const vl_batch* batch);

@@ -38,10 +38,17 @@ def test_struct_layout_matches_header_constants():
     assert C.sizeof(capi.WindowResult) == 7 * 8 + 3 * 4 + 4 + 5 * 8
 
 
-def _desc(n=10, l=20, k=8, r=1, mode=0, max_iter=100):
+_KEEP = []
+
+
+def _desc(n=10, l=20, k=8, r=1, mode=0, max_iter=100, codes="zeros"):
     d = capi.WindowDesc()
     d.mode, d.n_reads, d.length, d.n_clusters, d.n_starts, d.max_iter = mode, n, l, k, r, max_iter
     d.alpha0, d.conv_thres = 1e-4, 1e-3
+    if codes is not None:
+        arr = np.zeros((max(n, 1), max(l, 1)), dtype=np.uint8) if isinstance(codes, str) else codes
+        _KEEP.append(arr)
+        d.codes = capi.u8_ptr(arr)
     return d
 
 
@@ -54,9 +61,19 @@ def test_workspace_bytes_scales_and_validates():
     assert capi.lib.vl_batch_workspace_bytes(descs, 1, C.byref(nbytes)) == 0
     big = nbytes.value
     assert big > small > 0
-    # dominant terms: two FP64 (N, L) arrays + R responsibility matrices
-    assert big > 2 * 8 * 1000 * 201 + 3 * 8 * 1000 * 100
-    for bad in (_desc(k=capi.MAX_CLUSTERS + 1), _desc(n=0), _desc(mode=7), _desc(max_iter=0)):
+    # dominant terms: one FP64 (N, L) operand + R responsibility matrices
+    assert big > 8 * 1000 * 201 + 3 * 8 * 1000 * 100
+    # the minority lists are sized from the read codes: entries off the per-position majority
+    rng = np.random.default_rng(0)
+    noisy = np.zeros((1000, 201), dtype=np.uint8)
+    flip = rng.random(noisy.shape) < 0.2
+    noisy[flip] = rng.integers(1, 5, size=int(flip.sum()))
+    descs = (capi.WindowDesc * 1)(_desc(n=1000, l=201, k=100, r=3, codes=noisy))
+    assert capi.lib.vl_batch_workspace_bytes(descs, 1, C.byref(nbytes)) == 0
+    extra = nbytes.value - big
+    nnz = int(flip.sum())
+    assert abs(extra - 24 * nnz) <= 2048      # 4 + 8 + 4 + 8 bytes per entry, 256-byte aligned arrays
+    for bad in (_desc(k=capi.MAX_CLUSTERS + 1), _desc(n=0), _desc(mode=7), _desc(max_iter=0), _desc(codes=None)):
         descs = (capi.WindowDesc * 1)(bad)
         assert capi.lib.vl_batch_workspace_bytes(descs, 1, C.byref(nbytes)) != 0
         assert len(capi.lib.vl_last_error()) > 0

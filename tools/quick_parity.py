@@ -50,6 +50,10 @@ def case(mode, n_raw, L, K, T=6):
         print("  max rel elbo-history diff:", br.rel_err(r.history_elbo[:m], np.array(traj.history_elbo[:m])))
 
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "small":
+        case("uqs", 120, 40, 10, T=3)
+        case("lep", 120, 40, 20, T=3)
+        sys.exit(0)
     case("uqs", 300, 60, 10)
     case("lep", 300, 60, 10)
     case("uqs", 600, 201, 100)

@@ -1,11 +1,11 @@
-// C ABI of the CAVI engine (include/viloca_b200.h): workspace layout, host<->device
-// transfers, the iteration driver, and result export.  No process-global state other than a
-// thread-local error string.
+// C ABI of the CAVI engine (include/viloca_b200.h): workspace layout, window analysis
+// (singled-out base per position, minority lists), host<->device transfers, the iteration
+// driver with its per-chunk kernel-class scheduling, and result export.  No process-global
+// state other than a thread-local error string.
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
-#include <map>
 #include <string>
 #include <vector>
 
@@ -34,14 +34,15 @@ inline size_t align_up(size_t x, size_t a = kAlign) { return (x + a - 1) / a * a
 inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
 
 struct RestartLayout {
-  size_t z, h, zpart, hpart, alpha, mlp, hist;
+  size_t z, h, g, gm, zpart, hpart, alpha, mlp, mlp_lay, lay, gat, lay_z, hist;
 };
 
 struct WindowLayout {
   int mode, N, L, K, R, max_iter;
   int Npad, Ls, KT, KS, K8, n_ztiles, n_htiles;
   double alpha0, conv_thres;
-  size_t codes, lt, lo, w, mcount, ref;
+  size_t nnz_cap;
+  size_t dm, w, ltsum, mcount, ref, maj, sr_ptr, sr_idx, sr_d, sp_ptr, sp_n, sp_wd;
   std::vector<RestartLayout> rs;
   int first_problem;
 };
@@ -50,19 +51,88 @@ struct Layout {
   std::vector<WindowLayout> wins;
   int n_problems = 0;
   size_t data_begin = 0, data_end = 0;   // zero-filled on upload
-  size_t probs = 0, states = 0, done = 0;
-  size_t htiles = 0, ztiles = 0;         // tile maps of all classes, back to back
-  size_t export_buf = 0;                 // max K*L*B doubles
-  size_t tmp_z = 0, tmp_h = 0, tmp_hpart = 0, tmp_group = 0, tmp_prob = 0, tmp_state = 0, tmp_tiles = 0;
+  size_t probs = 0, states = 0, done = 0, pstat = 0;
+  size_t htiles = 0, ztiles = 0, plist = 0;
+  size_t raw_codes = 0, raw_lt = 0, raw_lo = 0;      // staging of one window's raw arrays
+  size_t export_h = 0, export_z = 0;
+  size_t tmp_z = 0, tmp_h = 0, tmp_g = 0, tmp_gm = 0, tmp_hpart = 0, tmp_group = 0, tmp_prob = 0,
+         tmp_state = 0, tmp_tiles = 0, tmp_lay = 0, tmp_gat = 0, tmp_mlp = 0;
   size_t total = 0;
   size_t n_htiles_total = 0, n_ztiles_total = 0;
 };
 
-struct KernelClass {
-  int kt, mode;
-  std::vector<int2> htiles, ztiles;
-  size_t h_off = 0, z_off = 0;   // element offsets into the device tile maps
+// What the kernels need to know about the bases of one window: the base singled out per
+// position (most frequent called base, first on ties) and the entries that carry another
+// base, listed by read (ascending position) and by (position, base) (ascending read).
+struct WindowAnalysis {
+  std::vector<uint8_t> maj;
+  std::vector<int> sr_ptr, sr_idx, sp_ptr, sp_n;
+  std::vector<double> sr_d, sp_wd;
+  size_t nnz = 0;
 };
+
+void majority_bases(const vl_window_desc& d, int Ls, std::vector<uint8_t>& maj) {
+  const int N = d.n_reads, L = d.length;
+  std::vector<int> cnt((size_t)L * VL_N_BASES, 0);
+  for (int n = 0; n < N; ++n) {
+    const uint8_t* row = d.codes + (size_t)n * L;
+    for (int l = 0; l < L; ++l)
+      if (row[l] < VL_N_BASES) ++cnt[(size_t)l * VL_N_BASES + row[l]];
+  }
+  maj.assign(Ls, 0);
+  for (int l = 0; l < L; ++l) {
+    int best = 0;
+    for (int b = 1; b < VL_N_BASES; ++b)
+      if (cnt[(size_t)l * VL_N_BASES + b] > cnt[(size_t)l * VL_N_BASES + best]) best = b;
+    maj[l] = (uint8_t)best;
+  }
+}
+
+size_t count_minority(const vl_window_desc& d, const std::vector<uint8_t>& maj) {
+  const int N = d.n_reads, L = d.length;
+  size_t nnz = 0;
+  for (int n = 0; n < N; ++n) {
+    const uint8_t* row = d.codes + (size_t)n * L;
+    for (int l = 0; l < L; ++l) nnz += (row[l] < VL_N_BASES && row[l] != maj[l]);
+  }
+  return nnz;
+}
+
+void analyze_window(const vl_window_desc& d, int Npad, int Ls, WindowAnalysis& A) {
+  const int N = d.n_reads, L = d.length;
+  const bool uqs = d.mode == VL_MODE_UQS;
+  majority_bases(d, Ls, A.maj);
+  A.sr_ptr.assign((size_t)Npad + 1, 0);
+  A.sp_ptr.assign((size_t)Ls * VL_N_BASES + 1, 0);
+  A.sr_idx.clear(); A.sr_d.clear();
+  for (int n = 0; n < N; ++n) {
+    const uint8_t* row = d.codes + (size_t)n * L;
+    for (int l = 0; l < L; ++l) {
+      const uint8_t c = row[l];
+      if (c < VL_N_BASES && c != A.maj[l]) {
+        const size_t off = (size_t)n * L + l;
+        A.sr_idx.push_back(l * VL_N_BASES + c);
+        A.sr_d.push_back(uqs ? d.log_hit[off] - d.log_off[off] : 1.0);
+        ++A.sp_ptr[(size_t)l * VL_N_BASES + c + 1];
+      }
+    }
+    A.sr_ptr[n + 1] = (int)A.sr_idx.size();
+  }
+  for (int n = N; n < Npad; ++n) A.sr_ptr[n + 1] = A.sr_ptr[N];
+  A.nnz = A.sr_idx.size();
+  for (size_t i = 1; i < A.sp_ptr.size(); ++i) A.sp_ptr[i] += A.sp_ptr[i - 1];
+  A.sp_n.assign(A.nnz, 0);
+  A.sp_wd.assign(A.nnz, 0.0);
+  std::vector<int> fill(A.sp_ptr.begin(), A.sp_ptr.end() - 1);
+  for (int n = 0; n < N; ++n) {
+    const double wn = d.weights[n];
+    for (int e = A.sr_ptr[n]; e < A.sr_ptr[n + 1]; ++e) {
+      const int at = fill[A.sr_idx[e]]++;
+      A.sp_n[at] = n;
+      A.sp_wd[at] = wn * A.sr_d[e];
+    }
+  }
+}
 
 int build_layout(const vl_window_desc* w, int n, Layout& lay, std::string& err) {
   if (n <= 0 || !w) { err = "no windows"; return 1; }
@@ -71,8 +141,9 @@ int build_layout(const vl_window_desc* w, int n, Layout& lay, std::string& err) 
   lay.wins.resize(n);
   lay.n_problems = 0;
   lay.data_begin = 0;
-  size_t max_export = 0, max_z = 0, max_h = 0;
+  size_t max_nl = 0, max_exp_h = 0, max_exp_z = 0, max_z = 0, max_h = 0, max_gm = 0;
   int max_htiles = 0;
+  std::vector<uint8_t> maj;
   for (int i = 0; i < n; ++i) {
     const vl_window_desc& d = w[i];
     WindowLayout& W = lay.wins[i];
@@ -82,39 +153,57 @@ int build_layout(const vl_window_desc* w, int n, Layout& lay, std::string& err) 
       snprintf(buf, sizeof buf, "window %d: n_reads, length, n_clusters, n_starts and max_iter must be positive", i);
       err = buf; return 1;
     }
-    const int kt = vl_supported_kt(d.n_clusters);
-    if (kt < 0) { snprintf(buf, sizeof buf, "window %d: n_clusters=%d exceeds VL_MAX_CLUSTERS=%d", i, d.n_clusters, VL_MAX_CLUSTERS); err = buf; return 1; }
+    if (d.n_clusters > VL_MAX_CLUSTERS) { snprintf(buf, sizeof buf, "window %d: n_clusters=%d exceeds VL_MAX_CLUSTERS=%d", i, d.n_clusters, VL_MAX_CLUSTERS); err = buf; return 1; }
+    if (!d.codes) { snprintf(buf, sizeof buf, "window %d: codes is NULL (the read codes size the minority lists)", i); err = buf; return 1; }
     W.mode = d.mode; W.N = d.n_reads; W.L = d.length; W.K = d.n_clusters; W.R = d.n_starts;
     W.max_iter = d.max_iter; W.alpha0 = d.alpha0; W.conv_thres = d.conv_thres;
     W.Npad = round_up(W.N, VL_ZT_READS);
-    W.Ls = round_up(W.L, VL_HT_POS);
-    W.KT = kt; W.KS = vl_ks(kt); W.K8 = vl_k8(kt);
+    W.Ls = round_up(W.L, VL_PT);
+    W.KT = (W.K + 7) / 8; W.KS = vl_ks(W.KT); W.K8 = 8 * W.KT;
     W.n_ztiles = W.Npad / VL_ZT_READS;
-    W.n_htiles = W.Ls / VL_HT_POS;
+    W.n_htiles = W.Ls / VL_PT;
+    majority_bases(d, W.Ls, maj);
+    W.nnz_cap = std::max<size_t>(count_minority(d, maj), 1);
     const size_t nl = (size_t)W.Npad * W.Ls;
-    W.codes = take(nl);
-    if (W.mode == VL_MODE_UQS) { W.lt = take(nl * 8); W.lo = take(nl * 8); } else { W.lt = W.lo = 0; }
+    W.dm = take(nl * 8);
     W.w = take((size_t)W.Npad * 8);
+    W.ltsum = take((size_t)W.Npad * 8);
     W.mcount = take((size_t)W.Npad * 8);
     W.ref = take((size_t)W.Ls);
+    W.maj = take((size_t)W.Ls);
+    W.sr_ptr = take(((size_t)W.Npad + 1) * 4);
+    W.sr_idx = take(W.nnz_cap * 4);
+    W.sr_d = take(W.nnz_cap * 8);
+    W.sp_ptr = take(((size_t)W.Ls * VL_N_BASES + 1) * 4);
+    W.sp_n = take(W.nnz_cap * 4);
+    W.sp_wd = take(W.nnz_cap * 8);
     W.rs.resize(W.R);
     W.first_problem = lay.n_problems;
     for (int r = 0; r < W.R; ++r) {
       RestartLayout& RL = W.rs[r];
       RL.z = take((size_t)W.Npad * W.KS * 8);
-      RL.h = take((size_t)W.Ls * VL_B * W.KS * 8);
+      RL.h = take((size_t)W.Ls * VL_N_BASES * W.KS * 8);
+      RL.g = take((size_t)W.Ls * VL_N_BASES * W.KS * 8);
+      RL.gm = take((size_t)W.Ls * W.KS * 8);
       RL.zpart = take((size_t)W.n_ztiles * (W.K8 + VL_ZP_EXTRA) * 8);
       RL.hpart = take((size_t)W.n_htiles * VL_HP_STRIDE * 8);
       RL.alpha = take((size_t)W.K8 * 8);
       RL.mlp = take((size_t)W.K8 * 8);
+      RL.mlp_lay = take((size_t)W.K8 * 8);
+      RL.lay = take((size_t)W.K8 * 4);
+      RL.gat = take((size_t)W.K8 * 4);
+      RL.lay_z = take((size_t)W.K8 * 4);
     }
     // history_elbo of the R restarts, contiguous so that one 2-D copy fetches them
     const size_t hist0 = take((size_t)W.R * W.max_iter * 8);
     for (int r = 0; r < W.R; ++r) W.rs[r].hist = hist0 + (size_t)r * W.max_iter * 8;
     lay.n_problems += W.R;
-    max_export = std::max(max_export, (size_t)W.K * W.L * VL_B * 8);
+    max_nl = std::max(max_nl, (size_t)W.N * W.L);
+    max_exp_h = std::max(max_exp_h, (size_t)W.K * W.L * VL_N_BASES * 8);
+    max_exp_z = std::max(max_exp_z, (size_t)W.N * W.K * 8);
     max_z = std::max(max_z, (size_t)W.Npad * W.KS * 8);
-    max_h = std::max(max_h, (size_t)W.Ls * VL_B * W.KS * 8);
+    max_h = std::max(max_h, (size_t)W.Ls * VL_N_BASES * W.KS * 8);
+    max_gm = std::max(max_gm, (size_t)W.Ls * W.KS * 8);
     max_htiles = std::max(max_htiles, W.n_htiles);
     lay.n_htiles_total += (size_t)W.n_htiles * W.R;
     lay.n_ztiles_total += (size_t)W.n_ztiles * W.R;
@@ -123,16 +212,27 @@ int build_layout(const vl_window_desc* w, int n, Layout& lay, std::string& err) 
   lay.probs = take((size_t)lay.n_problems * sizeof(VlProblem));
   lay.states = take((size_t)lay.n_problems * sizeof(VlState));
   lay.done = take(64);
+  lay.pstat = take((size_t)lay.n_problems * sizeof(int4));
   lay.htiles = take(lay.n_htiles_total * sizeof(int2));
   lay.ztiles = take(lay.n_ztiles_total * sizeof(int2));
-  lay.export_buf = take(max_export);
+  lay.plist = take((size_t)lay.n_problems * sizeof(int2));
+  lay.raw_codes = take(max_nl);
+  lay.raw_lt = take(max_nl * 8);
+  lay.raw_lo = take(max_nl * 8);
+  lay.export_h = take(max_exp_h);
+  lay.export_z = take(max_exp_z);
   lay.tmp_z = take(max_z);
   lay.tmp_h = take(max_h);
+  lay.tmp_g = take(max_h);
+  lay.tmp_gm = take(max_gm);
   lay.tmp_hpart = take((size_t)max_htiles * VL_HP_STRIDE * 8);
   lay.tmp_group = take(VL_MAX_CLUSTERS * sizeof(int));
   lay.tmp_prob = take(sizeof(VlProblem));
   lay.tmp_state = take(sizeof(VlState));
   lay.tmp_tiles = take((size_t)max_htiles * sizeof(int2));
+  lay.tmp_lay = take(VL_MAX_CLUSTERS * sizeof(int));
+  lay.tmp_gat = take(VL_MAX_CLUSTERS * sizeof(int));
+  lay.tmp_mlp = take(VL_MAX_CLUSTERS * sizeof(double));
   lay.total = off;
   return 0;
 }
@@ -146,9 +246,16 @@ struct vl_batch {
   size_t ws_bytes = 0;
   Layout lay;
   std::vector<VlProblem> probs;        // host mirror of the device problem table
-  std::vector<KernelClass> classes;
-  std::vector<VlState> states;         // host mirror filled by fetch / set_state
-  int* h_done = nullptr;               // pinned
+  std::vector<int> order;              // problems, costliest window first
+  std::vector<VlState> states;         // host mirror filled by fetch / upload
+  std::vector<int4> pstat;             // host mirror: (running, tiles needed, valid slots, updates)
+  // pinned staging of the per-chunk schedule
+  int2* h_htiles = nullptr; int2* h_ztiles = nullptr; int2* h_plist = nullptr; int4* h_pstat = nullptr;
+  int n_ht[VL_N_CLASSES][2] = {}, n_zt[VL_N_CLASSES][2] = {};
+  size_t off_ht[VL_N_CLASSES][2] = {}, off_zt[VL_N_CLASSES][2] = {};
+  int n_sched = 0;
+  bool sched_dirty = true;
+  int skip_dead = 1;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   double last_ms = 0.0;
   bool uploaded = false;
@@ -157,22 +264,89 @@ struct vl_batch {
   VlProblem* d_probs() const { return dev<VlProblem>(lay.probs); }
   VlState* d_states() const { return dev<VlState>(lay.states); }
   int* d_done() const { return dev<int>(lay.done); }
+  int4* d_pstat() const { return dev<int4>(lay.pstat); }
 };
 
 namespace {
 
-int run_iterations(vl_batch* b, int n_iter, int64_t* launches) {
-  for (int it = 0; it < n_iter; ++it) {
-    for (const KernelClass& c : b->classes) {
-      VL_CUDA(vl_launch_contractions(c.kt, c.mode, b->d_probs(), b->dev<int2>(b->lay.htiles) + c.h_off,
-                                     (int)c.htiles.size(), b->dev<int2>(b->lay.ztiles) + c.z_off,
-                                     (int)c.ztiles.size(), true, true, b->stream));
-      *launches += 2;
+// Tile maps of the still-running restarts, grouped by kernel class (layout width) and mode.
+int schedule(vl_batch* b) {
+  const Layout& L = b->lay;
+  std::vector<int2> ht[VL_N_CLASSES][2], zt[VL_N_CLASSES][2];
+  b->n_sched = 0;
+  for (int p : b->order) {
+    const int4 st = b->pstat[p];
+    if (st.x == 0) continue;
+    const VlProblem& P = b->probs[p];
+    const int cls = vl_class_of_tiles(st.y), m = P.mode == VL_MODE_LEP ? 1 : 0;
+    for (int t = 0; t < P.n_htiles; ++t) ht[cls][m].push_back(make_int2(p, t));
+    for (int t = 0; t < P.n_ztiles; ++t) zt[cls][m].push_back(make_int2(p, t));
+    b->h_plist[b->n_sched++] = make_int2(p, vl_class_capacity(cls));
+  }
+  size_t ho = 0, zo = 0;
+  for (int c = 0; c < VL_N_CLASSES; ++c)
+    for (int m = 0; m < 2; ++m) {
+      b->n_ht[c][m] = (int)ht[c][m].size(); b->off_ht[c][m] = ho;
+      b->n_zt[c][m] = (int)zt[c][m].size(); b->off_zt[c][m] = zo;
+      std::copy(ht[c][m].begin(), ht[c][m].end(), b->h_htiles + ho);
+      std::copy(zt[c][m].begin(), zt[c][m].end(), b->h_ztiles + zo);
+      ho += ht[c][m].size(); zo += zt[c][m].size();
     }
-    VL_CUDA(vl_launch_scalar(b->d_probs(), b->lay.n_problems, b->d_done(), b->stream));
+  cudaStream_t s = b->stream;
+  if (ho) VL_CUDA(cudaMemcpyAsync(b->dev<int2>(L.htiles), b->h_htiles, ho * sizeof(int2), cudaMemcpyHostToDevice, s));
+  if (zo) VL_CUDA(cudaMemcpyAsync(b->dev<int2>(L.ztiles), b->h_ztiles, zo * sizeof(int2), cudaMemcpyHostToDevice, s));
+  if (b->n_sched) VL_CUDA(cudaMemcpyAsync(b->dev<int2>(L.plist), b->h_plist, (size_t)b->n_sched * sizeof(int2), cudaMemcpyHostToDevice, s));
+  b->sched_dirty = false;
+  return 0;
+}
+
+int launch_phase(vl_batch* b, int phase, int64_t* launches) {
+  const Layout& L = b->lay;
+  for (int c = 0; c < VL_N_CLASSES; ++c)
+    for (int m = 0; m < 2; ++m) {
+      const int mode = m ? VL_MODE_LEP : VL_MODE_UQS;
+      if (phase == 0 && b->n_ht[c][m] > 0) {
+        VL_CUDA(vl_launch_haplo(c, mode, b->d_probs(), b->dev<int2>(L.htiles) + b->off_ht[c][m], b->n_ht[c][m], b->stream));
+        *launches += 1;
+      }
+      if (phase == 1 && b->n_zt[c][m] > 0) {
+        VL_CUDA(vl_launch_cluster(c, mode, b->d_probs(), b->dev<int2>(L.ztiles) + b->off_zt[c][m], b->n_zt[c][m], b->stream));
+        *launches += 1;
+      }
+    }
+  if (phase == 2 && b->n_sched > 0) {
+    VL_CUDA(vl_launch_scalar(b->d_probs(), b->dev<int2>(L.plist), b->n_sched, b->d_done(), b->d_pstat(), b->stream));
     *launches += 1;
   }
   return 0;
+}
+
+int run_iterations(vl_batch* b, int n_iter, int64_t* launches) {
+  for (int it = 0; it < n_iter; ++it)
+    for (int phase = 0; phase < 3; ++phase)
+      if (launch_phase(b, phase, launches)) return 1;
+  return 0;
+}
+
+// Read the per-restart status back and note whether the schedule has to be rebuilt.
+int sync_status(vl_batch* b, int* n_running) {
+  const int np = b->lay.n_problems;
+  VL_CUDA(cudaMemcpyAsync(b->h_pstat, b->d_pstat(), (size_t)np * sizeof(int4), cudaMemcpyDeviceToHost, b->stream));
+  VL_CUDA(cudaStreamSynchronize(b->stream));
+  int running = 0;
+  for (int p = 0; p < np; ++p) {
+    const int4 now = b->h_pstat[p], old = b->pstat[p];
+    if (now.x != old.x || vl_class_of_tiles(now.y) != vl_class_of_tiles(old.y)) b->sched_dirty = true;
+    b->pstat[p] = now;
+    running += now.x;
+  }
+  if (n_running) *n_running = running;
+  return 0;
+}
+
+void identity_layout(int K, int K8, std::vector<int>& lay, std::vector<int>& gat) {
+  lay.assign(K8, -1); gat.assign(K8, 0);
+  for (int k = 0; k < K; ++k) { lay[k] = k; gat[k] = k; }
 }
 
 }  // namespace
@@ -222,15 +396,14 @@ int vl_batch_create(vl_batch** out, int32_t device, const vl_window_desc* window
   cudaError_t e = cudaSetDevice(device);
   if (e != cudaSuccess) { delete b; return fail(std::string("cudaSetDevice: ") + cudaGetErrorString(e)); }
 
-  // problem table + tile maps, grouped by kernel class (cluster-tile count, mode); within a
-  // class the costliest windows come first so that the long CTAs start early
   const Layout& L = b->lay;
   b->probs.resize(L.n_problems);
   b->states.resize(L.n_problems);
-  std::map<std::pair<int, int>, int> class_of;
-  std::vector<int> order(L.wins.size());
-  for (size_t i = 0; i < order.size(); ++i) order[i] = (int)i;
-  std::stable_sort(order.begin(), order.end(), [&](int x, int y) {
+  b->pstat.assign(L.n_problems, make_int4(0, 0, 0, 0));
+  // within a kernel class the costliest windows come first so that the long CTAs start early
+  std::vector<int> worder(L.wins.size());
+  for (size_t i = 0; i < worder.size(); ++i) worder[i] = (int)i;
+  std::stable_sort(worder.begin(), worder.end(), [&](int x, int y) {
     const WindowLayout& A = L.wins[x]; const WindowLayout& B = L.wins[y];
     return (double)A.Npad * A.Ls > (double)B.Npad * B.Ls;
   });
@@ -239,35 +412,29 @@ int vl_batch_create(vl_batch** out, int32_t device, const vl_window_desc* window
     for (int r = 0; r < W.R; ++r) {
       VlProblem& P = b->probs[W.first_problem + r];
       P.mode = W.mode; P.N = W.N; P.L = W.L; P.K = W.K;
-      P.Npad = W.Npad; P.Ls = W.Ls; P.KS = W.KS; P.KT = W.KT;
+      P.Npad = W.Npad; P.Ls = W.Ls; P.KT = W.KT; P.pad0 = 0;
       P.n_ztiles = W.n_ztiles; P.n_htiles = W.n_htiles; P.window = (int)i; P.restart = r;
-      P.codes = b->dev<uint8_t>(W.codes);
-      P.lt = (W.mode == VL_MODE_UQS) ? b->dev<double>(W.lt) : nullptr;
-      P.lo = (W.mode == VL_MODE_UQS) ? b->dev<double>(W.lo) : nullptr;
+      P.dm = b->dev<double>(W.dm);
       P.w = b->dev<double>(W.w);
+      P.ltsum = b->dev<double>(W.ltsum);
       P.mcount = b->dev<double>(W.mcount);
       P.ref = b->dev<uint8_t>(W.ref);
+      P.maj = b->dev<uint8_t>(W.maj);
+      P.sr_ptr = b->dev<int>(W.sr_ptr); P.sr_idx = b->dev<int>(W.sr_idx); P.sr_d = b->dev<double>(W.sr_d);
+      P.sp_ptr = b->dev<int>(W.sp_ptr); P.sp_nc = b->dev<int>(W.sp_n); P.sp_wd = b->dev<double>(W.sp_wd);
       const RestartLayout& RL = W.rs[r];
       P.z = b->dev<double>(RL.z); P.h = b->dev<double>(RL.h);
+      P.g = b->dev<double>(RL.g); P.gm = b->dev<double>(RL.gm);
       P.zpart = b->dev<double>(RL.zpart); P.hpart = b->dev<double>(RL.hpart);
       P.alpha = b->dev<double>(RL.alpha); P.mlp = b->dev<double>(RL.mlp);
+      P.mlp_lay = b->dev<double>(RL.mlp_lay);
+      P.lay = b->dev<int>(RL.lay); P.gat = b->dev<int>(RL.gat); P.lay_z = b->dev<int>(RL.lay_z);
       P.hist = b->dev<double>(RL.hist);
       P.st = b->d_states() + (W.first_problem + r);
     }
   }
-  for (int wi : order) {
-    const WindowLayout& W = L.wins[wi];
-    auto key = std::make_pair(W.KT, W.mode);
-    if (!class_of.count(key)) { class_of[key] = (int)b->classes.size(); b->classes.push_back(KernelClass{W.KT, W.mode}); }
-    KernelClass& C = b->classes[class_of[key]];
-    for (int r = 0; r < W.R; ++r) {
-      const int p = W.first_problem + r;
-      for (int t = 0; t < W.n_htiles; ++t) C.htiles.push_back(make_int2(p, t));
-      for (int t = 0; t < W.n_ztiles; ++t) C.ztiles.push_back(make_int2(p, t));
-    }
-  }
-  size_t ho = 0, zo = 0;
-  for (KernelClass& C : b->classes) { C.h_off = ho; C.z_off = zo; ho += C.htiles.size(); zo += C.ztiles.size(); }
+  for (int wi : worder)
+    for (int r = 0; r < L.wins[wi].R; ++r) b->order.push_back(L.wins[wi].first_problem + r);
 
 #define VL_CREATE_CUDA(expr)                                                                    \
   do {                                                                                          \
@@ -278,17 +445,14 @@ int vl_batch_create(vl_batch** out, int32_t device, const vl_window_desc* window
       return fail(m_);                                                                          \
     }                                                                                           \
   } while (0)
-  VL_CREATE_CUDA(cudaMallocHost(reinterpret_cast<void**>(&b->h_done), 64));
+  VL_CREATE_CUDA(cudaMallocHost(reinterpret_cast<void**>(&b->h_htiles), std::max<size_t>(L.n_htiles_total, 1) * sizeof(int2)));
+  VL_CREATE_CUDA(cudaMallocHost(reinterpret_cast<void**>(&b->h_ztiles), std::max<size_t>(L.n_ztiles_total, 1) * sizeof(int2)));
+  VL_CREATE_CUDA(cudaMallocHost(reinterpret_cast<void**>(&b->h_plist), (size_t)L.n_problems * sizeof(int2)));
+  VL_CREATE_CUDA(cudaMallocHost(reinterpret_cast<void**>(&b->h_pstat), (size_t)L.n_problems * sizeof(int4)));
   VL_CREATE_CUDA(cudaEventCreate(&b->ev0));
   VL_CREATE_CUDA(cudaEventCreate(&b->ev1));
   VL_CREATE_CUDA(cudaMemcpyAsync(b->d_probs(), b->probs.data(), b->probs.size() * sizeof(VlProblem),
                                  cudaMemcpyHostToDevice, b->stream));
-  for (const KernelClass& C : b->classes) {
-    VL_CREATE_CUDA(cudaMemcpyAsync(b->dev<int2>(L.htiles) + C.h_off, C.htiles.data(), C.htiles.size() * sizeof(int2),
-                                   cudaMemcpyHostToDevice, b->stream));
-    VL_CREATE_CUDA(cudaMemcpyAsync(b->dev<int2>(L.ztiles) + C.z_off, C.ztiles.data(), C.ztiles.size() * sizeof(int2),
-                                   cudaMemcpyHostToDevice, b->stream));
-  }
   VL_CREATE_CUDA(cudaStreamSynchronize(b->stream));
 #undef VL_CREATE_CUDA
   *out = b;
@@ -298,10 +462,19 @@ int vl_batch_create(vl_batch** out, int32_t device, const vl_window_desc* window
 void vl_batch_destroy(vl_batch* b) {
   if (!b) return;
   cudaSetDevice(b->device);
-  if (b->h_done) cudaFreeHost(b->h_done);
+  if (b->h_htiles) cudaFreeHost(b->h_htiles);
+  if (b->h_ztiles) cudaFreeHost(b->h_ztiles);
+  if (b->h_plist) cudaFreeHost(b->h_plist);
+  if (b->h_pstat) cudaFreeHost(b->h_pstat);
   if (b->ev0) cudaEventDestroy(b->ev0);
   if (b->ev1) cudaEventDestroy(b->ev1);
   delete b;
+}
+
+int vl_batch_set_option(vl_batch* b, int32_t option, int32_t value) {
+  if (!b) return fail("batch is NULL");
+  if (option == VL_OPT_SKIP_DEAD) { b->skip_dead = value ? 1 : 0; return 0; }
+  return fail("unknown option");
 }
 
 int vl_batch_upload(vl_batch* b, const vl_window_desc* windows, int32_t n_windows) {
@@ -311,6 +484,8 @@ int vl_batch_upload(vl_batch* b, const vl_window_desc* windows, int32_t n_window
   VL_CUDA(cudaSetDevice(b->device));
   cudaStream_t s = b->stream;
   VL_CUDA(cudaMemsetAsync(b->ws + L.data_begin, 0, L.data_end - L.data_begin, s));
+  WindowAnalysis A;
+  std::vector<uint8_t> ref;
   for (int i = 0; i < n_windows; ++i) {
     const vl_window_desc& d = windows[i];
     const WindowLayout& W = L.wins[i];
@@ -318,18 +493,39 @@ int vl_batch_upload(vl_batch* b, const vl_window_desc* windows, int32_t n_window
       return fail("window shape differs from the one the batch was created with");
     if (!d.codes || !d.weights || !d.ref_codes || !d.init_cluster || !d.init_scalars)
       return fail("window input pointer is NULL");
-    if (W.mode == VL_MODE_UQS && (!d.log_hit || !d.log_off)) return fail("uqs window without log_hit/log_off");
-    // padding of codes must read as 'N': fill, then copy the real rows over it
-    VL_CUDA(cudaMemsetAsync(b->ws + W.codes, VL_CODE_N, (size_t)W.Npad * W.Ls, s));
-    VL_CUDA(cudaMemsetAsync(b->ws + W.ref, VL_CODE_N, (size_t)W.Ls, s));
-    VL_CUDA(cudaMemcpy2DAsync(b->ws + W.codes, W.Ls, d.codes, W.L, W.L, W.N, cudaMemcpyHostToDevice, s));
-    if (W.mode == VL_MODE_UQS) {
-      VL_CUDA(cudaMemcpy2DAsync(b->ws + W.lt, (size_t)W.Ls * 8, d.log_hit, (size_t)W.L * 8, (size_t)W.L * 8, W.N, cudaMemcpyHostToDevice, s));
-      VL_CUDA(cudaMemcpy2DAsync(b->ws + W.lo, (size_t)W.Ls * 8, d.log_off, (size_t)W.L * 8, (size_t)W.L * 8, W.N, cudaMemcpyHostToDevice, s));
+    const bool uqs = W.mode == VL_MODE_UQS;
+    if (uqs && (!d.log_hit || !d.log_off)) return fail("uqs window without log_hit/log_off");
+    analyze_window(d, W.Npad, W.Ls, A);
+    if (A.nnz > W.nnz_cap) {
+      char buf[200];
+      snprintf(buf, sizeof buf, "window %d: %zu minority entries but the batch was created for %zu; create a new batch for these reads",
+               i, A.nnz, W.nnz_cap);
+      return fail(buf);
     }
+    const size_t nl = (size_t)W.N * W.L;
+    // the staging area is reused window after window; stream order keeps that safe, but the
+    // host vectors of the analysis are reused too, hence the synchronize at the end of the body
+    VL_CUDA(cudaMemcpyAsync(b->ws + L.raw_codes, d.codes, nl, cudaMemcpyHostToDevice, s));
+    if (uqs) {
+      VL_CUDA(cudaMemcpyAsync(b->ws + L.raw_lt, d.log_hit, nl * 8, cudaMemcpyHostToDevice, s));
+      VL_CUDA(cudaMemcpyAsync(b->ws + L.raw_lo, d.log_off, nl * 8, cudaMemcpyHostToDevice, s));
+    }
+    ref.assign(W.Ls, VL_CODE_N);
+    std::memcpy(ref.data(), d.ref_codes, W.L);
+    VL_CUDA(cudaMemcpyAsync(b->ws + W.ref, ref.data(), W.Ls, cudaMemcpyHostToDevice, s));
+    VL_CUDA(cudaMemcpyAsync(b->ws + W.maj, A.maj.data(), W.Ls, cudaMemcpyHostToDevice, s));
     VL_CUDA(cudaMemcpyAsync(b->ws + W.w, d.weights, (size_t)W.N * 8, cudaMemcpyHostToDevice, s));
-    VL_CUDA(cudaMemcpyAsync(b->ws + W.ref, d.ref_codes, (size_t)W.L, cudaMemcpyHostToDevice, s));
-    VL_CUDA(vl_launch_mcount(b->dev<uint8_t>(W.codes), b->dev<double>(W.mcount), W.Npad, W.Ls, s));
+    VL_CUDA(cudaMemcpyAsync(b->ws + W.sr_ptr, A.sr_ptr.data(), A.sr_ptr.size() * 4, cudaMemcpyHostToDevice, s));
+    VL_CUDA(cudaMemcpyAsync(b->ws + W.sp_ptr, A.sp_ptr.data(), A.sp_ptr.size() * 4, cudaMemcpyHostToDevice, s));
+    if (A.nnz) {
+      VL_CUDA(cudaMemcpyAsync(b->ws + W.sr_idx, A.sr_idx.data(), A.nnz * 4, cudaMemcpyHostToDevice, s));
+      VL_CUDA(cudaMemcpyAsync(b->ws + W.sr_d, A.sr_d.data(), A.nnz * 8, cudaMemcpyHostToDevice, s));
+      VL_CUDA(cudaMemcpyAsync(b->ws + W.sp_n, A.sp_n.data(), A.nnz * 4, cudaMemcpyHostToDevice, s));
+      VL_CUDA(cudaMemcpyAsync(b->ws + W.sp_wd, A.sp_wd.data(), A.nnz * 8, cudaMemcpyHostToDevice, s));
+    }
+    VL_CUDA(vl_launch_prepare(b->dev<uint8_t>(L.raw_codes), b->dev<double>(L.raw_lt), b->dev<double>(L.raw_lo),
+                              b->dev<uint8_t>(W.maj), b->dev<double>(W.dm), b->dev<double>(W.mcount),
+                              b->dev<double>(W.ltsum), W.N, W.L, W.Npad, W.Ls, W.mode, s));
     for (int r = 0; r < W.R; ++r) {
       VL_CUDA(cudaMemcpy2DAsync(b->ws + W.rs[r].z, (size_t)W.KS * 8, d.init_cluster + (size_t)r * W.N * W.K,
                                 (size_t)W.K * 8, (size_t)W.K * 8, W.N, cudaMemcpyHostToDevice, s));
@@ -340,12 +536,15 @@ int vl_batch_upload(vl_batch* b, const vl_window_desc* windows, int32_t n_window
       S.a0 = in[0]; S.b0 = in[1]; S.mlg0 = in[2]; S.mlg1 = in[3];
       S.c0 = in[4]; S.d0 = in[5]; S.mlt0 = in[6]; S.mlt1 = in[7];
       S.max_iter = W.max_iter;
+      S.skip = b->skip_dead;
     }
+    VL_CUDA(cudaStreamSynchronize(s));
   }
   VL_CUDA(cudaMemcpyAsync(b->d_states(), b->states.data(), b->states.size() * sizeof(VlState), cudaMemcpyHostToDevice, s));
   VL_CUDA(cudaMemsetAsync(b->d_done(), 0, 64, s));
-  VL_CUDA(vl_launch_init(b->d_probs(), L.n_problems, s));
-  VL_CUDA(cudaStreamSynchronize(s));
+  VL_CUDA(vl_launch_init(b->d_probs(), L.n_problems, b->d_pstat(), s));
+  if (sync_status(b, nullptr)) return 1;
+  b->sched_dirty = true;
   b->uploaded = true;
   return 0;
 }
@@ -355,15 +554,18 @@ int vl_batch_run(vl_batch* b, int64_t* n_launches_out) {
   if (!b->uploaded) return fail("vl_batch_run before vl_batch_upload");
   VL_CUDA(cudaSetDevice(b->device));
   int64_t launches = 0;
-  const int chunk = 8;
   int max_iter = 0;
   for (const WindowLayout& W : b->lay.wins) max_iter = std::max(max_iter, W.max_iter);
   VL_CUDA(cudaEventRecord(b->ev0, b->stream));
-  for (int done_iters = 0; done_iters < max_iter + chunk; done_iters += chunk) {
+  int running = 1, n_chunks = 0;
+  for (int64_t done_iters = 0; running > 0 && done_iters < (int64_t)max_iter + 64; ++n_chunks) {
+    // the layouts shrink fastest in the first iterations: short chunks there keep the restarts
+    // in the narrowest kernel class that fits them
+    const int chunk = n_chunks < 6 ? 4 : 32;
+    if (b->sched_dirty && schedule(b)) return 1;
     if (run_iterations(b, chunk, &launches)) return 1;
-    VL_CUDA(cudaMemcpyAsync(b->h_done, b->d_done(), sizeof(int), cudaMemcpyDeviceToHost, b->stream));
-    VL_CUDA(cudaStreamSynchronize(b->stream));
-    if (*b->h_done >= b->lay.n_problems) break;
+    if (sync_status(b, &running)) return 1;
+    done_iters += chunk;
   }
   VL_CUDA(cudaEventRecord(b->ev1, b->stream));
   VL_CUDA(cudaEventSynchronize(b->ev1));
@@ -381,7 +583,12 @@ int vl_batch_step(vl_batch* b, int32_t n_updates, int64_t* n_launches_out) {
   VL_CUDA(cudaSetDevice(b->device));
   int64_t launches = 0;
   VL_CUDA(cudaEventRecord(b->ev0, b->stream));
-  if (run_iterations(b, n_updates, &launches)) return 1;
+  // one update per schedule: a layout may move to another kernel class at any update
+  for (int it = 0; it < n_updates; ++it) {
+    if (b->sched_dirty && schedule(b)) return 1;
+    if (run_iterations(b, 1, &launches)) return 1;
+    if (sync_status(b, nullptr)) return 1;
+  }
   VL_CUDA(cudaEventRecord(b->ev1, b->stream));
   VL_CUDA(cudaEventSynchronize(b->ev1));
   float ms = 0.f;
@@ -397,33 +604,34 @@ int vl_batch_profile_step(vl_batch* b, int32_t n_updates, double* ms_out, int64_
   if (!ms_out || !n_out || n_updates < 0) return fail("bad argument");
   VL_CUDA(cudaSetDevice(b->device));
   for (int i = 0; i < 3; ++i) { ms_out[i] = 0.0; n_out[i] = 0; }
-  cudaEvent_t ev[4];
+  cudaEvent_t ev[2];
   for (auto& e : ev) VL_CUDA(cudaEventCreate(&e));
-  const Layout& L = b->lay;
   for (int it = 0; it < n_updates; ++it) {
-    for (const KernelClass& c : b->classes) {
+    if (b->sched_dirty && schedule(b)) return 1;
+    VL_CUDA(cudaStreamSynchronize(b->stream));
+    for (int phase = 0; phase < 3; ++phase) {
+      int64_t n = 0;
       VL_CUDA(cudaEventRecord(ev[0], b->stream));
-      VL_CUDA(vl_launch_contractions(c.kt, c.mode, b->d_probs(), b->dev<int2>(L.htiles) + c.h_off, (int)c.htiles.size(),
-                                     nullptr, 0, true, false, b->stream));
+      if (launch_phase(b, phase, &n)) return 1;
       VL_CUDA(cudaEventRecord(ev[1], b->stream));
-      VL_CUDA(vl_launch_contractions(c.kt, c.mode, b->d_probs(), nullptr, 0, b->dev<int2>(L.ztiles) + c.z_off,
-                                     (int)c.ztiles.size(), false, true, b->stream));
-      VL_CUDA(cudaEventRecord(ev[2], b->stream));
-      VL_CUDA(cudaEventSynchronize(ev[2]));
-      float m0 = 0.f, m1 = 0.f;
-      VL_CUDA(cudaEventElapsedTime(&m0, ev[0], ev[1]));
-      VL_CUDA(cudaEventElapsedTime(&m1, ev[1], ev[2]));
-      ms_out[0] += m0; ms_out[1] += m1; n_out[0] += 1; n_out[1] += 1;
+      VL_CUDA(cudaEventSynchronize(ev[1]));
+      float m = 0.f;
+      VL_CUDA(cudaEventElapsedTime(&m, ev[0], ev[1]));
+      ms_out[phase] += m; n_out[phase] += n;
     }
-    VL_CUDA(cudaEventRecord(ev[2], b->stream));
-    VL_CUDA(vl_launch_scalar(b->d_probs(), L.n_problems, b->d_done(), b->stream));
-    VL_CUDA(cudaEventRecord(ev[3], b->stream));
-    VL_CUDA(cudaEventSynchronize(ev[3]));
-    float m2 = 0.f;
-    VL_CUDA(cudaEventElapsedTime(&m2, ev[2], ev[3]));
-    ms_out[2] += m2; n_out[2] += 1;
+    if (sync_status(b, nullptr)) return 1;
   }
   for (auto& e : ev) cudaEventDestroy(e);
+  return 0;
+}
+
+int vl_batch_problem_stats(vl_batch* b, int32_t* out, int32_t n_problems) {
+  if (!b || !out) return fail("NULL argument");
+  if (n_problems != b->lay.n_problems) return fail("n_problems differs from the batch");
+  for (int p = 0; p < n_problems; ++p) {
+    const int4 st = b->pstat[p];
+    out[4 * p + 0] = st.x; out[4 * p + 1] = st.y; out[4 * p + 2] = st.z; out[4 * p + 3] = st.w;
+  }
   return 0;
 }
 
@@ -473,18 +681,26 @@ int vl_batch_fetch(vl_batch* b, vl_window_result* results, int32_t n_windows) {
     const int sr = (R.state_restart < 0) ? best : R.state_restart;
     if (sr >= W.R) return fail("state_restart out of range");
     const RestartLayout& RL = W.rs[sr];
-    const VlState& S = b->states[W.first_problem + sr];
+    const int p = W.first_problem + sr;
+    const VlState& S = b->states[p];
+    bool used_export = false;
     if (R.mean_haplo) {
-      VL_CUDA(vl_launch_export_haplo(b->dev<double>(RL.h), b->dev<double>(L.export_buf), W.K, W.L, W.KS, s));
-      VL_CUDA(cudaMemcpyAsync(R.mean_haplo, b->ws + L.export_buf, (size_t)W.K * W.L * VL_B * 8, cudaMemcpyDeviceToHost, s));
-      // export_buf is reused by the next window
-      VL_CUDA(cudaStreamSynchronize(s));
+      const size_t total = (size_t)W.K * W.L * VL_N_BASES;
+      VL_CUDA(vl_launch_export_haplo(b->d_probs() + p, b->dev<double>(L.export_h), total, s));
+      VL_CUDA(cudaMemcpyAsync(R.mean_haplo, b->ws + L.export_h, total * 8, cudaMemcpyDeviceToHost, s));
+      used_export = true;
     }
-    if (R.mean_cluster)
-      VL_CUDA(cudaMemcpy2DAsync(R.mean_cluster, (size_t)W.K * 8, b->ws + RL.z, (size_t)W.KS * 8, (size_t)W.K * 8, W.N, cudaMemcpyDeviceToHost, s));
+    if (R.mean_cluster) {
+      const size_t total = (size_t)W.N * W.K;
+      VL_CUDA(vl_launch_export_cluster(b->d_probs() + p, b->dev<double>(L.export_z), total, s));
+      VL_CUDA(cudaMemcpyAsync(R.mean_cluster, b->ws + L.export_z, total * 8, cudaMemcpyDeviceToHost, s));
+      used_export = true;
+    }
     if (R.alpha) VL_CUDA(cudaMemcpyAsync(R.alpha, b->ws + RL.alpha, (size_t)W.K * 8, cudaMemcpyDeviceToHost, s));
     if (R.mean_log_pi) VL_CUDA(cudaMemcpyAsync(R.mean_log_pi, b->ws + RL.mlp, (size_t)W.K * 8, cudaMemcpyDeviceToHost, s));
     if (R.scalars) fill_scalars(S, R.scalars);
+    // the export buffers are reused by the next window
+    if (used_export) VL_CUDA(cudaStreamSynchronize(s));
   }
   VL_CUDA(cudaStreamSynchronize(s));
   return 0;
@@ -503,25 +719,34 @@ int vl_batch_set_state(vl_batch* b, int32_t window, int32_t restart, const doubl
   cudaStream_t s = b->stream;
   const RestartLayout& RL = W.rs[restart];
   const int p = W.first_problem + restart;
+  // the state arrives in cluster order: back to the identity layout
+  std::vector<int> lay, gat;
+  identity_layout(W.K, W.K8, lay, gat);
+  std::vector<double> lp(W.K8, 0.0);
+  std::memcpy(lp.data(), mean_log_pi, (size_t)W.K * 8);
+  VL_CUDA(cudaMemsetAsync(b->ws + RL.z, 0, (size_t)W.Npad * W.KS * 8, s));
   VL_CUDA(cudaMemcpy2DAsync(b->ws + RL.z, (size_t)W.KS * 8, mean_cluster, (size_t)W.K * 8, (size_t)W.K * 8, W.N, cudaMemcpyHostToDevice, s));
-  VL_CUDA(cudaMemcpyAsync(b->ws + RL.mlp, mean_log_pi, (size_t)W.K * 8, cudaMemcpyHostToDevice, s));
+  VL_CUDA(cudaMemcpyAsync(b->ws + RL.mlp, lp.data(), (size_t)W.K8 * 8, cudaMemcpyHostToDevice, s));
+  VL_CUDA(cudaMemcpyAsync(b->ws + RL.mlp_lay, lp.data(), (size_t)W.K8 * 8, cudaMemcpyHostToDevice, s));
+  VL_CUDA(cudaMemcpyAsync(b->ws + RL.lay, lay.data(), (size_t)W.K8 * 4, cudaMemcpyHostToDevice, s));
+  VL_CUDA(cudaMemcpyAsync(b->ws + RL.lay_z, lay.data(), (size_t)W.K8 * 4, cudaMemcpyHostToDevice, s));
+  VL_CUDA(cudaMemcpyAsync(b->ws + RL.gat, gat.data(), (size_t)W.K8 * 4, cudaMemcpyHostToDevice, s));
   VlState S;
   VL_CUDA(cudaMemcpyAsync(&S, b->d_states() + p, sizeof S, cudaMemcpyDeviceToHost, s));
   VL_CUDA(cudaStreamSynchronize(s));
-  if (S.active == 0 && S.status != VL_STATUS_RUNNING) {
-    // revive a finished restart; the done counter must stay consistent
-    VL_CUDA(cudaMemcpyAsync(b->h_done, b->d_done(), sizeof(int), cudaMemcpyDeviceToHost, s));
-    VL_CUDA(cudaStreamSynchronize(s));
-    *b->h_done -= 1;
-    VL_CUDA(cudaMemcpyAsync(b->d_done(), b->h_done, sizeof(int), cudaMemcpyHostToDevice, s));
-  }
   S.mlg0 = scalars[VL_S_MLG0]; S.mlg1 = scalars[VL_S_MLG1];
   S.mlt0 = scalars[VL_S_MLT0]; S.mlt1 = scalars[VL_S_MLT1];
   S.dsum_alpha = scalars[VL_S_DSUM_ALPHA]; S.dsum_ab = scalars[VL_S_DSUM_AB]; S.dsum_cd = scalars[VL_S_DSUM_CD];
   S.iter = iter; S.converged = 0; S.status = VL_STATUS_RUNNING; S.active = 1;
   S.n_hist = 0; S.n_updates = 0; S.h_last = 0.0; S.h_prev = 0.0;
+  S.ktl = W.KT; S.ktl_z = W.KT; S.nlay = W.K; S.ghost = -1; S.nlay_z = W.K; S.ghost_z = -1;
+  S.ghost_mult = 0.0; S.stalled = 0; S.skip = b->skip_dead;
   VL_CUDA(cudaMemcpyAsync(b->d_states() + p, &S, sizeof S, cudaMemcpyHostToDevice, s));
+  const int4 st = make_int4(1, W.KT, W.K, 0);
+  VL_CUDA(cudaMemcpyAsync(b->d_pstat() + p, &st, sizeof st, cudaMemcpyHostToDevice, s));
   VL_CUDA(cudaStreamSynchronize(s));
+  b->pstat[p] = st;
+  b->sched_dirty = true;
   return 0;
 }
 
@@ -539,33 +764,44 @@ int vl_batch_merge_haplo(vl_batch* b, int32_t window, int32_t restart, const int
   VL_CUDA(cudaSetDevice(b->device));
   cudaStream_t s = b->stream;
   const int p = W.first_problem + restart;
+  const int G = n_groups, KTg = (G + 7) / 8, KSg = vl_ks(KTg);
   VL_CUDA(cudaMemcpyAsync(b->ws + L.tmp_group, group_of, (size_t)W.K * sizeof(int), cudaMemcpyHostToDevice, s));
-  VL_CUDA(vl_launch_merge(b->probs[p].z, b->dev<double>(L.tmp_z), b->dev<int>(L.tmp_group), W.Npad, W.K, n_groups, W.KS, s));
-  // a one-problem batch: same window tensors, merged responsibilities, scratch outputs
+  VL_CUDA(vl_launch_merge(b->d_probs() + p, b->dev<double>(L.tmp_z), b->dev<int>(L.tmp_group), G, KSg,
+                          (size_t)W.Npad * KSg, s));
+  // a one-problem batch: same window tensors, merged responsibilities in an identity layout
+  // over the G groups, scratch outputs
   VlProblem T = b->probs[p];
-  T.K = n_groups;
+  T.K = G; T.KT = KTg;
   T.z = b->dev<double>(L.tmp_z);
-  T.h = b->dev<double>(L.tmp_h);
+  T.h = b->dev<double>(L.tmp_h); T.g = b->dev<double>(L.tmp_g); T.gm = b->dev<double>(L.tmp_gm);
   T.hpart = b->dev<double>(L.tmp_hpart);
+  T.lay = b->dev<int>(L.tmp_lay); T.lay_z = b->dev<int>(L.tmp_lay); T.gat = b->dev<int>(L.tmp_gat);
+  T.mlp_lay = b->dev<double>(L.tmp_mlp);
   T.st = b->dev<VlState>(L.tmp_state);
   VlState S;
   VL_CUDA(cudaMemcpyAsync(&S, b->d_states() + p, sizeof S, cudaMemcpyDeviceToHost, s));
   VL_CUDA(cudaStreamSynchronize(s));
   S.active = 1;
+  S.ktl = KTg; S.ktl_z = KTg; S.nlay = G; S.ghost = -1; S.nlay_z = G; S.ghost_z = -1; S.ghost_mult = 0.0;
+  std::vector<int> lay, gat;
+  identity_layout(G, 8 * KTg, lay, gat);
   std::vector<int2> tiles(W.n_htiles);
   for (int t = 0; t < W.n_htiles; ++t) tiles[t] = make_int2(0, t);
+  VL_CUDA(cudaMemcpyAsync(b->ws + L.tmp_lay, lay.data(), lay.size() * 4, cudaMemcpyHostToDevice, s));
+  VL_CUDA(cudaMemcpyAsync(b->ws + L.tmp_gat, gat.data(), gat.size() * 4, cudaMemcpyHostToDevice, s));
   VL_CUDA(cudaMemcpyAsync(b->ws + L.tmp_state, &S, sizeof S, cudaMemcpyHostToDevice, s));
   VL_CUDA(cudaMemcpyAsync(b->ws + L.tmp_prob, &T, sizeof T, cudaMemcpyHostToDevice, s));
   VL_CUDA(cudaMemcpyAsync(b->ws + L.tmp_tiles, tiles.data(), tiles.size() * sizeof(int2), cudaMemcpyHostToDevice, s));
-  VL_CUDA(vl_launch_contractions(W.KT, W.mode, b->dev<VlProblem>(L.tmp_prob), b->dev<int2>(L.tmp_tiles), W.n_htiles,
-                                 nullptr, 0, true, false, s));
+  VL_CUDA(vl_launch_haplo(vl_class_of_tiles(KTg), W.mode, b->dev<VlProblem>(L.tmp_prob), b->dev<int2>(L.tmp_tiles),
+                          W.n_htiles, s));
   if (merged_haplo_out) {
-    VL_CUDA(vl_launch_export_haplo(b->dev<double>(L.tmp_h), b->dev<double>(L.export_buf), n_groups, W.L, W.KS, s));
-    VL_CUDA(cudaMemcpyAsync(merged_haplo_out, b->ws + L.export_buf, (size_t)n_groups * W.L * VL_B * 8, cudaMemcpyDeviceToHost, s));
+    const size_t total = (size_t)G * W.L * VL_N_BASES;
+    VL_CUDA(vl_launch_export_haplo(b->dev<VlProblem>(L.tmp_prob), b->dev<double>(L.export_h), total, s));
+    VL_CUDA(cudaMemcpyAsync(merged_haplo_out, b->ws + L.export_h, total * 8, cudaMemcpyDeviceToHost, s));
   }
   if (merged_cluster_out)
-    VL_CUDA(cudaMemcpy2DAsync(merged_cluster_out, (size_t)n_groups * 8, b->ws + L.tmp_z, (size_t)W.KS * 8,
-                              (size_t)n_groups * 8, W.N, cudaMemcpyDeviceToHost, s));
+    VL_CUDA(cudaMemcpy2DAsync(merged_cluster_out, (size_t)G * 8, b->ws + L.tmp_z, (size_t)KSg * 8,
+                              (size_t)G * 8, W.N, cudaMemcpyDeviceToHost, s));
   VL_CUDA(cudaStreamSynchronize(s));
   return 0;
 }

@@ -3,6 +3,20 @@
 // Vocabulary follows the reference (viloca/local_haplotype_inference): a *window* holds N
 // unique reads of length L over the alphabet "ACGT-" (B = 5); a *restart* is one CAVI run on
 // a window from one seeded initial state; K is the number of clusters (haplotypes).
+//
+// Formulation.  The reference's operand E[n,l,b] (preparation.py:123-157) has
+// two distinct values per (read, position): log theta at the called base c and
+// log((1-theta)/(B-1)) elsewhere.  With d = log theta - log((1-theta)/(B-1)) and
+// g[k,l,b] = 1 - h[k,l,b] = sum_{b' != b} h[k,l,b']:
+//   contraction #1   sum_{l,b} E h        = ltsum[n] - Y[n,k],  Y = sum_l d[n,l] g[k,l,c[n,l]]
+//   contraction #2   sum_n w z E [b]      = (b-independent) + sum_n w z d [c[n,l] == b]
+// The b-independent part cancels in the softmax over bases.  Per position one base maj[l] is
+// singled out (the most frequent one): entries with c == maj[l] form the dense operand
+// Dm[n,l] (0 elsewhere) that is contracted on the FP64 tensor pipe with a 5x smaller
+// reduction than E; the few entries with another base are kept in two sparse lists (by read,
+// by position).  Clusters whose responsibilities underflowed to exactly 0 for every read are
+// removed from the dense work: the *layout* lists the live clusters plus one ghost slot that
+// carries the (identical) values of all dead clusters with their multiplicity.
 #pragma once
 #include <cstdint>
 #include <cuda_runtime.h>
@@ -11,23 +25,28 @@
 #define VL_LOG4 1.3862943611198906   // log(B - 1)
 
 // tile geometry (see DESIGN.md "Kernels")
-#define VL_HT_POS 16     // positions per haplotype-update CTA
-#define VL_H_NC 32       // reads per TMA stage of the haplotype-update kernel
+#define VL_PT 16         // positions per operand tile (= positions per haplotype-update CTA)
 #define VL_ZT_READS 64   // reads per responsibility-update CTA
-#define VL_Z_PC 8        // positions per TMA stage of the responsibility-update kernel
+#define VL_H_NC 32       // reads per stage of the haplotype-update kernel
 #define VL_STAGES 3
 #define VL_THREADS 128
-#define VL_ZP_EXTRA 8    // scalars appended to each per-tile column-sum record
+#define VL_MAX_KT 16     // 8-slot tiles of a layout (VL_MAX_CLUSTERS / 8)
+#define VL_ZP_EXTRA 8    // scalars appended to each per-tile column-sum record: data, ent, c, d
 #define VL_HP_STRIDE 4
 
-__host__ __device__ constexpr int vl_k8(int kt) { return 8 * kt; }
-// Row stride (in doubles) of every K-major row.  K8 + 4 makes (4 consecutive rows) x (8
-// consecutive columns) 64-bit shared-memory reads of one m8n8k4 B fragment hit 32 distinct
-// banks per half-warp: 2*KS mod 32 is 8 or 24.
+// Row stride (in doubles) of every slot-major row of a layout with kt tiles.  8*kt + 4 makes
+// (4 consecutive rows) x (8 consecutive columns) 64-bit shared-memory reads of one m8n8k4 B
+// fragment hit 16 distinct 8-byte banks per half-warp.
 __host__ __device__ constexpr int vl_ks(int kt) { return 8 * kt + 4; }
 
+// Dense operand tiles: element (read n, position l) of Dm lives at
+//   ((l / 16) * Npad + n) * 16 + ((l % 16 + 4 * (n % 4)) % 16)
+// i.e. position-tile-major, one 128-byte line per read, rotated by 4 doubles per read so that
+// both fragment shapes (8 reads x 4 positions, 4 reads x 8 positions) read 16 distinct banks.
+__host__ __device__ __forceinline__ int vl_dm_col(int n, int p) { return (p + 4 * (n & 3)) & 15; }
+
 // Per-restart running state: the scalar part of state_curr_dict plus the loop variables of
-// run_cavi (use_quality_scores/cavi.py:114-169).
+// run_cavi (use_quality_scores/cavi.py:114-169) and the live-cluster layout.
 struct VlState {
   double alpha0, thr;
   double a0, b0, c0, d0;                    // state_init: gamma_a, gamma_b, theta_c, theta_d
@@ -37,26 +56,48 @@ struct VlState {
   double dsum_alpha, dsum_ab, dsum_cd;      // the (stale) digamma sums, cavi.py:122-128
   double elbo, t_data, t_pi, t_cluster, t_haplo, t_gamma, t_theta;
   double h_last, h_prev;                    // history_elbo[-1], history_elbo[-2]
-  int iter, n_updates, n_hist, converged, status, active, max_iter, pad_;
+  double ghost_mult;                        // number of dead clusters the ghost slot stands for
+  int iter, n_updates, n_hist, converged, status, active, max_iter;
+  int ktl;        // tiles of the current layout (h, g, gm and the next z are stored in it)
+  int ktl_z;      // tiles of the layout z is stored in (gat maps current slots to its slots)
+  int nlay;       // valid slots of the current layout: live clusters (+ 1 ghost)
+  int ghost;      // slot of the ghost, or -1 when every cluster is live
+  int nlay_z, ghost_z;   // the same for the layout z (and the last h) are stored in
+  int skip;       // 1 = remove dead clusters from the layout (exact), 0 = always dense
+  int stalled;    // layout grew past the kernel class this restart is scheduled in
 };
 
 // Read-only description of one (window, restart) problem.
 struct VlProblem {
   int mode, N, L, K;
-  int Npad, Ls, KS, KT;
+  int Npad, Ls, KT, pad0;
   int n_ztiles, n_htiles, window, restart;
-  const uint8_t* codes;    // [Npad][Ls]  0..4, 255 = N
-  const double* lt;        // [Npad][Ls]  log theta            (uqs)
-  const double* lo;        // [Npad][Ls]  log((1-theta)/(B-1)) (uqs)
-  const double* w;         // [Npad]      read multiplicity, 0 in the padding
-  const double* mcount;    // [Npad]      number of called (non-N) positions
+  // window tensors (shared by the restarts of a window)
+  const double* dm;        // [Ls/16][Npad][16] dense operand, see vl_dm_col
+  const double* w;         // [Npad]  read multiplicity, 0 in the padding
+  const double* ltsum;     // [Npad]  uqs: sum over called positions of log theta
+  const double* mcount;    // [Npad]  number of called (non-N) positions
   const uint8_t* ref;      // [Ls]
-  double* z;               // [Npad][KS]       mean_cluster
-  double* h;               // [Ls][B][KS]      mean_haplo, position-major
+  const uint8_t* maj;      // [Ls]    base singled out per position
+  const int* sr_ptr;       // [Npad+1] minority entries by read ...
+  const int* sr_idx;       //   l * 5 + c
+  const double* sr_d;      //   d[n,l]
+  const int* sp_ptr;       // [Ls+1]  ... and by position, sorted by (c, n)
+  const int* sp_nc;        //   n * 8 + c
+  const double* sp_wd;     //   w_n * d[n,l]
+  // restart tensors; "slot" = column of the current layout
+  double* z;               // [Npad][vl_ks(ktl_z)]   mean_cluster
+  double* h;               // [Ls][5][vl_ks(ktl)]    mean_haplo
+  double* g;               // [Ls][5][vl_ks(ktl)]    1 - mean_haplo, summed from the other bases
+  double* gm;              // [Ls][vl_ks(ktl)]       g at the singled-out base
   double* zpart;           // [n_ztiles][8*KT + VL_ZP_EXTRA]
   double* hpart;           // [n_htiles][VL_HP_STRIDE]
-  double* alpha;           // [8*KT]
-  double* mlp;             // [8*KT]  mean_log_pi
+  double* alpha;           // [8*KT]  per cluster
+  double* mlp;             // [8*KT]  mean_log_pi per cluster
+  double* mlp_lay;         // [8*KT]  mean_log_pi per slot
+  int* lay;                // [8*KT]  slot -> cluster (ghost: one of the dead clusters)
+  int* gat;                // [8*KT]  slot -> slot of the layout z is stored in
+  int* lay_z;              // [8*KT]  slot -> cluster for the layout z is stored in
   double* hist;            // [max_iter] history_elbo
   VlState* st;
 };

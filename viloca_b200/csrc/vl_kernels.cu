@@ -1,20 +1,18 @@
-// CAVI kernels for sm_100a: the two dense FP64 contractions of one CAVI iteration on the
-// FP64 tensor pipe (DMMA m8n8k4) with the softmax / ELBO reductions fused into their
-// epilogues, plus the per-restart scalar update that closes the iteration.
-//
-// One iteration of a (window, restart) problem = three launches over the whole batch:
+// CAVI kernels for sm_100a.  One iteration of a (window, restart) problem = three launches
+// over the whole batch:
 //   vl_haplo_kernel    update_mean_haplo   (uqs update_eqs.py:73-101, lep update_eqs.py:115-159)
 //                      + the sums update_a_and_b / elbo_haplo need (update_eqs.py:103-112,
 //                      elbo_eqs.py:65-78)
 //   vl_cluster_kernel  update_mean_cluster (uqs update_eqs.py:55-71, lep update_eqs.py:90-112)
 //                      + the sums update_alpha / elbo_data / elbo_cluster / update_c_and_d need
-//   vl_scalar_kernel   alpha, mean_log_pi, a, b, (c, d), the ELBO and the loop state machine
-//                      of run_cavi (cavi.py:120-169)
+//   vl_scalar_kernel   alpha, mean_log_pi, a, b, (c, d), the ELBO, the loop state machine of
+//                      run_cavi (cavi.py:120-169) and the next live-cluster layout
 //
-// The one-hot, quality-weighted read tensor E[n,l,b] (preparation.py:123-157) is never
-// materialised: each thread builds its DMMA A-fragment in registers from the compact form
-// (base code, log theta, log((1-theta)/(B-1))).  The other operand (responsibilities or
-// haplotype table) is staged in shared memory by TMA bulk copies behind mbarriers.
+// Both contractions run on the FP64 tensor pipe (DMMA m8n8k4) over the dense majority operand
+// Dm (vl_device.cuh), whose tiles and the other operand (responsibilities or the haplotype
+// complement table) are staged in shared memory by TMA bulk copies behind mbarriers; the
+// minority entries are added from the sparse lists; softmax / ELBO reductions are fused into
+// the epilogues.
 #include "vl_device.cuh"
 #include "vl_launch.h"
 #include "../../include/viloca_b200.h"
@@ -30,33 +28,44 @@ __device__ __forceinline__ double warp_sum(double v) {
 }
 
 // =========================================================================================
-// update_mean_haplo: C[k,l,b] = sum_n (w_n z_nk) E[n,l,b], then softmax over b.
-// CTA = 16 positions x all clusters; warp (lg, kh) = 8 positions x 5 bases x half of the
-// cluster tiles; the DMMA M dimension is the position, so one thread ends up holding all
-// five bases of its (position, cluster) pairs and the softmax over b is thread-local.
+// update_mean_haplo.  Per (position l, slot s) the logits over the bases are
+//   b = maj[l]:  T[l,s]  = sum_n w_n z[n,s] Dm[n,l]          (dense, DMMA, M = position)
+//   b other:     Cm[l,b,s] = sum_{minority entries (n,l,b)} (w_n d) z[n,s]   (sparse list)
+// plus the reference term; the part of the reference's logits that does not depend on b is
+// dropped (it cancels in the softmax).  CTA = 16 positions x all slots; warp (lg, rh) = 8
+// positions x one half of the reads of every stage; the two halves are added in fixed order.
 // =========================================================================================
-template <int KT, int MODE>
-__global__ void __launch_bounds__(VL_THREADS, 2)
+template <int NB, int MODE>
+__global__ void __launch_bounds__(VL_THREADS)
 vl_haplo_kernel(const VlProblem* __restrict__ probs, const int2* __restrict__ tiles) {
-  constexpr int KTW = (KT + 1) / 2;
-  constexpr int KS = vl_ks(KT);
-  constexpr uint32_t STAGE_BYTES = VL_H_NC * KS * sizeof(double);
+  constexpr int KTM = 4 * NB;
+  constexpr int KSM = vl_ks(KTM);
+  constexpr int DM_STAGE = VL_H_NC * VL_PT;            // doubles
+  constexpr int ST_STRIDE = DM_STAGE + VL_H_NC + VL_H_NC * KSM;   // dm | w | z
   extern __shared__ __align__(128) unsigned char vl_smem[];
-  double* zs = reinterpret_cast<double*>(vl_smem);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(vl_smem + VL_STAGES * STAGE_BYTES);
+  double* stg = reinterpret_cast<double*>(vl_smem);
+  __shared__ uint64_t bars[VL_STAGES];
   __shared__ double red[VL_THREADS / 32][4];
 
   const int2 tm = tiles[blockIdx.x];
   const VlProblem& P = probs[tm.x];
   const VlState* S = P.st;
-  if (S->active == 0) return;
+  const int ktl = S->ktl, ktz = S->ktl_z;
+  if (S->active == 0 || ktl > KTM || ktz > KTM) return;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, q = lane & 3;
-  const int lg = warp & 1, kh = warp >> 1, kt0 = kh * KTW;
-  const int l = tm.y * VL_HT_POS + lg * 8 + g;
-  const int Ls = P.Ls, Npad = P.Npad;
+  const int lg = warp & 1, rh = warp >> 1;
+  const int Npad = P.Npad;
+  const int KSz = vl_ks(ktz), KSn = vl_ks(ktl), K8 = 8 * ktl;
+  const int nlay = S->nlay;
   const int nchunks = Npad / VL_H_NC;
+  const int l0 = tm.y * VL_PT;
+  const double* __restrict__ dmg = P.dm + (size_t)tm.y * Npad * VL_PT;
   const double* __restrict__ zg = P.z;
+  const double* __restrict__ wg = P.w;
+  const int* __restrict__ gat = P.gat;
+  const uint32_t z_bytes = (uint32_t)(VL_H_NC * KSz * sizeof(double));
+  const uint32_t stage_bytes = (uint32_t)((DM_STAGE + VL_H_NC) * sizeof(double)) + z_bytes;
 
   if (tid == 0) {
 #pragma unroll
@@ -64,123 +73,152 @@ vl_haplo_kernel(const VlProblem* __restrict__ probs, const int2* __restrict__ ti
     vl_fence_mbar_init();
   }
   __syncthreads();
-  if (tid == 0) {
-    for (int s = 0; s < VL_STAGES - 1 && s < nchunks; ++s) {
-      vl_mbar_expect_tx(&bars[s], STAGE_BYTES);
-      vl_tma_load_1d(zs + s * VL_H_NC * KS, zg + (size_t)s * VL_H_NC * KS, STAGE_BYTES, &bars[s]);
-    }
+  auto issue = [&](int c) {
+    const int sn = c % VL_STAGES;
+    double* dst = stg + (size_t)sn * ST_STRIDE;
+    vl_mbar_expect_tx(&bars[sn], stage_bytes);
+    vl_tma_load_1d(dst, dmg + (size_t)c * DM_STAGE, DM_STAGE * sizeof(double), &bars[sn]);
+    vl_tma_load_1d(dst + DM_STAGE, wg + (size_t)c * VL_H_NC, VL_H_NC * sizeof(double), &bars[sn]);
+    vl_tma_load_1d(dst + DM_STAGE + VL_H_NC, zg + (size_t)c * VL_H_NC * KSz, z_bytes, &bars[sn]);
+  };
+  if (tid == 0)
+    for (int c = 0; c < VL_STAGES - 1 && c < nchunks; ++c) issue(c);
+
+  // column of the stored z each of this thread's B-fragment columns comes from
+  int co[KTM];
+#pragma unroll
+  for (int i = 0; i < KTM; ++i) {
+    const int s = 8 * i + g;
+    co[i] = (i < ktl && s < nlay) ? gat[s] : 0;
   }
-
-  double acc[VL_B][KTW][2];
+  double acc[KTM][2];
 #pragma unroll
-  for (int b = 0; b < VL_B; ++b)
-#pragma unroll
-    for (int i = 0; i < KTW; ++i) { acc[b][i][0] = 0.0; acc[b][i][1] = 0.0; }
+  for (int i = 0; i < KTM; ++i) { acc[i][0] = 0.0; acc[i][1] = 0.0; }
 
-  // compact operand of read n = 4*step + q at this thread's position, prefetched one step ahead
-  const uint8_t* __restrict__ codes = P.codes;
-  const double* __restrict__ ltp = P.lt;
-  const double* __restrict__ lop = P.lo;
-  const double* __restrict__ wp = P.w;
-  int n = q;
-  size_t off = (size_t)q * Ls + l;
-  unsigned c_nx = codes[off];
-  double w_nx = wp[n], lt_nx = 0.0, lo_nx = 0.0;
-  if (MODE == VL_MODE_UQS) { lt_nx = ltp[off]; lo_nx = lop[off]; }
-
+  const int acol = (lg * 8 + g + 4 * q) & 15;      // vl_dm_col(row, lg*8+g) with row % 4 == q
   for (int c = 0; c < nchunks; ++c) {
     const int st = c % VL_STAGES;
-    if (tid == 0 && c + VL_STAGES - 1 < nchunks) {
-      const int cn = c + VL_STAGES - 1, sn = cn % VL_STAGES;
-      vl_mbar_expect_tx(&bars[sn], STAGE_BYTES);
-      vl_tma_load_1d(zs + sn * VL_H_NC * KS, zg + (size_t)cn * VL_H_NC * KS, STAGE_BYTES, &bars[sn]);
-    }
+    if (tid == 0 && c + VL_STAGES - 1 < nchunks) issue(c + VL_STAGES - 1);
     vl_mbar_wait(&bars[st], (c / VL_STAGES) & 1);
-    const double* zt = zs + st * VL_H_NC * KS + q * KS + g;
+    const double* dt = stg + (size_t)st * ST_STRIDE;
+    const double* wt = dt + DM_STAGE;
+    const double* zt = wt + VL_H_NC;
 #pragma unroll
-    for (int s = 0; s < VL_H_NC / 4; ++s) {
-      const unsigned cc = c_nx;
-      const double wv = w_nx, ltv = lt_nx, lov = lo_nx;
-      n += 4;
-      if (n < Npad) {
-        off += (size_t)4 * Ls;
-        c_nx = codes[off];
-        w_nx = wp[n];
-        if (MODE == VL_MODE_UQS) { lt_nx = ltp[off]; lo_nx = lop[off]; }
-      }
-      double a[VL_B];
-      if (MODE == VL_MODE_UQS) {
-        const double hit = (cc == VL_CODE_N) ? 0.0 : wv * ltv;
-        const double base = (cc == VL_CODE_N) ? 0.0 : wv * lov;
+    for (int s = 0; s < 4; ++s) {
+      const int row = rh * 16 + 4 * s + q;
+      const double a = wt[row] * dt[row * VL_PT + acol];
+      const double* zr = zt + row * KSz;
 #pragma unroll
-        for (int b = 0; b < VL_B; ++b) a[b] = (cc == (unsigned)b) ? hit : base;
-      } else {
-#pragma unroll
-        for (int b = 0; b < VL_B; ++b) a[b] = (cc == (unsigned)b) ? wv : 0.0;
-      }
-#pragma unroll
-      for (int i = 0; i < KTW; ++i) {
-        if (i < KTW - 1 || (KT % 2 == 0) || kh == 0) {
-          const double bf = zt[(4 * s) * KS + (kt0 + i) * 8];
-#pragma unroll
-          for (int b = 0; b < VL_B; ++b) vl_dmma(acc[b][i], a[b], bf);
-        }
-      }
+      for (int i = 0; i < KTM; ++i)
+        if (i < ktl) vl_dmma(acc[i], a, zr[co[i]]);
     }
     __syncthreads();
   }
 
-  // ---- epilogue: + ref_part, softmax over b, the three sums, store mean_haplo ----
-  const double mlg0 = S->mlg0, refoff = S->mlg1 - VL_LOG4;
-  double b1 = 0.0, b2 = 0.0;
-  if (MODE == VL_MODE_LEP) { b1 = S->mlt0; b2 = S->mlt1 - VL_LOG4; }
-  const unsigned rc = P.ref[l];
-  const bool lvalid = l < P.L;
-  const int K = P.K;
-  double s_ref = 0.0, s_nref = 0.0, s_ent = 0.0;
-  double* hrow = P.h + (size_t)l * VL_B * KS;
+  // ---- the stage buffers are free now: T [16][K8] and Cm [16][5][K8] live in them ----
+  double* T = stg;
+  double* Cm = stg + VL_PT * K8;
+  if (rh == 1) {
 #pragma unroll
-  for (int i = 0; i < KTW; ++i) {
-    if (i < KTW - 1 || (KT % 2 == 0) || kh == 0) {
-      const int kb = (kt0 + i) * 8 + 2 * q;
-      double out[VL_B][2];
+    for (int i = 0; i < KTM; ++i)
+      if (i < ktl)
+        *reinterpret_cast<double2*>(T + (lg * 8 + g) * K8 + 8 * i + 2 * q) = make_double2(acc[i][0], acc[i][1]);
+  }
+  __syncthreads();
+  if (rh == 0) {
 #pragma unroll
-      for (int j = 0; j < 2; ++j) {
-        double lgt[VL_B];
-        if (MODE == VL_MODE_UQS) {
+    for (int i = 0; i < KTM; ++i)
+      if (i < ktl) {
+        double2* tp = reinterpret_cast<double2*>(T + (lg * 8 + g) * K8 + 8 * i + 2 * q);
+        const double2 o = *tp;
+        *tp = make_double2(acc[i][0] + o.x, acc[i][1] + o.y);
+      }
+  }
+  // minority entries of this tile's positions: warp = 4 positions, lanes = slots
+  {
+    const int* __restrict__ sp_ptr = P.sp_ptr;
+    const int* __restrict__ sp_n = P.sp_nc;
+    const double* __restrict__ sp_wd = P.sp_wd;
+    int gl[NB];
 #pragma unroll
-          for (int b = 0; b < VL_B; ++b) lgt[b] = acc[b][i][j] + ((rc == (unsigned)b) ? mlg0 : refoff);
-        } else {
-          double tot = 0.0;
+    for (int j = 0; j < NB; ++j) {
+      const int s = lane + 32 * j;
+      gl[j] = (s < nlay) ? gat[s] : 0;
+    }
+    for (int pp = 0; pp < 4; ++pp) {
+      const int pos = warp * 4 + pp;
+      const int l = l0 + pos;
+      for (int b = 0; b < VL_B; ++b) {
+        const int e0 = sp_ptr[l * VL_B + b], e1 = sp_ptr[l * VL_B + b + 1];
+        double av[NB];
 #pragma unroll
-          for (int b = 0; b < VL_B; ++b) tot += acc[b][i][j];
+        for (int j = 0; j < NB; ++j) av[j] = 0.0;
+#pragma unroll 4
+        for (int e = e0; e < e1; ++e) {
+          const double wd = sp_wd[e];
+          const double* zr = zg + (size_t)sp_n[e] * KSz;
 #pragma unroll
-          for (int b = 0; b < VL_B; ++b)
-            lgt[b] = b1 * acc[b][i][j] + b2 * (tot - acc[b][i][j]) + ((rc == (unsigned)b) ? mlg0 : refoff);
+          for (int j = 0; j < NB; ++j) av[j] += wd * zr[gl[j]];
         }
-        double m = lgt[0];
 #pragma unroll
-        for (int b = 1; b < VL_B; ++b) m = fmax(m, lgt[b]);
-        double e[VL_B], sum = 0.0;
-#pragma unroll
-        for (int b = 0; b < VL_B; ++b) { e[b] = exp(lgt[b] - m); sum += e[b]; }
-        if (lvalid && (kb + j) < K) {
-          const double ls = log(sum);
-#pragma unroll
-          for (int b = 0; b < VL_B; ++b) {
-            const double hb = e[b] / sum;
-            if (rc == (unsigned)b) s_ref += hb; else s_nref += hb;
-            if (hb > 0.0) s_ent += hb * ((lgt[b] - m) - ls);
-            out[b][j] = hb;
-          }
-        } else {
-#pragma unroll
-          for (int b = 0; b < VL_B; ++b) out[b][j] = 0.0;
+        for (int j = 0; j < NB; ++j) {
+          const int s = lane + 32 * j;
+          if (s < K8) Cm[(pos * VL_B + b) * K8 + s] = av[j];
         }
       }
+    }
+  }
+  __syncthreads();
+
+  // ---- epilogue: + ref_part, softmax over b, the three sums, store h, g, gm ----
+  const double mlg0 = S->mlg0, refoff = S->mlg1 - VL_LOG4;
+  double cscale = 1.0;
+  if (MODE == VL_MODE_LEP) cscale = S->mlt0 - (S->mlt1 - VL_LOG4);
+  const int ghost = S->ghost;
+  const double gmult = S->ghost_mult;
+  const int L = P.L;
+  double s_ref = 0.0, s_nref = 0.0, s_ent = 0.0;
+  for (int idx = tid; idx < VL_PT * K8; idx += VL_THREADS) {
+    const int pos = idx / K8, slot = idx - pos * K8;
+    const int l = l0 + pos;
+    const unsigned rc = P.ref[l], mj = P.maj[l];
+    double* hp = P.h + (size_t)l * VL_B * KSn + slot;
+    double* gp = P.g + (size_t)l * VL_B * KSn + slot;
+    if (l < L && slot < nlay) {
+      double lgt[VL_B];
 #pragma unroll
-      for (int b = 0; b < VL_B; ++b)
-        *reinterpret_cast<double2*>(hrow + b * KS + kb) = make_double2(out[b][0], out[b][1]);
+      for (int b = 0; b < VL_B; ++b) {
+        const double cb = (mj == (unsigned)b) ? T[pos * K8 + slot] : Cm[(pos * VL_B + b) * K8 + slot];
+        lgt[b] = ((MODE == VL_MODE_LEP) ? cscale * cb : cb) + ((rc == (unsigned)b) ? mlg0 : refoff);
+      }
+      double m = lgt[0];
+#pragma unroll
+      for (int b = 1; b < VL_B; ++b) m = fmax(m, lgt[b]);
+      double e[VL_B], sum = 0.0;
+#pragma unroll
+      for (int b = 0; b < VL_B; ++b) { e[b] = exp(lgt[b] - m); sum += e[b]; }
+      const double ls = log(sum);
+      const double mu = (slot == ghost) ? gmult : 1.0;
+      double r0 = 0.0, r1 = 0.0, r2 = 0.0, gmaj = 0.0;
+#pragma unroll
+      for (int b = 0; b < VL_B; ++b) {
+        const double hb = e[b] / sum;
+        double oth = 0.0;
+#pragma unroll
+        for (int b2 = 0; b2 < VL_B; ++b2) if (b2 != b) oth += e[b2];
+        const double gb = oth / sum;
+        if (rc == (unsigned)b) r0 += hb; else r1 += hb;
+        if (hb > 0.0) r2 += hb * ((lgt[b] - m) - ls);
+        hp[b * KSn] = hb;
+        gp[b * KSn] = gb;
+        if (mj == (unsigned)b) gmaj = gb;
+      }
+      P.gm[(size_t)l * KSn + slot] = gmaj;
+      s_ref += mu * r0; s_nref += mu * r1; s_ent += mu * r2;
+    } else {
+#pragma unroll
+      for (int b = 0; b < VL_B; ++b) { hp[b * KSn] = 0.0; gp[b * KSn] = 0.0; }
+      P.gm[(size_t)l * KSn + slot] = 0.0;
     }
   }
   s_ref = warp_sum(s_ref); s_nref = warp_sum(s_nref); s_ent = warp_sum(s_ent);
@@ -195,32 +233,38 @@ vl_haplo_kernel(const VlProblem* __restrict__ probs, const int2* __restrict__ ti
 }
 
 // =========================================================================================
-// update_mean_cluster: X[n,k] = sum_{l,b} E[n,l,b] h[k,l,b], then softmax over k.
-// CTA = 64 reads x all clusters; warp = 16 reads (two m8 tiles) x all cluster tiles.  The
-// reduction index runs over (position, base): one k4 step covers 4 positions of one base.
+// update_mean_cluster.  Y[n,s] = sum_l Dm[n,l] gm[l,s] (dense, DMMA, M = read) + the minority
+// entries of read n; uqs logits = ltsum[n] - Y + mean_log_pi, softmax over the slots with the
+// ghost slot counted ghost_mult times.  CTA = 64 reads x all slots; warp = 16 reads.
 // =========================================================================================
-template <int KT, int MODE>
-__global__ void __launch_bounds__(VL_THREADS, 2)
+template <int NB, int MODE>
+__global__ void __launch_bounds__(VL_THREADS)
 vl_cluster_kernel(const VlProblem* __restrict__ probs, const int2* __restrict__ tiles) {
-  constexpr int KS = vl_ks(KT), K8 = vl_k8(KT);
-  constexpr int STAGE_DOUBLES = VL_Z_PC * VL_B * KS;
-  constexpr uint32_t STAGE_BYTES = STAGE_DOUBLES * sizeof(double);
+  constexpr int KTM = 4 * NB;
+  constexpr int KSM = vl_ks(KTM), K8M = 8 * KTM;
+  constexpr int DM_STAGE = VL_ZT_READS * VL_PT;        // doubles
+  constexpr int ST_STRIDE = DM_STAGE + VL_PT * KSM;    // dm | gm
   extern __shared__ __align__(128) unsigned char vl_smem[];
-  double* hs = reinterpret_cast<double*>(vl_smem);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(vl_smem + VL_STAGES * STAGE_BYTES);
-  double* red_cs = reinterpret_cast<double*>(vl_smem + VL_STAGES * STAGE_BYTES + 64);   // [4][K8]
-  double* red_sc = red_cs + (VL_THREADS / 32) * K8;                                       // [4][4]
+  double* stg = reinterpret_cast<double*>(vl_smem);
+  double* red_cs = stg + VL_STAGES * ST_STRIDE;        // [4][K8M]
+  __shared__ uint64_t bars[VL_STAGES];
+  __shared__ double red_sc[VL_THREADS / 32][4];
 
   const int2 tm = tiles[blockIdx.x];
   const VlProblem& P = probs[tm.x];
   const VlState* S = P.st;
-  if (S->active == 0) return;
+  const int ktl = S->ktl;
+  if (S->active == 0 || ktl > KTM || S->ktl_z > KTM) return;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, q = lane & 3;
-  const int Ls = P.Ls;
-  const int nst = Ls / VL_Z_PC;
-  const int n0 = tm.y * VL_ZT_READS + warp * 16 + g;
-  const double* __restrict__ hg = P.h;
+  const int Npad = P.Npad;
+  const int KS = vl_ks(ktl), K8 = 8 * ktl;
+  const int nst = P.Ls / VL_PT;
+  const int n0 = tm.y * VL_ZT_READS;
+  const double* __restrict__ dmg = P.dm + (size_t)n0 * VL_PT;
+  const double* __restrict__ gmg = P.gm;
+  const uint32_t gm_bytes = (uint32_t)(VL_PT * KS * sizeof(double));
+  const uint32_t stage_bytes = (uint32_t)(DM_STAGE * sizeof(double)) + gm_bytes;
 
   if (tid == 0) {
 #pragma unroll
@@ -228,136 +272,123 @@ vl_cluster_kernel(const VlProblem* __restrict__ probs, const int2* __restrict__ 
     vl_fence_mbar_init();
   }
   __syncthreads();
-  if (tid == 0) {
-    for (int s = 0; s < VL_STAGES - 1 && s < nst; ++s) {
-      vl_mbar_expect_tx(&bars[s], STAGE_BYTES);
-      vl_tma_load_1d(hs + s * STAGE_DOUBLES, hg + (size_t)s * STAGE_DOUBLES, STAGE_BYTES, &bars[s]);
-    }
-  }
+  auto issue = [&](int c) {
+    const int sn = c % VL_STAGES;
+    double* dst = stg + (size_t)sn * ST_STRIDE;
+    vl_mbar_expect_tx(&bars[sn], stage_bytes);
+    vl_tma_load_1d(dst, dmg + (size_t)c * Npad * VL_PT, DM_STAGE * sizeof(double), &bars[sn]);
+    vl_tma_load_1d(dst + DM_STAGE, gmg + (size_t)c * VL_PT * KS, gm_bytes, &bars[sn]);
+  };
+  if (tid == 0)
+    for (int c = 0; c < VL_STAGES - 1 && c < nst; ++c) issue(c);
 
-  double acc[2][KT][2];
+  double acc[2][KTM][2];
 #pragma unroll
   for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
-    for (int kt = 0; kt < KT; ++kt) { acc[mt][kt][0] = 0.0; acc[mt][kt][1] = 0.0; }
+    for (int i = 0; i < KTM; ++i) { acc[mt][i][0] = 0.0; acc[mt][i][1] = 0.0; }
 
-  const uint8_t* __restrict__ codes = P.codes;
-  const double* __restrict__ ltp = P.lt;
-  const double* __restrict__ lop = P.lo;
-  size_t off[2];
-  off[0] = (size_t)n0 * Ls + q;
-  off[1] = (size_t)(n0 + 8) * Ls + q;
-  unsigned c_nx[2][2];
-  double lt_nx[2][2], lo_nx[2][2];
-#pragma unroll
-  for (int mt = 0; mt < 2; ++mt)
-#pragma unroll
-    for (int l4 = 0; l4 < 2; ++l4) {
-      c_nx[mt][l4] = codes[off[mt] + 4 * l4];
-      lt_nx[mt][l4] = 0.0; lo_nx[mt][l4] = 0.0;
-      if (MODE == VL_MODE_UQS) { lt_nx[mt][l4] = ltp[off[mt] + 4 * l4]; lo_nx[mt][l4] = lop[off[mt] + 4 * l4]; }
-    }
-
+  const int r0 = warp * 16 + g;                    // rows r0 and r0 + 8 of the tile; r0 % 4 == g % 4
   for (int c = 0; c < nst; ++c) {
     const int st = c % VL_STAGES;
-    if (tid == 0 && c + VL_STAGES - 1 < nst) {
-      const int cn = c + VL_STAGES - 1, sn = cn % VL_STAGES;
-      vl_mbar_expect_tx(&bars[sn], STAGE_BYTES);
-      vl_tma_load_1d(hs + sn * STAGE_DOUBLES, hg + (size_t)cn * STAGE_DOUBLES, STAGE_BYTES, &bars[sn]);
-    }
-    unsigned cc[2][2];
-    double hitv[2][2], offv[2][2];
-#pragma unroll
-    for (int mt = 0; mt < 2; ++mt)
-#pragma unroll
-      for (int l4 = 0; l4 < 2; ++l4) {
-        cc[mt][l4] = c_nx[mt][l4];
-        if (MODE == VL_MODE_UQS) {
-          hitv[mt][l4] = (cc[mt][l4] == VL_CODE_N) ? 0.0 : lt_nx[mt][l4];
-          offv[mt][l4] = (cc[mt][l4] == VL_CODE_N) ? 0.0 : lo_nx[mt][l4];
-        } else {
-          hitv[mt][l4] = 1.0; offv[mt][l4] = 0.0;
-        }
-      }
-    if (c + 1 < nst) {
-#pragma unroll
-      for (int mt = 0; mt < 2; ++mt) {
-        off[mt] += VL_Z_PC;
-#pragma unroll
-        for (int l4 = 0; l4 < 2; ++l4) {
-          c_nx[mt][l4] = codes[off[mt] + 4 * l4];
-          if (MODE == VL_MODE_UQS) { lt_nx[mt][l4] = ltp[off[mt] + 4 * l4]; lo_nx[mt][l4] = lop[off[mt] + 4 * l4]; }
-        }
-      }
-    }
+    if (tid == 0 && c + VL_STAGES - 1 < nst) issue(c + VL_STAGES - 1);
     vl_mbar_wait(&bars[st], (c / VL_STAGES) & 1);
-    const double* ht = hs + st * STAGE_DOUBLES + q * VL_B * KS + g;
+    const double* dt = stg + (size_t)st * ST_STRIDE;
+    const double* gt = dt + DM_STAGE + g;
 #pragma unroll
-    for (int l4 = 0; l4 < 2; ++l4) {
+    for (int s = 0; s < 4; ++s) {
+      const int col = (4 * s + q + 4 * (g & 3)) & 15;
+      const double a0 = dt[r0 * VL_PT + col];
+      const double a1 = dt[(r0 + 8) * VL_PT + col];
+      const double* gr = gt + (4 * s + q) * KS;
 #pragma unroll
-      for (int b = 0; b < VL_B; ++b) {
-        const double a0 = (cc[0][l4] == (unsigned)b) ? hitv[0][l4] : offv[0][l4];
-        const double a1 = (cc[1][l4] == (unsigned)b) ? hitv[1][l4] : offv[1][l4];
-        const double* hb = ht + (4 * l4 * VL_B + b) * KS;
-#pragma unroll
-        for (int kt = 0; kt < KT; ++kt) {
-          const double bf = hb[kt * 8];
-          vl_dmma(acc[0][kt], a0, bf);
-          vl_dmma(acc[1][kt], a1, bf);
+      for (int i = 0; i < KTM; ++i)
+        if (i < ktl) {
+          const double bf = gr[8 * i];
+          vl_dmma(acc[0][i], a0, bf);
+          vl_dmma(acc[1][i], a1, bf);
         }
-      }
     }
     __syncthreads();
   }
 
-  // ---- epilogue: + mean_log_pi, softmax over k, the reductions, store mean_cluster ----
-  const double* __restrict__ mlp = P.mlp;
-  const int K = P.K, N = P.N;
+  // ---- minority entries of this thread's two reads ----
+  {
+    const int* __restrict__ sr_ptr = P.sr_ptr;
+    const int* __restrict__ sr_idx = P.sr_idx;
+    const double* __restrict__ sr_d = P.sr_d;
+    const double* __restrict__ gtab = P.g;
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt) {
+      const int n = n0 + r0 + 8 * mt;
+      const int e0 = sr_ptr[n], e1 = sr_ptr[n + 1];
+      for (int e = e0; e < e1; ++e) {
+        const double d = sr_d[e];
+        const double* gp = gtab + (size_t)sr_idx[e] * KS + 2 * q;
+#pragma unroll
+        for (int i = 0; i < KTM; ++i)
+          if (i < ktl) {
+            const double2 gv = *reinterpret_cast<const double2*>(gp + 8 * i);
+            acc[mt][i][0] += d * gv.x;
+            acc[mt][i][1] += d * gv.y;
+          }
+      }
+    }
+  }
+
+  // ---- epilogue: logits, softmax over the slots, the reductions, store mean_cluster ----
+  const double* __restrict__ mlpl = P.mlp_lay;
+  const int N = P.N, nlay = S->nlay, ghost = S->ghost;
+  const double gmult = S->ghost_mult;
   double b1 = 0.0, b2 = 0.0;
   const double Lf = (double)P.L;
   if (MODE == VL_MODE_LEP) { b1 = S->mlt0; b2 = S->mlt1 - VL_LOG4; }
   double s_data = 0.0, s_ent = 0.0, s_c = 0.0, s_d = 0.0;
+  double cs[KTM][2];
 #pragma unroll
   for (int mt = 0; mt < 2; ++mt) {
-    const int n = n0 + 8 * mt;
+    const int n = n0 + r0 + 8 * mt;
     const bool valid = n < N;
     const double wn = P.w[n];
     const double mc = P.mcount[n];
-    double t[KT][2];
+    const double base = (MODE == VL_MODE_UQS) ? P.ltsum[n] : mc;
+    double t[KTM][2];
     double m = neg_inf();
 #pragma unroll
-    for (int kt = 0; kt < KT; ++kt)
+    for (int i = 0; i < KTM; ++i)
+      if (i < ktl) {
 #pragma unroll
-      for (int j = 0; j < 2; ++j) {
-        const int k = kt * 8 + 2 * q + j;
-        const double x = acc[mt][kt][j];
-        double tv;
-        if (k < K) {
-          const double lp = mlp[k];
-          tv = (MODE == VL_MODE_UQS) ? (x + lp) : (b1 * x + b2 * (Lf - x) + lp);
-        } else {
-          tv = neg_inf();
+        for (int j = 0; j < 2; ++j) {
+          const int s = 8 * i + 2 * q + j;
+          // uqs: X = sum_{l,b} E h;  lep: S = sum_{l,b} r h  (update_eqs.py:57 / lep :98-99)
+          const double x = base - acc[mt][i][j];
+          acc[mt][i][j] = x;
+          double tv = neg_inf();
+          if (s < nlay) tv = ((MODE == VL_MODE_UQS) ? x : (b1 * x + b2 * (Lf - x))) + mlpl[s];
+          t[i][j] = tv;
+          m = fmax(m, tv);
         }
-        t[kt][j] = tv;
-        m = fmax(m, tv);
       }
     m = fmax(m, __shfl_xor_sync(0xffffffffu, m, 1));
     m = fmax(m, __shfl_xor_sync(0xffffffffu, m, 2));
     double sum = 0.0, u = 0.0, v = 0.0;
 #pragma unroll
-    for (int kt = 0; kt < KT; ++kt)
+    for (int i = 0; i < KTM; ++i)
+      if (i < ktl) {
 #pragma unroll
-      for (int j = 0; j < 2; ++j) {
-        const int k = kt * 8 + 2 * q + j;
-        double e = 0.0;
-        if (k < K) {
-          const double dt = t[kt][j] - m;
-          e = exp(dt);
-          if (e > 0.0) u += e * dt;
-          v += e * acc[mt][kt][j];
+        for (int j = 0; j < 2; ++j) {
+          const int s = 8 * i + 2 * q + j;
+          double e = 0.0;
+          if (s < nlay) {
+            const double dt = t[i][j] - m;
+            e = exp(dt);
+            const double em = (s == ghost) ? gmult * e : e;
+            if (e > 0.0) u += em * dt;
+            v += em * acc[mt][i][j];
+            sum += em;
+          }
+          t[i][j] = e;
         }
-        t[kt][j] = e;
-        sum += e;
       }
     const double psum = sum;   // this thread's share of the row sum
     sum += __shfl_xor_sync(0xffffffffu, sum, 1);
@@ -374,81 +405,102 @@ vl_cluster_kernel(const VlProblem* __restrict__ probs, const int2* __restrict__ 
     }
     double* zrow = P.z + (size_t)n * KS + 2 * q;
 #pragma unroll
-    for (int kt = 0; kt < KT; ++kt) {
-      const double z0 = valid ? t[kt][0] / sum : 0.0;
-      const double z1 = valid ? t[kt][1] / sum : 0.0;
-      *reinterpret_cast<double2*>(zrow + kt * 8) = make_double2(z0, z1);
-      // the weighted column sums of this thread's two rows are collected in acc[0]
-      if (mt == 0) { acc[0][kt][0] = wn * z0; acc[0][kt][1] = wn * z1; }
-      else { acc[0][kt][0] += wn * z0; acc[0][kt][1] += wn * z1; }
-    }
+    for (int i = 0; i < KTM; ++i)
+      if (i < ktl) {
+        const double z0 = valid ? t[i][0] / sum : 0.0;
+        const double z1 = valid ? t[i][1] / sum : 0.0;
+        *reinterpret_cast<double2*>(zrow + 8 * i) = make_double2(z0, z1);
+        if (mt == 0) { cs[i][0] = wn * z0; cs[i][1] = wn * z1; }
+        else { cs[i][0] += wn * z0; cs[i][1] += wn * z1; }
+      }
   }
 #pragma unroll
-  for (int kt = 0; kt < KT; ++kt)
+  for (int i = 0; i < KTM; ++i)
+    if (i < ktl) {
 #pragma unroll
-    for (int j = 0; j < 2; ++j) {
-      double v = acc[0][kt][j];
-      v += __shfl_xor_sync(0xffffffffu, v, 4);
-      v += __shfl_xor_sync(0xffffffffu, v, 8);
-      v += __shfl_xor_sync(0xffffffffu, v, 16);
-      if (g == 0) red_cs[warp * K8 + kt * 8 + 2 * q + j] = v;
+      for (int j = 0; j < 2; ++j) {
+        double v = cs[i][j];
+        v += __shfl_xor_sync(0xffffffffu, v, 4);
+        v += __shfl_xor_sync(0xffffffffu, v, 8);
+        v += __shfl_xor_sync(0xffffffffu, v, 16);
+        if (g == 0) red_cs[warp * K8M + 8 * i + 2 * q + j] = v;
+      }
     }
   s_data = warp_sum(s_data); s_ent = warp_sum(s_ent); s_c = warp_sum(s_c); s_d = warp_sum(s_d);
   if (lane == 0) {
-    red_sc[warp * 4 + 0] = s_data; red_sc[warp * 4 + 1] = s_ent;
-    red_sc[warp * 4 + 2] = s_c;    red_sc[warp * 4 + 3] = s_d;
+    red_sc[warp][0] = s_data; red_sc[warp][1] = s_ent; red_sc[warp][2] = s_c; red_sc[warp][3] = s_d;
   }
   __syncthreads();
-  double* zp = P.zpart + (size_t)tm.y * (K8 + VL_ZP_EXTRA);
+  const int K8rec = 8 * P.KT;
+  double* zp = P.zpart + (size_t)tm.y * (K8rec + VL_ZP_EXTRA);
   for (int k = tid; k < K8 + 4; k += VL_THREADS) {
     double v = 0.0;
     if (k < K8) {
 #pragma unroll
-      for (int wI = 0; wI < VL_THREADS / 32; ++wI) v += red_cs[wI * K8 + k];
+      for (int wI = 0; wI < VL_THREADS / 32; ++wI) v += red_cs[wI * K8M + k];
+      zp[k] = v;
     } else {
 #pragma unroll
-      for (int wI = 0; wI < VL_THREADS / 32; ++wI) v += red_sc[wI * 4 + (k - K8)];
+      for (int wI = 0; wI < VL_THREADS / 32; ++wI) v += red_sc[wI][k - K8];
+      zp[K8rec + (k - K8)] = v;
     }
-    zp[k] = v;
   }
 }
 
 // =========================================================================================
-// Scalar update, ELBO, and the loop state machine of run_cavi.
+// Scalar update, ELBO, the loop state machine of run_cavi, and the next layout.
+// One CTA per scheduled restart; plist entries are (problem, tile capacity of its class).
 // =========================================================================================
-__global__ void __launch_bounds__(256)
-vl_scalar_kernel(const VlProblem* __restrict__ probs, int* __restrict__ done_count) {
-  const VlProblem& P = probs[blockIdx.x];
+__global__ void __launch_bounds__(VL_THREADS)
+vl_scalar_kernel(const VlProblem* __restrict__ probs, const int2* __restrict__ plist,
+                 int* __restrict__ done_count, int4* __restrict__ pstat) {
+  const int2 pe = plist[blockIdx.x];
+  const VlProblem& P = probs[pe.x];
   VlState* S = P.st;
-  if (S->active == 0) return;
-  __shared__ double sh_cs[VL_MAX_CLUSTERS];
+  const int ktl = S->ktl;
+  if (S->active == 0 || ktl > pe.y || S->ktl_z > pe.y) return;
+  __shared__ double sh_cs[VL_MAX_CLUSTERS];       // column sums per slot
+  __shared__ double sh_ck[VL_MAX_CLUSTERS];       // column sums per cluster
+  __shared__ double sh_lp[VL_MAX_CLUSTERS];       // mean_log_pi per cluster
+  __shared__ int sh_slot[VL_MAX_CLUSTERS];        // cluster -> slot
   __shared__ double sh_sc[8];
-  __shared__ double sh_t[6][VL_MAX_CLUSTERS];
-  __shared__ double sh_sum[6];
+  __shared__ double sh_t[5][VL_MAX_CLUSTERS];
+  __shared__ double sh_sum[5];
   const int tid = threadIdx.x;
-  const int K = P.K, K8 = 8 * P.KT, ZS = K8 + VL_ZP_EXTRA;
+  const int K = P.K, K8rec = 8 * P.KT, ZS = K8rec + VL_ZP_EXTRA;
+  const int nlay = S->nlay, ghost = S->ghost;
 
-  if (tid < K8 + 4) {
-    // fixed-order sum over the read tiles: column sums (k < K8) and the four scalars
-    const double* zp = P.zpart + tid;   // column tid, or scalar tid - K8 stored right after the columns
+  // fixed-order sums over the read tiles (column sums per slot, four scalars) and over the
+  // position tiles (three scalars)
+  for (int c = tid; c < 8 * ktl + 7; c += VL_THREADS) {
     double v = 0.0;
-    for (int t = 0; t < P.n_ztiles; ++t) v += zp[(size_t)t * ZS];
-    if (tid < K8) sh_cs[tid] = v; else sh_sc[tid - K8] = v;
-  } else if (tid < K8 + 7) {
-    const int j = tid - K8 - 4;
-    double v = 0.0;
-    for (int t = 0; t < P.n_htiles; ++t) v += P.hpart[(size_t)t * VL_HP_STRIDE + j];
-    sh_sc[4 + j] = v;
+    if (c < 8 * ktl) {
+      for (int t = 0; t < P.n_ztiles; ++t) v += P.zpart[(size_t)t * ZS + c];
+      sh_cs[c] = v;
+    } else if (c < 8 * ktl + 4) {
+      const int j = c - 8 * ktl;
+      for (int t = 0; t < P.n_ztiles; ++t) v += P.zpart[(size_t)t * ZS + K8rec + j];
+      sh_sc[j] = v;
+    } else {
+      const int j = c - 8 * ktl - 4;
+      for (int t = 0; t < P.n_htiles; ++t) v += P.hpart[(size_t)t * VL_HP_STRIDE + j];
+      sh_sc[4 + j] = v;
+    }
   }
+  if (tid < K) sh_slot[tid] = ghost;
+  __syncthreads();
+  if (tid < nlay && tid != ghost) sh_slot[P.lay[tid]] = tid;
   __syncthreads();
 
   const double alpha0 = S->alpha0;
   if (tid < K) {
-    const double cs = sh_cs[tid];
+    const double cs = sh_cs[sh_slot[tid]];               // a dead cluster has the ghost's sum
     const double al = alpha0 + cs;                       // update_alpha, update_eqs.py:114-121
     const double lp = vl_digamma(al) - S->dsum_alpha;    // get_mean_log_pi, update_eqs.py:40-46
     P.alpha[tid] = al;
     P.mlp[tid] = lp;
+    sh_ck[tid] = cs;
+    sh_lp[tid] = lp;
     sh_t[0][tid] = (alpha0 - 1.0) * lp;
     sh_t[1][tid] = (al - 1.0) * lp;
     sh_t[2][tid] = lgamma(al);
@@ -530,15 +582,50 @@ vl_scalar_kernel(const VlProblem* __restrict__ probs, int* __restrict__ done_cou
   }
   S->iter = iter; S->converged = converged; S->n_hist = n_hist; S->n_updates = n_updates;
   S->h_last = h_last; S->h_prev = h_prev; S->status = status;
-  if (stop) {
+
+  // ---- layout of the next iteration ----
+  // z is now stored in the current layout.  A cluster stays in the layout while any read gives
+  // it a non-zero responsibility (column sum > 0; the weights are positive); all others have
+  // mean_cluster[:,k] == 0 exactly, hence identical mean_haplo rows, logits and mean_log_pi,
+  // and are represented by the single ghost slot with multiplicity.
+  int nl = nlay, kt_new = ktl, gh = ghost;
+  for (int s = 0; s < 8 * ktl; ++s) P.lay_z[s] = P.lay[s];
+  S->nlay_z = nlay; S->ghost_z = ghost;
+  if (!stop) {
+    const bool skip = S->skip != 0;
+    int s = 0, first_dead = -1, n_dead = 0;
+    for (int k = 0; k < K; ++k) {
+      if (!skip || sh_ck[k] > 0.0) {
+        P.lay[s] = k; P.gat[s] = sh_slot[k]; P.mlp_lay[s] = sh_lp[k];
+        ++s;
+      } else {
+        if (first_dead < 0) first_dead = k;
+        ++n_dead;
+      }
+    }
+    gh = -1;
+    if (n_dead > 0) {
+      gh = s;
+      P.lay[s] = first_dead; P.gat[s] = sh_slot[first_dead]; P.mlp_lay[s] = sh_lp[first_dead];
+      ++s;
+    }
+    nl = s;
+    kt_new = (nl + 7) / 8;
+    for (; s < 8 * kt_new; ++s) { P.lay[s] = -1; P.gat[s] = 0; P.mlp_lay[s] = 0.0; }
+    S->ghost_mult = (double)n_dead;
+    S->nlay = nl; S->ghost = gh;
+    S->ktl_z = ktl; S->ktl = kt_new;
+  } else {
+    S->ktl_z = ktl;
     S->active = 0;
     atomicAdd(done_count, 1);
   }
+  pstat[pe.x] = make_int4(stop ? 0 : 1, max(kt_new, ktl), nl, n_updates);
 }
 
-// One thread per problem: state_init_dict of draw_init_state (initialization.py:6-43) and the
-// first refresh of the digamma sums (cavi.py:122-128 at iter = 0).
-__global__ void vl_init_kernel(const VlProblem* __restrict__ probs, int n_probs) {
+// One thread per problem: state_init_dict of draw_init_state (initialization.py:6-43), the
+// first refresh of the digamma sums (cavi.py:122-128 at iter = 0) and the identity layout.
+__global__ void vl_init_kernel(const VlProblem* __restrict__ probs, int n_probs, int4* __restrict__ pstat) {
   const int p = blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= n_probs) return;
   const VlProblem& P = probs[p];
@@ -549,7 +636,14 @@ __global__ void vl_init_kernel(const VlProblem* __restrict__ probs, int n_probs)
   for (int k = 0; k < K; ++k) sum_alpha += alpha0;
   const double ds = vl_digamma(sum_alpha);
   const double lp0 = vl_digamma(alpha0) - ds;
-  for (int k = 0; k < K8; ++k) { P.alpha[k] = (k < K) ? alpha0 : 0.0; P.mlp[k] = (k < K) ? lp0 : 0.0; }
+  for (int k = 0; k < K8; ++k) {
+    P.alpha[k] = (k < K) ? alpha0 : 0.0;
+    P.mlp[k] = (k < K) ? lp0 : 0.0;
+    P.mlp_lay[k] = (k < K) ? lp0 : 0.0;
+    P.lay[k] = (k < K) ? k : -1;
+    P.lay_z[k] = (k < K) ? k : -1;
+    P.gat[k] = (k < K) ? k : 0;
+  }
   S->lnB0 = K * lgamma(alpha0) - lgamma(sum_alpha);
   S->betaln_ab0 = vl_betaln(S->a0, S->b0);
   S->a = S->a0; S->b = S->b0; S->c = S->c0; S->d = S->d0;
@@ -564,109 +658,202 @@ __global__ void vl_init_kernel(const VlProblem* __restrict__ probs, int n_probs)
   S->h_last = 0.0; S->h_prev = 0.0;
   S->iter = 0; S->n_updates = 0; S->n_hist = 0; S->converged = 0;
   S->status = VL_STATUS_RUNNING; S->active = 1;
+  S->ktl = P.KT; S->ktl_z = P.KT; S->nlay = K; S->ghost = -1; S->ghost_mult = 0.0; S->stalled = 0;
+  S->nlay_z = K; S->ghost_z = -1;
+  pstat[p] = make_int4(1, P.KT, K, 0);
 }
 
-// number of called (non-N) positions per read: n_non_N of lep preparation.py:13
-__global__ void vl_mcount_kernel(const uint8_t* __restrict__ codes, double* __restrict__ mcount,
-                                 int Npad, int Ls) {
+// Dense operand of one window from the raw arrays: Dm[n,l] = d at entries whose base is the
+// singled-out one of the position (d = log theta - log((1-theta)/(B-1)) for uqs, 1 for lep),
+// 0 elsewhere (other base, 'N', padding).  One thread per (read, position) of a tile.
+__global__ void vl_prepare_dm_kernel(const uint8_t* __restrict__ codes, const double* __restrict__ lt,
+                                     const double* __restrict__ lo, const uint8_t* __restrict__ maj,
+                                     double* __restrict__ dm, int N, int L, int Npad, int mode) {
+  const int pt = blockIdx.y;
+  const int n = blockIdx.x * (blockDim.x / VL_PT) + threadIdx.x / VL_PT;
+  const int p = threadIdx.x % VL_PT;
+  if (n >= Npad) return;
+  const int l = pt * VL_PT + p;
+  double v = 0.0;
+  if (n < N && l < L) {
+    const size_t off = (size_t)n * L + l;
+    const unsigned c = codes[off];
+    if (c < VL_B && c == maj[l]) v = (mode == VL_MODE_UQS) ? (lt[off] - lo[off]) : 1.0;
+  }
+  dm[((size_t)pt * Npad + n) * VL_PT + vl_dm_col(n, p)] = v;
+}
+
+// per read: number of called positions (n_non_N of lep preparation.py:13) and, for uqs, the
+// sum of log theta over them
+__global__ void vl_prepare_rows_kernel(const uint8_t* __restrict__ codes, const double* __restrict__ lt,
+                                       double* __restrict__ mcount, double* __restrict__ ltsum,
+                                       int N, int L, int Npad, int mode) {
   const int n = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (n >= Npad) return;
   const int lane = threadIdx.x & 31;
-  int cnt = 0;
-  for (int l = lane; l < Ls; l += 32) cnt += (codes[(size_t)n * Ls + l] != VL_CODE_N);
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
-  if (lane == 0) mcount[n] = (double)cnt;
+  double cnt = 0.0, s = 0.0;
+  if (n < N)
+    for (int l = lane; l < L; l += 32) {
+      const size_t off = (size_t)n * L + l;
+      if (codes[off] < VL_B) {
+        cnt += 1.0;
+        if (mode == VL_MODE_UQS) s += lt[off];
+      }
+    }
+  cnt = warp_sum(cnt); s = warp_sum(s);
+  if (lane == 0) { mcount[n] = cnt; ltsum[n] = s; }
 }
 
-// mean_haplo [Ls][B][KS] -> reference layout (K, L, B)
-__global__ void vl_export_haplo_kernel(const double* __restrict__ h, double* __restrict__ out,
-                                       int K, int L, int KS) {
-  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const size_t total = (size_t)K * L * VL_B;
-  if (i >= total) return;
-  const int b = (int)(i % VL_B);
-  const int l = (int)((i / VL_B) % L);
-  const int k = (int)(i / ((size_t)VL_B * L));
-  out[i] = h[((size_t)l * VL_B + b) * KS + k];
+__device__ __forceinline__ void build_slot_table(const VlProblem& P, int* slot_of) {
+  // cluster -> slot of the layout z and h are stored in; dead clusters share the ghost slot
+  const VlState* S = P.st;
+  for (int k = threadIdx.x; k < P.K; k += blockDim.x) slot_of[k] = S->ghost_z;
+  __syncthreads();
+  for (int s = threadIdx.x; s < S->nlay_z; s += blockDim.x)
+    if (s != S->ghost_z) slot_of[P.lay_z[s]] = s;
+  __syncthreads();
 }
 
-// merge_cluster_assignments (analyze_results.py:160-167): members added in ascending k
-__global__ void vl_merge_kernel(const double* __restrict__ z, double* __restrict__ zm,
-                                const int* __restrict__ group_of, int N, int K, int G, int KS) {
-  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= (size_t)N * KS) return;
-  const int n = (int)(i / KS), j = (int)(i % KS);
-  double s = 0.0;
-  if (j < G)
-    for (int k = 0; k < K; ++k) if (group_of[k] == j) s += z[(size_t)n * KS + k];
-  zm[i] = s;
+// mean_haplo [Ls][B][KS] in layout order -> reference layout (K, L, B)
+__global__ void vl_export_haplo_kernel(const VlProblem* __restrict__ prob, double* __restrict__ out) {
+  __shared__ int slot_of[VL_MAX_CLUSTERS];
+  const VlProblem& P = *prob;
+  build_slot_table(P, slot_of);
+  const int KS = vl_ks(P.st->ktl_z);
+  const size_t total = (size_t)P.K * P.L * VL_B;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int b = (int)(i % VL_B);
+    const int l = (int)((i / VL_B) % P.L);
+    const int k = (int)(i / ((size_t)VL_B * P.L));
+    out[i] = P.h[((size_t)l * VL_B + b) * KS + slot_of[k]];
+  }
 }
 
-template <int KT, int MODE>
-cudaError_t launch_pair(const VlProblem* probs, const int2* htiles, int n_ht, const int2* ztiles,
-                        int n_zt, bool do_h, bool do_z, cudaStream_t stream) {
-  constexpr int KS = vl_ks(KT), K8 = vl_k8(KT);
-  const size_t smem_h = (size_t)VL_STAGES * VL_H_NC * KS * 8 + 64;
-  const size_t smem_z = (size_t)VL_STAGES * VL_Z_PC * VL_B * KS * 8 + 64 + (size_t)(VL_THREADS / 32) * (K8 + 4) * 8;
-  // per-device attribute; cheap enough to set on every launch (contexts on several GPUs may
-  // live in one process)
-  cudaError_t e = cudaFuncSetAttribute(vl_haplo_kernel<KT, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_h);
+// mean_cluster [Npad][KS] in layout order -> (N, K)
+__global__ void vl_export_cluster_kernel(const VlProblem* __restrict__ prob, double* __restrict__ out) {
+  __shared__ int slot_of[VL_MAX_CLUSTERS];
+  const VlProblem& P = *prob;
+  build_slot_table(P, slot_of);
+  const int KS = vl_ks(P.st->ktl_z);
+  const size_t total = (size_t)P.N * P.K;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int k = (int)(i % P.K);
+    const size_t n = i / P.K;
+    out[i] = P.z[n * KS + slot_of[k]];
+  }
+}
+
+// merge_cluster_assignments (analyze_results.py:160-167): members added in ascending k;
+// output rows have the stride of an identity layout over G groups
+__global__ void vl_merge_kernel(const VlProblem* __restrict__ prob, double* __restrict__ zm,
+                                const int* __restrict__ group_of, int G, int KSg) {
+  __shared__ int slot_of[VL_MAX_CLUSTERS];
+  const VlProblem& P = *prob;
+  build_slot_table(P, slot_of);
+  const int KS = vl_ks(P.st->ktl_z);
+  const size_t total = (size_t)P.Npad * KSg;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const size_t n = i / KSg;
+    const int j = (int)(i % KSg);
+    double s = 0.0;
+    if (j < G && n < (size_t)P.N)
+      for (int k = 0; k < P.K; ++k) if (group_of[k] == j) s += P.z[n * KS + slot_of[k]];
+    zm[i] = s;
+  }
+}
+
+template <int NB>
+constexpr size_t smem_haplo() {
+  return (size_t)VL_STAGES * (VL_H_NC * VL_PT + VL_H_NC + VL_H_NC * vl_ks(4 * NB)) * sizeof(double);
+}
+template <int NB>
+constexpr size_t smem_cluster() {
+  return ((size_t)VL_STAGES * (VL_ZT_READS * VL_PT + VL_PT * vl_ks(4 * NB)) + (VL_THREADS / 32) * 32 * NB) * sizeof(double);
+}
+
+template <int NB, int MODE>
+cudaError_t launch_haplo(const VlProblem* probs, const int2* tiles, int n, cudaStream_t stream) {
+  // the post-loop tables T [16][K8] + Cm [16][5][K8] reuse the stage buffers
+  static_assert(smem_haplo<NB>() >= (size_t)VL_PT * 6 * 32 * NB * sizeof(double), "haplo smem union");
+  cudaError_t e = cudaFuncSetAttribute(vl_haplo_kernel<NB, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)smem_haplo<NB>());
   if (e != cudaSuccess) return e;
-  e = cudaFuncSetAttribute(vl_cluster_kernel<KT, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_z);
+  vl_haplo_kernel<NB, MODE><<<n, VL_THREADS, smem_haplo<NB>(), stream>>>(probs, tiles);
+  return cudaGetLastError();
+}
+template <int NB, int MODE>
+cudaError_t launch_cluster(const VlProblem* probs, const int2* tiles, int n, cudaStream_t stream) {
+  cudaError_t e = cudaFuncSetAttribute(vl_cluster_kernel<NB, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)smem_cluster<NB>());
   if (e != cudaSuccess) return e;
-  if (do_h && n_ht > 0) vl_haplo_kernel<KT, MODE><<<n_ht, VL_THREADS, smem_h, stream>>>(probs, htiles);
-  if (do_z && n_zt > 0) vl_cluster_kernel<KT, MODE><<<n_zt, VL_THREADS, smem_z, stream>>>(probs, ztiles);
+  vl_cluster_kernel<NB, MODE><<<n, VL_THREADS, smem_cluster<NB>(), stream>>>(probs, tiles);
   return cudaGetLastError();
 }
 
 }  // namespace
 
-int vl_supported_kt(int K) {
-  const int kts[] = {2, 4, 7, 10, 13, 16};
-  for (int kt : kts) if (K <= 8 * kt) return kt;
-  return -1;
-}
+int vl_class_of_tiles(int kt) { return kt <= 4 ? 0 : (kt <= 8 ? 1 : 2); }
+int vl_class_capacity(int cls) { return cls == 0 ? 4 : (cls == 1 ? 8 : 16); }
 
-cudaError_t vl_launch_contractions(int kt, int mode, const VlProblem* probs, const int2* htiles,
-                                   int n_ht, const int2* ztiles, int n_zt, bool do_h, bool do_z,
-                                   cudaStream_t stream) {
-#define VL_CASE(KT_)                                                                               \
-  case KT_:                                                                                        \
-    return (mode == VL_MODE_UQS)                                                                   \
-               ? launch_pair<KT_, VL_MODE_UQS>(probs, htiles, n_ht, ztiles, n_zt, do_h, do_z, stream) \
-               : launch_pair<KT_, VL_MODE_LEP>(probs, htiles, n_ht, ztiles, n_zt, do_h, do_z, stream);
-  switch (kt) {
-    VL_CASE(2) VL_CASE(4) VL_CASE(7) VL_CASE(10) VL_CASE(13) VL_CASE(16)
-    default: return cudaErrorInvalidValue;
+#define VL_DISPATCH(FN, ...)                                                             \
+  switch (cls * 2 + (mode == VL_MODE_LEP ? 1 : 0)) {                                     \
+    case 0: return FN<1, VL_MODE_UQS>(__VA_ARGS__);                                      \
+    case 1: return FN<1, VL_MODE_LEP>(__VA_ARGS__);                                      \
+    case 2: return FN<2, VL_MODE_UQS>(__VA_ARGS__);                                      \
+    case 3: return FN<2, VL_MODE_LEP>(__VA_ARGS__);                                      \
+    case 4: return FN<4, VL_MODE_UQS>(__VA_ARGS__);                                      \
+    case 5: return FN<4, VL_MODE_LEP>(__VA_ARGS__);                                      \
+    default: return cudaErrorInvalidValue;                                               \
   }
-#undef VL_CASE
+
+cudaError_t vl_launch_haplo(int cls, int mode, const VlProblem* probs, const int2* tiles, int n_tiles,
+                            cudaStream_t stream) {
+  if (n_tiles <= 0) return cudaSuccess;
+  VL_DISPATCH(launch_haplo, probs, tiles, n_tiles, stream)
 }
 
-cudaError_t vl_launch_scalar(const VlProblem* probs, int n_probs, int* done_count, cudaStream_t stream) {
-  if (n_probs > 0) vl_scalar_kernel<<<n_probs, 256, 0, stream>>>(probs, done_count);
+cudaError_t vl_launch_cluster(int cls, int mode, const VlProblem* probs, const int2* tiles, int n_tiles,
+                              cudaStream_t stream) {
+  if (n_tiles <= 0) return cudaSuccess;
+  VL_DISPATCH(launch_cluster, probs, tiles, n_tiles, stream)
+}
+
+cudaError_t vl_launch_scalar(const VlProblem* probs, const int2* plist, int n, int* done_count, int4* pstat,
+                             cudaStream_t stream) {
+  if (n > 0) vl_scalar_kernel<<<n, VL_THREADS, 0, stream>>>(probs, plist, done_count, pstat);
   return cudaGetLastError();
 }
 
-cudaError_t vl_launch_init(const VlProblem* probs, int n_probs, cudaStream_t stream) {
-  if (n_probs > 0) vl_init_kernel<<<(n_probs + 127) / 128, 128, 0, stream>>>(probs, n_probs);
+cudaError_t vl_launch_init(const VlProblem* probs, int n_probs, int4* pstat, cudaStream_t stream) {
+  if (n_probs > 0) vl_init_kernel<<<(n_probs + 127) / 128, 128, 0, stream>>>(probs, n_probs, pstat);
   return cudaGetLastError();
 }
 
-cudaError_t vl_launch_mcount(const uint8_t* codes, double* mcount, int Npad, int Ls, cudaStream_t stream) {
-  vl_mcount_kernel<<<(Npad + 3) / 4, 128, 0, stream>>>(codes, mcount, Npad, Ls);
+cudaError_t vl_launch_prepare(const uint8_t* codes, const double* lt, const double* lo, const uint8_t* maj,
+                              double* dm, double* mcount, double* ltsum, int N, int L, int Npad, int Ls,
+                              int mode, cudaStream_t stream) {
+  const dim3 grid((Npad + 15) / 16, Ls / VL_PT);
+  vl_prepare_dm_kernel<<<grid, 256, 0, stream>>>(codes, lt, lo, maj, dm, N, L, Npad, mode);
+  vl_prepare_rows_kernel<<<(Npad + 3) / 4, 128, 0, stream>>>(codes, lt, mcount, ltsum, N, L, Npad, mode);
   return cudaGetLastError();
 }
 
-cudaError_t vl_launch_export_haplo(const double* h, double* out, int K, int L, int KS, cudaStream_t stream) {
-  const size_t total = (size_t)K * L * VL_B;
-  vl_export_haplo_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(h, out, K, L, KS);
+static unsigned export_grid(size_t total) {
+  return (unsigned)std::min<size_t>((total + 255) / 256, 148 * 8);
+}
+
+cudaError_t vl_launch_export_haplo(const VlProblem* prob, double* out, size_t total, cudaStream_t stream) {
+  vl_export_haplo_kernel<<<export_grid(total), 256, 0, stream>>>(prob, out);
   return cudaGetLastError();
 }
 
-cudaError_t vl_launch_merge(const double* z, double* zm, const int* group_of, int N, int K, int G,
-                            int KS, cudaStream_t stream) {
-  const size_t total = (size_t)N * KS;
-  vl_merge_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(z, zm, group_of, N, K, G, KS);
+cudaError_t vl_launch_export_cluster(const VlProblem* prob, double* out, size_t total, cudaStream_t stream) {
+  vl_export_cluster_kernel<<<export_grid(total), 256, 0, stream>>>(prob, out);
+  return cudaGetLastError();
+}
+
+cudaError_t vl_launch_merge(const VlProblem* prob, double* zm, const int* group_of, int G, int KSg,
+                            size_t total, cudaStream_t stream) {
+  vl_merge_kernel<<<export_grid(total), 256, 0, stream>>>(prob, zm, group_of, G, KSg);
   return cudaGetLastError();
 }

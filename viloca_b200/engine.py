@@ -144,7 +144,8 @@ class WindowOutcome:
 class CaviBatch:
     """All (window, restart) problems of ``windows`` on one device."""
 
-    def __init__(self, windows: Sequence[Window], device: int = 0, stream: Optional[int] = None):
+    def __init__(self, windows: Sequence[Window], device: int = 0, stream: Optional[int] = None,
+                 skip_dead: bool = True):
         if not windows:
             raise ValueError("empty batch")
         self.windows = list(windows)
@@ -164,6 +165,8 @@ class CaviBatch:
                                             self.workspace_bytes, C.c_void_p(stream or 0)))
         self.n_problems = sum(w.n_starts for w in self.windows)
         self.launches = 0
+        if not skip_dead:
+            capi.check(capi.lib.vl_batch_set_option(self._handle, capi.OPT_SKIP_DEAD, 0))
 
     # -- lifetime ------------------------------------------------------------------------
     def close(self) -> None:
@@ -211,6 +214,12 @@ class CaviBatch:
         capi.check(capi.lib.vl_batch_profile_step(self._handle, int(n_updates), ms, cnt))
         self.launches += int(sum(cnt))
         return {k: (float(ms[i]), int(cnt[i])) for i, k in enumerate(("haplo", "cluster", "scalar"))}
+
+    def problem_stats(self) -> np.ndarray:
+        """(n_problems, 4) int32: running, 8-cluster tiles, clusters in the layout, updates."""
+        out = np.zeros((self.n_problems, 4), dtype=np.int32)
+        capi.check(capi.lib.vl_batch_problem_stats(self._handle, capi.i32_ptr(out), self.n_problems))
+        return out
 
     def last_device_ms(self) -> float:
         return float(capi.lib.vl_batch_last_device_ms(self._handle))

@@ -121,6 +121,18 @@ int vl_device_count(void);
 int vl_batch_workspace_bytes(const vl_window_desc* windows, int32_t n_windows, size_t* bytes_out);
 
 /*
+ * Host-only (no CUDA call): how the engine will lay out the reads of one window.  The
+ * one-hot-expanded read matrix has a column per (position, base); the most frequent base of
+ * every position and every other pair that at least max(2, min(64, N/128)) reads carry become
+ * dense operand columns (all columns of a position inside one 16-column tile), the remaining
+ * entries go to sparse lists.  n_cols_out: dense columns including tile padding; n_sparse_out:
+ * sparse entries; col_lb (optional, capacity 5 * length + 16 rounded up to 16): l * 5 + b per
+ * dense column, -1 for padding.  Only mode, n_reads, length and codes of the desc are read.
+ */
+int vl_window_plan(const vl_window_desc* window, int32_t* n_cols_out, int64_t* n_sparse_out,
+                   int32_t* col_lb);
+
+/*
  * Create a batch on `device` inside a caller-owned device workspace.  `stream` is a
  * cudaStream_t (NULL = the legacy default stream).  Shapes and `codes` are read here (see
  * vl_batch_workspace_bytes); the other host pointers are not.
@@ -137,6 +149,12 @@ void vl_batch_destroy(vl_batch* batch);
  * computation gives.  0 keeps all K clusters in every contraction.
  */
 #define VL_OPT_SKIP_DEAD 1
+/*
+ * VL_OPT_RESIDENT (default 1): restarts whose live clusters fit 4 tiles and whose operand fits
+ * one SM's shared memory iterate inside a persistent one-CTA-per-restart kernel; 0 keeps every
+ * restart on the three per-iteration kernels.  May be changed between runs.
+ */
+#define VL_OPT_RESIDENT 2
 int vl_batch_set_option(vl_batch* batch, int32_t option, int32_t value);
 
 /* Host -> device copy of every window's inputs and initial state; resets all restarts. */
@@ -176,8 +194,9 @@ int vl_batch_merge_haplo(vl_batch* batch, int32_t window, int32_t restart,
 
 /*
  * Like vl_batch_step, but brackets every launch with CUDA events on the launching stream and
- * returns the summed device time per kernel (ms) and the launch counts:
- * ms[0]/n[0] haplotype update, ms[1]/n[1] responsibility update, ms[2]/n[2] scalar update.
+ * returns the summed device time per kernel (ms) and the launch counts, arrays of 4:
+ * [0] haplotype update, [1] responsibility update, [2] scalar update (general path, one launch
+ * each per update), [3] resident kernel (one launch does all n_updates of its restarts).
  * Used by bench.py for the live roofline numbers; not a fast path.
  */
 int vl_batch_profile_step(vl_batch* batch, int32_t n_updates, double* ms_out, int64_t* n_out);
@@ -188,6 +207,12 @@ int vl_batch_profile_step(vl_batch* batch, int32_t n_updates, double* ms_out, in
  * slot for the dead ones), updates done.  out: [4 * n_problems].
  */
 int vl_batch_problem_stats(vl_batch* batch, int32_t* out, int32_t n_problems);
+
+/*
+ * Development aid: per-phase cycle counters of one CTA of the resident kernel (16 values).
+ * Fails unless the library was built with -DVL_RS_PROFILE (python -m viloca_b200.build --profile).
+ */
+int vl_debug_counters(uint64_t* out16, int32_t reset);
 
 /* Milliseconds the last vl_batch_run / vl_batch_step spent on the device (CUDA events). */
 double vl_batch_last_device_ms(const vl_batch* batch);

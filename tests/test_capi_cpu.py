@@ -63,21 +63,74 @@ def test_workspace_bytes_scales_and_validates():
     assert big > small > 0
     # dominant terms: one FP64 (N, L) operand + R responsibility matrices
     assert big > 8 * 1000 * 201 + 3 * 8 * 1000 * 100
-    # the minority lists are sized from the read codes: entries off the per-position majority
+    # the operand is sized from the read codes.  Rare off-majority entries go to the sparse
+    # lists (4 + 8 + 4 + 8 bytes each) ...
     rng = np.random.default_rng(0)
+    rare = np.zeros((1000, 201), dtype=np.uint8)
+    flip = rng.random(rare.shape) < 0.002
+    rare[flip] = rng.integers(1, 5, size=int(flip.sum()))
+    descs = (capi.WindowDesc * 1)(_desc(n=1000, l=201, k=100, r=3, codes=rare))
+    assert capi.lib.vl_batch_workspace_bytes(descs, 1, C.byref(nbytes)) == 0
+    assert abs((nbytes.value - big) - 24 * int(flip.sum())) <= 2048
+    # ... while (position, base) pairs that many reads carry become extra dense columns
     noisy = np.zeros((1000, 201), dtype=np.uint8)
     flip = rng.random(noisy.shape) < 0.2
     noisy[flip] = rng.integers(1, 5, size=int(flip.sum()))
     descs = (capi.WindowDesc * 1)(_desc(n=1000, l=201, k=100, r=3, codes=noisy))
     assert capi.lib.vl_batch_workspace_bytes(descs, 1, C.byref(nbytes)) == 0
-    extra = nbytes.value - big
-    nnz = int(flip.sum())
-    assert abs(extra - 24 * nnz) <= 2048      # 4 + 8 + 4 + 8 bytes per entry, 256-byte aligned arrays
+    assert nbytes.value - big > 4 * 201 * 1000 * 8
     for bad in (_desc(k=capi.MAX_CLUSTERS + 1), _desc(n=0), _desc(mode=7), _desc(max_iter=0), _desc(codes=None)):
         descs = (capi.WindowDesc * 1)(bad)
         assert capi.lib.vl_batch_workspace_bytes(descs, 1, C.byref(nbytes)) != 0
         assert len(capi.lib.vl_last_error()) > 0
     assert capi.lib.vl_batch_workspace_bytes(None, 0, C.byref(nbytes)) != 0
+
+
+def _plan_numpy(codes):
+    """NumPy restatement of the dense-column rule documented at vl_window_plan."""
+    n, length = codes.shape
+    cnt = np.stack([(codes == b).sum(axis=0) for b in range(5)], axis=1)
+    thr = min(max(n // 128, 2), 64)
+    cols, in_tile = [], 0
+    for l in range(length):
+        best = int(np.argmax(cnt[l]))
+        bases = [b for b in range(5) if b == best or cnt[l, b] >= thr]
+        if len(cols) % 16 + len(bases) > 16 or (len(cols) % 16 == 0 and in_tile):
+            cols += [-1] * (-len(cols) % 16)
+            in_tile = 0
+        cols += [l * 5 + b for b in bases]
+        in_tile += 1
+    cols += [-1] * (-len(cols) % 16)
+    dense = set(c for c in cols if c >= 0)
+    sparse = sum(int(cnt[l, b]) for l in range(length) for b in range(5) if l * 5 + b not in dense)
+    return cols, sparse
+
+
+@pytest.mark.parametrize("n,length,p_err", [(300, 201, 0.01), (40, 16, 0.2), (1000, 57, 0.05), (5, 1, 0.5),
+                                            (700, 33, 0.6)])
+def test_window_plan_matches_documented_rule(n, length, p_err):
+    rng = np.random.default_rng(n + length)
+    codes = np.tile(rng.integers(0, 4, size=length).astype(np.uint8), (n, 1))
+    flip = rng.random(codes.shape) < p_err
+    codes[flip] = rng.integers(0, 5, size=int(flip.sum()))
+    codes[rng.random(codes.shape) < 0.1] = 255
+    if length > 3:
+        codes[:, 2] = 255                         # a position no read covers still gets its column
+    d = _desc(n=n, l=length, codes=np.ascontiguousarray(codes))
+    ncols, nsp = C.c_int32(0), C.c_int64(0)
+    cap = (5 * length + 31) // 16 * 16
+    col_lb = np.full(cap, -7, dtype=np.int32)
+    assert capi.lib.vl_window_plan(C.byref(d), C.byref(ncols), C.byref(nsp), capi.i32_ptr(col_lb)) == 0
+    exp_cols, exp_sparse = _plan_numpy(codes)
+    assert ncols.value == len(exp_cols) and ncols.value % 16 == 0
+    assert col_lb[:ncols.value].tolist() == exp_cols
+    assert nsp.value == exp_sparse
+    # every position owns at least one column and its columns share a tile
+    tiles = {}
+    for j, lb in enumerate(exp_cols):
+        if lb >= 0:
+            tiles.setdefault(lb // 5, set()).add(j // 16)
+    assert sorted(tiles) == list(range(length)) and all(len(t) == 1 for t in tiles.values())
 
 
 def test_create_rejects_bad_workspace():

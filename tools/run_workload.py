@@ -1,0 +1,23 @@
+"""One upload + run + fetch of a synthetic workload (profiling target for ncu).
+
+    python tools/run_workload.py [workload] [n_windows] [repeats]
+"""
+import os
+import sys
+import time
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from viloca_b200 import engine, synthetic  # noqa: E402
+
+name = sys.argv[1] if len(sys.argv) > 1 else "hiv5k_uqs"
+nw = int(sys.argv[2]) if len(sys.argv) > 2 and int(sys.argv[2]) > 0 else None
+rep = int(sys.argv[3]) if len(sys.argv) > 3 else 1
+wins = [w.pin() for w in synthetic.make_workload(name, nw)]
+resident = os.environ.get("VL_RESIDENT", "1") != "0"
+with engine.CaviBatch(wins, resident=resident) as b:
+    for _ in range(rep):
+        t0 = time.perf_counter(); b.upload(); t1 = time.perf_counter()
+        n = b.run(); t2 = time.perf_counter()
+        out = b.fetch(); t3 = time.perf_counter()
+        print(f"upload {1e3*(t1-t0):.1f} ms  run {1e3*(t2-t1):.1f} ms (device {b.last_device_ms():.1f} ms, {n} launches)"
+              f"  fetch {1e3*(t3-t2):.1f} ms  windows {len(wins)}", flush=True)

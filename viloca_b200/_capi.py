@@ -12,6 +12,7 @@ from . import build as _build
 
 ABI_VERSION = 2
 OPT_SKIP_DEAD = 1
+OPT_RESIDENT = 2
 N_BASES = 5
 CODE_N = 255
 MAX_CLUSTERS = 128
@@ -61,6 +62,7 @@ EXPORTS = (
     "vl_batch_create", "vl_batch_destroy", "vl_batch_upload", "vl_batch_run", "vl_batch_step",
     "vl_batch_fetch", "vl_batch_set_state", "vl_batch_merge_haplo", "vl_batch_profile_step",
     "vl_batch_last_device_ms", "vl_batch_set_option", "vl_batch_problem_stats",
+    "vl_window_plan", "vl_debug_counters",
 )
 
 
@@ -94,6 +96,8 @@ def _load():
     lib.vl_batch_set_state.argtypes = [C.c_void_p, C.c_int32, C.c_int32, _f64p, _f64p, _f64p, C.c_int32]
     lib.vl_batch_merge_haplo.argtypes = [C.c_void_p, C.c_int32, C.c_int32, _i32p, C.c_int32, _f64p, _f64p]
     lib.vl_batch_profile_step.argtypes = [C.c_void_p, C.c_int32, _f64p, C.POINTER(C.c_int64)]
+    lib.vl_window_plan.argtypes = [C.POINTER(WindowDesc), _i32p, C.POINTER(C.c_int64), _i32p]
+    lib.vl_debug_counters.argtypes = [C.POINTER(C.c_uint64), C.c_int32]
     lib.vl_batch_set_option.argtypes = [C.c_void_p, C.c_int32, C.c_int32]
     lib.vl_batch_problem_stats.argtypes = [C.c_void_p, _i32p, C.c_int32]
     lib.vl_batch_last_device_ms.argtypes = [C.c_void_p]

@@ -14,8 +14,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB_DIR = os.path.join(HERE, "lib")
 LIB_PATH = os.path.join(LIB_DIR, "libviloca_b200.so")
-SOURCES = ["vl_kernels.cu", "vl_api.cu"]
-HEADERS = ["vl_device.cuh", "vl_launch.h", os.path.join("..", "..", "include", "viloca_b200.h")]
+SOURCES = ["vl_kernels.cu", "vl_resident.cu", "vl_api.cu"]
+HEADERS = ["vl_device.cuh", "vl_cavi.cuh", "vl_launch.h", os.path.join("..", "..", "include", "viloca_b200.h")]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
     "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden",
@@ -36,7 +36,8 @@ def _stale(target: str, deps: list[str]) -> bool:
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
+def build(force: bool = False, verbose: bool = False, profile: bool = False) -> str:
+    """``profile=True`` compiles the resident kernel's cycle counters in (vl_debug_counters)."""
     os.makedirs(LIB_DIR, exist_ok=True)
     headers = [os.path.normpath(os.path.join(CSRC, h)) for h in HEADERS]
     objs = []
@@ -45,7 +46,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
         obj = os.path.join(LIB_DIR, src.replace(".cu", ".o"))
         objs.append(obj)
         if force or _stale(obj, [src_path] + headers):
-            cmd = [_nvcc()] + NVCC_FLAGS + ["-c", src_path, "-o", obj]
+            cmd = [_nvcc()] + NVCC_FLAGS + (["-DVL_RS_PROFILE"] if profile else []) + ["-c", src_path, "-o", obj]
             if verbose:
                 cmd.insert(1, "-Xptxas=-v")
                 print(" ".join(cmd), file=sys.stderr)
@@ -59,4 +60,5 @@ def build(force: bool = False, verbose: bool = False) -> str:
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    print(build(force="--force" in sys.argv or "--profile" in sys.argv, verbose="-v" in sys.argv,
+                profile="--profile" in sys.argv))

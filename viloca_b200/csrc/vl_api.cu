@@ -42,7 +42,8 @@ struct WindowLayout {
   int Npad, Ls, KT, KS, K8, n_ztiles, n_htiles;
   double alpha0, conv_thres;
   size_t nnz_cap;
-  size_t dm, w, ltsum, mcount, ref, maj, sr_ptr, sr_idx, sr_d, sp_ptr, sp_n, sp_wd;
+  int NCs;
+  size_t dm, w, ltsum, mcount, ref, col_lb, poscol, tile_pos, sr_ptr, sr_idx, sr_d, sp_ptr, sp_n, sp_wd;
   std::vector<RestartLayout> rs;
   int first_problem;
 };
@@ -52,7 +53,7 @@ struct Layout {
   int n_problems = 0;
   size_t data_begin = 0, data_end = 0;   // zero-filled on upload
   size_t probs = 0, states = 0, done = 0, pstat = 0;
-  size_t htiles = 0, ztiles = 0, plist = 0;
+  size_t htiles = 0, ztiles = 0, plist = 0, rlist = 0;
   size_t raw_codes = 0, raw_lt = 0, raw_lo = 0;      // staging of one window's raw arrays
   size_t export_h = 0, export_z = 0;
   size_t tmp_z = 0, tmp_h = 0, tmp_g = 0, tmp_gm = 0, tmp_hpart = 0, tmp_group = 0, tmp_prob = 0,
@@ -61,17 +62,22 @@ struct Layout {
   size_t n_htiles_total = 0, n_ztiles_total = 0;
 };
 
-// What the kernels need to know about the bases of one window: the base singled out per
-// position (most frequent called base, first on ties) and the entries that carry another
-// base, listed by read (ascending position) and by (position, base) (ascending read).
+// What the kernels need to know about the bases of one window (vl_device.cuh): which
+// (position, base) pairs are dense columns of the operand, and the remaining entries listed by
+// read (ascending position) and by (position, base) (ascending read).
 struct WindowAnalysis {
-  std::vector<uint8_t> maj;
+  int NCs = 0;                          // dense columns incl. padding, a multiple of 16
+  std::vector<int> col_lb, poscol, tile_pos;
   std::vector<int> sr_ptr, sr_idx, sp_ptr, sp_n;
   std::vector<double> sr_d, sp_wd;
-  size_t nnz = 0;
+  size_t nnz = 0;                       // sparse entries
 };
 
-void majority_bases(const vl_window_desc& d, int Ls, std::vector<uint8_t>& maj) {
+// Dense columns: the most frequent called base of every position (first on ties; base 0 if no
+// read covers the position) and every other pair carried by at least `thr` reads, where thr
+// grows with N: a dense column costs O(N) per contraction, a sparse entry one gathered row.
+// The columns of a position are consecutive and never straddle a 16-column tile.
+void plan_columns(const vl_window_desc& d, int Ls, WindowAnalysis& A) {
   const int N = d.n_reads, L = d.length;
   std::vector<int> cnt((size_t)L * VL_N_BASES, 0);
   for (int n = 0; n < N; ++n) {
@@ -79,29 +85,43 @@ void majority_bases(const vl_window_desc& d, int Ls, std::vector<uint8_t>& maj) 
     for (int l = 0; l < L; ++l)
       if (row[l] < VL_N_BASES) ++cnt[(size_t)l * VL_N_BASES + row[l]];
   }
-  maj.assign(Ls, 0);
+  const int thr = std::min(std::max(N / 128, 2), 64);
+  A.col_lb.clear(); A.tile_pos.clear();
+  A.poscol.assign((size_t)Ls * VL_N_BASES, -1);
+  std::vector<int> tile_positions;
+  auto close_tile = [&]() {
+    while (A.col_lb.size() % VL_PT) A.col_lb.push_back(-1);
+    tile_positions.resize(VL_PT, -1);
+    A.tile_pos.insert(A.tile_pos.end(), tile_positions.begin(), tile_positions.end());
+    tile_positions.clear();
+  };
+  size_t sparse = 0;
   for (int l = 0; l < L; ++l) {
+    const int* c = &cnt[(size_t)l * VL_N_BASES];
     int best = 0;
-    for (int b = 1; b < VL_N_BASES; ++b)
-      if (cnt[(size_t)l * VL_N_BASES + b] > cnt[(size_t)l * VL_N_BASES + best]) best = b;
-    maj[l] = (uint8_t)best;
+    for (int b = 1; b < VL_N_BASES; ++b) if (c[b] > c[best]) best = b;
+    int bases[VL_N_BASES], nb = 0;
+    for (int b = 0; b < VL_N_BASES; ++b) {
+      if (b == best || c[b] >= thr) bases[nb++] = b;
+      else sparse += c[b];
+    }
+    const size_t used = A.col_lb.size() % VL_PT;
+    if ((used == 0 && !tile_positions.empty()) || used + nb > VL_PT) close_tile();
+    for (int i = 0; i < nb; ++i) {
+      A.poscol[(size_t)l * VL_N_BASES + bases[i]] = (int)A.col_lb.size();
+      A.col_lb.push_back(l * VL_N_BASES + bases[i]);
+    }
+    tile_positions.push_back(l);
   }
-}
-
-size_t count_minority(const vl_window_desc& d, const std::vector<uint8_t>& maj) {
-  const int N = d.n_reads, L = d.length;
-  size_t nnz = 0;
-  for (int n = 0; n < N; ++n) {
-    const uint8_t* row = d.codes + (size_t)n * L;
-    for (int l = 0; l < L; ++l) nnz += (row[l] < VL_N_BASES && row[l] != maj[l]);
-  }
-  return nnz;
+  if (!tile_positions.empty()) close_tile();
+  A.NCs = (int)A.col_lb.size();
+  A.nnz = sparse;
 }
 
 void analyze_window(const vl_window_desc& d, int Npad, int Ls, WindowAnalysis& A) {
   const int N = d.n_reads, L = d.length;
   const bool uqs = d.mode == VL_MODE_UQS;
-  majority_bases(d, Ls, A.maj);
+  plan_columns(d, Ls, A);
   A.sr_ptr.assign((size_t)Npad + 1, 0);
   A.sp_ptr.assign((size_t)Ls * VL_N_BASES + 1, 0);
   A.sr_idx.clear(); A.sr_d.clear();
@@ -109,7 +129,7 @@ void analyze_window(const vl_window_desc& d, int Npad, int Ls, WindowAnalysis& A
     const uint8_t* row = d.codes + (size_t)n * L;
     for (int l = 0; l < L; ++l) {
       const uint8_t c = row[l];
-      if (c < VL_N_BASES && c != A.maj[l]) {
+      if (c < VL_N_BASES && A.poscol[(size_t)l * VL_N_BASES + c] < 0) {
         const size_t off = (size_t)n * L + l;
         A.sr_idx.push_back(l * VL_N_BASES + c);
         A.sr_d.push_back(uqs ? d.log_hit[off] - d.log_off[off] : 1.0);
@@ -143,7 +163,7 @@ int build_layout(const vl_window_desc* w, int n, Layout& lay, std::string& err) 
   lay.data_begin = 0;
   size_t max_nl = 0, max_exp_h = 0, max_exp_z = 0, max_z = 0, max_h = 0, max_gm = 0;
   int max_htiles = 0;
-  std::vector<uint8_t> maj;
+  WindowAnalysis plan;
   for (int i = 0; i < n; ++i) {
     const vl_window_desc& d = w[i];
     WindowLayout& W = lay.wins[i];
@@ -161,16 +181,18 @@ int build_layout(const vl_window_desc* w, int n, Layout& lay, std::string& err) 
     W.Ls = round_up(W.L, VL_PT);
     W.KT = (W.K + 7) / 8; W.KS = vl_ks(W.KT); W.K8 = 8 * W.KT;
     W.n_ztiles = W.Npad / VL_ZT_READS;
-    W.n_htiles = W.Ls / VL_PT;
-    majority_bases(d, W.Ls, maj);
-    W.nnz_cap = std::max<size_t>(count_minority(d, maj), 1);
-    const size_t nl = (size_t)W.Npad * W.Ls;
-    W.dm = take(nl * 8);
+    plan_columns(d, W.Ls, plan);
+    W.NCs = plan.NCs;
+    W.n_htiles = W.NCs / VL_PT;
+    W.nnz_cap = std::max<size_t>(plan.nnz, 1);
+    W.dm = take((size_t)W.Npad * W.NCs * 8);
     W.w = take((size_t)W.Npad * 8);
     W.ltsum = take((size_t)W.Npad * 8);
     W.mcount = take((size_t)W.Npad * 8);
     W.ref = take((size_t)W.Ls);
-    W.maj = take((size_t)W.Ls);
+    W.col_lb = take((size_t)W.NCs * 4);
+    W.poscol = take((size_t)W.Ls * VL_N_BASES * 4);
+    W.tile_pos = take((size_t)W.NCs * 4);
     W.sr_ptr = take(((size_t)W.Npad + 1) * 4);
     W.sr_idx = take(W.nnz_cap * 4);
     W.sr_d = take(W.nnz_cap * 8);
@@ -184,7 +206,7 @@ int build_layout(const vl_window_desc* w, int n, Layout& lay, std::string& err) 
       RL.z = take((size_t)W.Npad * W.KS * 8);
       RL.h = take((size_t)W.Ls * VL_N_BASES * W.KS * 8);
       RL.g = take((size_t)W.Ls * VL_N_BASES * W.KS * 8);
-      RL.gm = take((size_t)W.Ls * W.KS * 8);
+      RL.gm = take((size_t)W.NCs * W.KS * 8);
       RL.zpart = take((size_t)W.n_ztiles * (W.K8 + VL_ZP_EXTRA) * 8);
       RL.hpart = take((size_t)W.n_htiles * VL_HP_STRIDE * 8);
       RL.alpha = take((size_t)W.K8 * 8);
@@ -203,7 +225,7 @@ int build_layout(const vl_window_desc* w, int n, Layout& lay, std::string& err) 
     max_exp_z = std::max(max_exp_z, (size_t)W.N * W.K * 8);
     max_z = std::max(max_z, (size_t)W.Npad * W.KS * 8);
     max_h = std::max(max_h, (size_t)W.Ls * VL_N_BASES * W.KS * 8);
-    max_gm = std::max(max_gm, (size_t)W.Ls * W.KS * 8);
+    max_gm = std::max(max_gm, (size_t)W.NCs * W.KS * 8);
     max_htiles = std::max(max_htiles, W.n_htiles);
     lay.n_htiles_total += (size_t)W.n_htiles * W.R;
     lay.n_ztiles_total += (size_t)W.n_ztiles * W.R;
@@ -216,6 +238,7 @@ int build_layout(const vl_window_desc* w, int n, Layout& lay, std::string& err) 
   lay.htiles = take(lay.n_htiles_total * sizeof(int2));
   lay.ztiles = take(lay.n_ztiles_total * sizeof(int2));
   lay.plist = take((size_t)lay.n_problems * sizeof(int2));
+  lay.rlist = take((size_t)lay.n_problems * sizeof(int));
   lay.raw_codes = take(max_nl);
   lay.raw_lt = take(max_nl * 8);
   lay.raw_lo = take(max_nl * 8);
@@ -251,11 +274,14 @@ struct vl_batch {
   std::vector<int4> pstat;             // host mirror: (running, tiles needed, valid slots, updates)
   // pinned staging of the per-chunk schedule
   int2* h_htiles = nullptr; int2* h_ztiles = nullptr; int2* h_plist = nullptr; int4* h_pstat = nullptr;
+  int* h_rlist = nullptr;
+  int n_res[2] = {};                   // restarts scheduled on the resident kernel, per mode
+  size_t off_res[2] = {}, smem_res[2] = {};
   int n_ht[VL_N_CLASSES][2] = {}, n_zt[VL_N_CLASSES][2] = {};
   size_t off_ht[VL_N_CLASSES][2] = {}, off_zt[VL_N_CLASSES][2] = {};
   int n_sched = 0;
   bool sched_dirty = true;
-  int skip_dead = 1;
+  int skip_dead = 1, resident = 1;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   double last_ms = 0.0;
   bool uploaded = false;
@@ -269,21 +295,31 @@ struct vl_batch {
 
 namespace {
 
-// Tile maps of the still-running restarts, grouped by kernel class (layout width) and mode.
+// Where the still-running restarts go next: the resident kernel (narrow layouts that fit one
+// SM's shared memory) or the general path, there grouped by kernel class (layout width) and mode.
 int schedule(vl_batch* b) {
   const Layout& L = b->lay;
   std::vector<int2> ht[VL_N_CLASSES][2], zt[VL_N_CLASSES][2];
+  std::vector<int> res[2];
+  const size_t smem_limit = vl_resident_smem_limit();
   b->n_sched = 0;
+  b->smem_res[0] = b->smem_res[1] = 0;
   for (int p : b->order) {
     const int4 st = b->pstat[p];
     if (st.x == 0) continue;
     const VlProblem& P = b->probs[p];
     const int cls = vl_class_of_tiles(st.y), m = P.mode == VL_MODE_LEP ? 1 : 0;
+    const int nct = P.NCs / VL_PT;
+    if (b->resident && st.y <= VL_RS_MAX_KT && nct <= VL_RS_MAX_CT && vl_resident_smem_bytes(nct, st.y) <= smem_limit) {
+      res[m].push_back(p);
+      b->smem_res[m] = std::max(b->smem_res[m], vl_resident_smem_bytes(nct, st.y));
+      continue;
+    }
     for (int t = 0; t < P.n_htiles; ++t) ht[cls][m].push_back(make_int2(p, t));
     for (int t = 0; t < P.n_ztiles; ++t) zt[cls][m].push_back(make_int2(p, t));
     b->h_plist[b->n_sched++] = make_int2(p, vl_class_capacity(cls));
   }
-  size_t ho = 0, zo = 0;
+  size_t ho = 0, zo = 0, ro = 0;
   for (int c = 0; c < VL_N_CLASSES; ++c)
     for (int m = 0; m < 2; ++m) {
       b->n_ht[c][m] = (int)ht[c][m].size(); b->off_ht[c][m] = ho;
@@ -292,11 +328,29 @@ int schedule(vl_batch* b) {
       std::copy(zt[c][m].begin(), zt[c][m].end(), b->h_ztiles + zo);
       ho += ht[c][m].size(); zo += zt[c][m].size();
     }
+  for (int m = 0; m < 2; ++m) {
+    b->n_res[m] = (int)res[m].size(); b->off_res[m] = ro;
+    std::copy(res[m].begin(), res[m].end(), b->h_rlist + ro);
+    ro += res[m].size();
+  }
   cudaStream_t s = b->stream;
   if (ho) VL_CUDA(cudaMemcpyAsync(b->dev<int2>(L.htiles), b->h_htiles, ho * sizeof(int2), cudaMemcpyHostToDevice, s));
   if (zo) VL_CUDA(cudaMemcpyAsync(b->dev<int2>(L.ztiles), b->h_ztiles, zo * sizeof(int2), cudaMemcpyHostToDevice, s));
   if (b->n_sched) VL_CUDA(cudaMemcpyAsync(b->dev<int2>(L.plist), b->h_plist, (size_t)b->n_sched * sizeof(int2), cudaMemcpyHostToDevice, s));
+  if (ro) VL_CUDA(cudaMemcpyAsync(b->dev<int>(L.rlist), b->h_rlist, ro * sizeof(int), cudaMemcpyHostToDevice, s));
   b->sched_dirty = false;
+  return 0;
+}
+
+// n_iter updates of the restarts scheduled on the resident kernel (each CTA iterates on its own)
+int launch_resident(vl_batch* b, int n_iter, int64_t* launches) {
+  const Layout& L = b->lay;
+  for (int m = 0; m < 2; ++m)
+    if (b->n_res[m] > 0) {
+      VL_CUDA(vl_launch_resident(m ? VL_MODE_LEP : VL_MODE_UQS, b->d_probs(), b->dev<int>(L.rlist) + b->off_res[m],
+                                 b->n_res[m], n_iter, b->smem_res[m], b->d_done(), b->d_pstat(), b->stream));
+      *launches += 1;
+    }
   return 0;
 }
 
@@ -322,6 +376,7 @@ int launch_phase(vl_batch* b, int phase, int64_t* launches) {
 }
 
 int run_iterations(vl_batch* b, int n_iter, int64_t* launches) {
+  if (launch_resident(b, n_iter, launches)) return 1;
   for (int it = 0; it < n_iter; ++it)
     for (int phase = 0; phase < 3; ++phase)
       if (launch_phase(b, phase, launches)) return 1;
@@ -336,7 +391,7 @@ int sync_status(vl_batch* b, int* n_running) {
   int running = 0;
   for (int p = 0; p < np; ++p) {
     const int4 now = b->h_pstat[p], old = b->pstat[p];
-    if (now.x != old.x || vl_class_of_tiles(now.y) != vl_class_of_tiles(old.y)) b->sched_dirty = true;
+    if (now.x != old.x || now.y != old.y) b->sched_dirty = true;
     b->pstat[p] = now;
     running += now.x;
   }
@@ -371,6 +426,17 @@ int vl_batch_workspace_bytes(const vl_window_desc* windows, int32_t n_windows, s
   std::string err;
   if (build_layout(windows, n_windows, lay, err)) return fail(err);
   *bytes_out = lay.total;
+  return 0;
+}
+
+int vl_window_plan(const vl_window_desc* w, int32_t* n_cols_out, int64_t* n_sparse_out, int32_t* col_lb) {
+  if (!w || !w->codes) return fail("window or its codes is NULL");
+  if (w->n_reads <= 0 || w->length <= 0) return fail("n_reads and length must be positive");
+  WindowAnalysis A;
+  plan_columns(*w, round_up(w->length, VL_PT), A);
+  if (n_cols_out) *n_cols_out = A.NCs;
+  if (n_sparse_out) *n_sparse_out = (int64_t)A.nnz;
+  if (col_lb) std::copy(A.col_lb.begin(), A.col_lb.end(), col_lb);
   return 0;
 }
 
@@ -412,16 +478,16 @@ int vl_batch_create(vl_batch** out, int32_t device, const vl_window_desc* window
     for (int r = 0; r < W.R; ++r) {
       VlProblem& P = b->probs[W.first_problem + r];
       P.mode = W.mode; P.N = W.N; P.L = W.L; P.K = W.K;
-      P.Npad = W.Npad; P.Ls = W.Ls; P.KT = W.KT; P.pad0 = 0;
+      P.Npad = W.Npad; P.Ls = W.Ls; P.KT = W.KT; P.NCs = W.NCs;
       P.n_ztiles = W.n_ztiles; P.n_htiles = W.n_htiles; P.window = (int)i; P.restart = r;
       P.dm = b->dev<double>(W.dm);
       P.w = b->dev<double>(W.w);
       P.ltsum = b->dev<double>(W.ltsum);
       P.mcount = b->dev<double>(W.mcount);
       P.ref = b->dev<uint8_t>(W.ref);
-      P.maj = b->dev<uint8_t>(W.maj);
+      P.col_lb = b->dev<int>(W.col_lb); P.poscol = b->dev<int>(W.poscol); P.tile_pos = b->dev<int>(W.tile_pos);
       P.sr_ptr = b->dev<int>(W.sr_ptr); P.sr_idx = b->dev<int>(W.sr_idx); P.sr_d = b->dev<double>(W.sr_d);
-      P.sp_ptr = b->dev<int>(W.sp_ptr); P.sp_nc = b->dev<int>(W.sp_n); P.sp_wd = b->dev<double>(W.sp_wd);
+      P.sp_ptr = b->dev<int>(W.sp_ptr); P.sp_n = b->dev<int>(W.sp_n); P.sp_wd = b->dev<double>(W.sp_wd);
       const RestartLayout& RL = W.rs[r];
       P.z = b->dev<double>(RL.z); P.h = b->dev<double>(RL.h);
       P.g = b->dev<double>(RL.g); P.gm = b->dev<double>(RL.gm);
@@ -449,6 +515,7 @@ int vl_batch_create(vl_batch** out, int32_t device, const vl_window_desc* window
   VL_CREATE_CUDA(cudaMallocHost(reinterpret_cast<void**>(&b->h_ztiles), std::max<size_t>(L.n_ztiles_total, 1) * sizeof(int2)));
   VL_CREATE_CUDA(cudaMallocHost(reinterpret_cast<void**>(&b->h_plist), (size_t)L.n_problems * sizeof(int2)));
   VL_CREATE_CUDA(cudaMallocHost(reinterpret_cast<void**>(&b->h_pstat), (size_t)L.n_problems * sizeof(int4)));
+  VL_CREATE_CUDA(cudaMallocHost(reinterpret_cast<void**>(&b->h_rlist), (size_t)L.n_problems * sizeof(int)));
   VL_CREATE_CUDA(cudaEventCreate(&b->ev0));
   VL_CREATE_CUDA(cudaEventCreate(&b->ev1));
   VL_CREATE_CUDA(cudaMemcpyAsync(b->d_probs(), b->probs.data(), b->probs.size() * sizeof(VlProblem),
@@ -466,6 +533,7 @@ void vl_batch_destroy(vl_batch* b) {
   if (b->h_ztiles) cudaFreeHost(b->h_ztiles);
   if (b->h_plist) cudaFreeHost(b->h_plist);
   if (b->h_pstat) cudaFreeHost(b->h_pstat);
+  if (b->h_rlist) cudaFreeHost(b->h_rlist);
   if (b->ev0) cudaEventDestroy(b->ev0);
   if (b->ev1) cudaEventDestroy(b->ev1);
   delete b;
@@ -474,6 +542,7 @@ void vl_batch_destroy(vl_batch* b) {
 int vl_batch_set_option(vl_batch* b, int32_t option, int32_t value) {
   if (!b) return fail("batch is NULL");
   if (option == VL_OPT_SKIP_DEAD) { b->skip_dead = value ? 1 : 0; return 0; }
+  if (option == VL_OPT_RESIDENT) { b->resident = value ? 1 : 0; b->sched_dirty = true; return 0; }
   return fail("unknown option");
 }
 
@@ -496,10 +565,10 @@ int vl_batch_upload(vl_batch* b, const vl_window_desc* windows, int32_t n_window
     const bool uqs = W.mode == VL_MODE_UQS;
     if (uqs && (!d.log_hit || !d.log_off)) return fail("uqs window without log_hit/log_off");
     analyze_window(d, W.Npad, W.Ls, A);
-    if (A.nnz > W.nnz_cap) {
-      char buf[200];
-      snprintf(buf, sizeof buf, "window %d: %zu minority entries but the batch was created for %zu; create a new batch for these reads",
-               i, A.nnz, W.nnz_cap);
+    if (A.nnz > W.nnz_cap || A.NCs != W.NCs) {
+      char buf[240];
+      snprintf(buf, sizeof buf, "window %d: %d dense columns / %zu sparse entries, but the batch was created for %d / %zu; "
+               "create a new batch for these reads", i, A.NCs, A.nnz, W.NCs, W.nnz_cap);
       return fail(buf);
     }
     const size_t nl = (size_t)W.N * W.L;
@@ -513,7 +582,9 @@ int vl_batch_upload(vl_batch* b, const vl_window_desc* windows, int32_t n_window
     ref.assign(W.Ls, VL_CODE_N);
     std::memcpy(ref.data(), d.ref_codes, W.L);
     VL_CUDA(cudaMemcpyAsync(b->ws + W.ref, ref.data(), W.Ls, cudaMemcpyHostToDevice, s));
-    VL_CUDA(cudaMemcpyAsync(b->ws + W.maj, A.maj.data(), W.Ls, cudaMemcpyHostToDevice, s));
+    VL_CUDA(cudaMemcpyAsync(b->ws + W.col_lb, A.col_lb.data(), (size_t)W.NCs * 4, cudaMemcpyHostToDevice, s));
+    VL_CUDA(cudaMemcpyAsync(b->ws + W.poscol, A.poscol.data(), A.poscol.size() * 4, cudaMemcpyHostToDevice, s));
+    VL_CUDA(cudaMemcpyAsync(b->ws + W.tile_pos, A.tile_pos.data(), (size_t)W.NCs * 4, cudaMemcpyHostToDevice, s));
     VL_CUDA(cudaMemcpyAsync(b->ws + W.w, d.weights, (size_t)W.N * 8, cudaMemcpyHostToDevice, s));
     VL_CUDA(cudaMemcpyAsync(b->ws + W.sr_ptr, A.sr_ptr.data(), A.sr_ptr.size() * 4, cudaMemcpyHostToDevice, s));
     VL_CUDA(cudaMemcpyAsync(b->ws + W.sp_ptr, A.sp_ptr.data(), A.sp_ptr.size() * 4, cudaMemcpyHostToDevice, s));
@@ -524,8 +595,8 @@ int vl_batch_upload(vl_batch* b, const vl_window_desc* windows, int32_t n_window
       VL_CUDA(cudaMemcpyAsync(b->ws + W.sp_wd, A.sp_wd.data(), A.nnz * 8, cudaMemcpyHostToDevice, s));
     }
     VL_CUDA(vl_launch_prepare(b->dev<uint8_t>(L.raw_codes), b->dev<double>(L.raw_lt), b->dev<double>(L.raw_lo),
-                              b->dev<uint8_t>(W.maj), b->dev<double>(W.dm), b->dev<double>(W.mcount),
-                              b->dev<double>(W.ltsum), W.N, W.L, W.Npad, W.Ls, W.mode, s));
+                              b->dev<int>(W.col_lb), b->dev<double>(W.dm), b->dev<double>(W.mcount),
+                              b->dev<double>(W.ltsum), W.N, W.L, W.Npad, W.NCs, W.mode, s));
     for (int r = 0; r < W.R; ++r) {
       VL_CUDA(cudaMemcpy2DAsync(b->ws + W.rs[r].z, (size_t)W.KS * 8, d.init_cluster + (size_t)r * W.N * W.K,
                                 (size_t)W.K * 8, (size_t)W.K * 8, W.N, cudaMemcpyHostToDevice, s));
@@ -558,10 +629,12 @@ int vl_batch_run(vl_batch* b, int64_t* n_launches_out) {
   for (const WindowLayout& W : b->lay.wins) max_iter = std::max(max_iter, W.max_iter);
   VL_CUDA(cudaEventRecord(b->ev0, b->stream));
   int running = 1, n_chunks = 0;
-  for (int64_t done_iters = 0; running > 0 && done_iters < (int64_t)max_iter + 64; ++n_chunks) {
+  for (int64_t done_iters = 0; running > 0 && done_iters < (int64_t)max_iter + 256; ++n_chunks) {
     // the layouts shrink fastest in the first iterations: short chunks there keep the restarts
     // in the narrowest kernel class that fits them
-    const int chunk = n_chunks < 6 ? 4 : 32;
+    // (a fixed function of the chunk index: the path a restart takes never depends on the
+    // other windows of the batch, so results are independent of the batch composition)
+    const int chunk = n_chunks < 6 ? 4 : (n_chunks < 14 ? 32 : 256);
     if (b->sched_dirty && schedule(b)) return 1;
     if (run_iterations(b, chunk, &launches)) return 1;
     if (sync_status(b, &running)) return 1;
@@ -603,24 +676,28 @@ int vl_batch_profile_step(vl_batch* b, int32_t n_updates, double* ms_out, int64_
   if (!b->uploaded) return fail("vl_batch_profile_step before vl_batch_upload");
   if (!ms_out || !n_out || n_updates < 0) return fail("bad argument");
   VL_CUDA(cudaSetDevice(b->device));
-  for (int i = 0; i < 3; ++i) { ms_out[i] = 0.0; n_out[i] = 0; }
+  for (int i = 0; i < 4; ++i) { ms_out[i] = 0.0; n_out[i] = 0; }
   cudaEvent_t ev[2];
   for (auto& e : ev) VL_CUDA(cudaEventCreate(&e));
-  for (int it = 0; it < n_updates; ++it) {
-    if (b->sched_dirty && schedule(b)) return 1;
-    VL_CUDA(cudaStreamSynchronize(b->stream));
-    for (int phase = 0; phase < 3; ++phase) {
-      int64_t n = 0;
-      VL_CUDA(cudaEventRecord(ev[0], b->stream));
-      if (launch_phase(b, phase, &n)) return 1;
-      VL_CUDA(cudaEventRecord(ev[1], b->stream));
-      VL_CUDA(cudaEventSynchronize(ev[1]));
-      float m = 0.f;
-      VL_CUDA(cudaEventElapsedTime(&m, ev[0], ev[1]));
-      ms_out[phase] += m; n_out[phase] += n;
-    }
-    if (sync_status(b, nullptr)) return 1;
-  }
+  auto timed = [&](int slot, auto&& fn) -> int {
+    int64_t n = 0;
+    VL_CUDA(cudaEventRecord(ev[0], b->stream));
+    if (fn(&n)) return 1;
+    VL_CUDA(cudaEventRecord(ev[1], b->stream));
+    VL_CUDA(cudaEventSynchronize(ev[1]));
+    float m = 0.f;
+    VL_CUDA(cudaEventElapsedTime(&m, ev[0], ev[1]));
+    if (n > 0) { ms_out[slot] += m; n_out[slot] += n; }
+    return 0;
+  };
+  if (b->sched_dirty && schedule(b)) return 1;
+  VL_CUDA(cudaStreamSynchronize(b->stream));
+  // the resident restarts do all n_updates in one launch; the general path is timed per kernel
+  if (timed(3, [&](int64_t* n) { return launch_resident(b, n_updates, n); })) return 1;
+  for (int it = 0; it < n_updates; ++it)
+    for (int phase = 0; phase < 3; ++phase)
+      if (timed(phase, [&](int64_t* n) { return launch_phase(b, phase, n); })) return 1;
+  if (sync_status(b, nullptr)) return 1;
   for (auto& e : ev) cudaEventDestroy(e);
   return 0;
 }
@@ -804,6 +881,13 @@ int vl_batch_merge_haplo(vl_batch* b, int32_t window, int32_t restart, const int
                               (size_t)G * 8, W.N, cudaMemcpyDeviceToHost, s));
   VL_CUDA(cudaStreamSynchronize(s));
   return 0;
+}
+
+int vl_debug_counters(uint64_t* out16, int32_t reset) {
+  static_assert(sizeof(unsigned long long) == sizeof(uint64_t), "counter width");
+  const int rc = vl_debug_resident_cycles(reinterpret_cast<unsigned long long*>(out16), reset);
+  if (rc == 2) return fail("library built without -DVL_RS_PROFILE");
+  return rc ? fail("cudaMemcpyFromSymbol failed") : 0;
 }
 
 double vl_batch_last_device_ms(const vl_batch* b) { return b ? b->last_ms : 0.0; }

@@ -1,0 +1,213 @@
+// Device code shared by the general-path kernels (vl_kernels.cu) and the resident kernel
+// (vl_resident.cu): small helpers and the scalar part of one CAVI update.
+#pragma once
+#include <type_traits>
+
+#include "vl_device.cuh"
+#include "../../include/viloca_b200.h"
+
+__device__ __forceinline__ double neg_inf() { return __longlong_as_double(0xfff0000000000000LL); }
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// Run f(std::integral_constant<int, kt>) for the run-time tile count kt in [1, KTM].  The DMMA
+// loops are instantiated per tile count because a predicated-off DMMA still occupies the FP64
+// pipe for a full issue slot on sm_100a (measured: 2.2x on the kt = 1 loops).
+template <int KTM, int KT = 1, class F>
+__device__ __forceinline__ void vl_dispatch_tiles(int kt, F&& f) {
+  if constexpr (KT >= KTM) {
+    f(std::integral_constant<int, KTM>{});
+  } else {
+    if (kt == KT) f(std::integral_constant<int, KT>{});
+    else vl_dispatch_tiles<KTM, KT + 1>(kt, f);
+  }
+}
+
+// Named barrier over the first `n` threads of the CTA (n a multiple of 32).  Barrier 0 over
+// the whole CTA is __syncthreads().
+template <int BAR>
+__device__ __forceinline__ void vl_bar_sync(int n) {
+  asm volatile("bar.sync %0, %1;\n" :: "r"(BAR), "r"(n) : "memory");
+}
+
+// Shared-memory scratch of vl_scalar_update.  The caller fills cs (column sums of w*z per
+// slot of the current layout) and sc (sum w z X | sum z log z | lep c | lep d | sum h ref |
+// sum h (1-ref) | sum h log h) before the call.
+struct VlScalarSmem {
+  double cs[VL_MAX_CLUSTERS];
+  double sc[8];
+  double part[VL_MAX_CLUSTERS / 32][5];
+  int slot[VL_MAX_CLUSTERS];
+  int nlive[VL_MAX_CLUSTERS / 32], fdead[VL_MAX_CLUSTERS / 32];
+  int stop;
+};
+
+// alpha, mean_log_pi, a, b, (c, d), the ELBO in the reference's term order, the loop state
+// machine of run_cavi (uqs cavi.py:120-169, lep cavi.py:135-199 as written) and the layout of
+// the next iteration.  Called by threads 0..127 of the CTA (one per cluster), which
+// synchronise on named barrier BAR; returns 1 to all of them when the restart left its loop.
+template <int BAR>
+__device__ __forceinline__ int vl_scalar_update(const VlProblem& P, VlState* S, VlScalarSmem& sm, int tid,
+                                                int* done_count, int4* pstat_entry) {
+  constexpr int NT = VL_MAX_CLUSTERS;
+  const int warp = tid >> 5, lane = tid & 31;
+  const int K = P.K;
+  const int ktl = S->ktl, nlay = S->nlay, ghost = S->ghost;
+
+  // z and h are now stored in the current layout: remember it for the exports
+  const int old_lay = (tid < 8 * ktl) ? P.lay[tid] : -1;
+  if (tid < 8 * ktl) P.lay_z[tid] = old_lay;
+  if (tid < K) sm.slot[tid] = ghost;
+  vl_bar_sync<BAR>(NT);
+  if (tid < nlay && tid != ghost) sm.slot[old_lay] = tid;
+  vl_bar_sync<BAR>(NT);
+
+  const double alpha0 = S->alpha0;
+  double cs = 0.0, lp = 0.0, q0 = 0.0, q1 = 0.0, q2 = 0.0, q3 = 0.0, q4 = 0.0;
+  int my_slot = 0;
+  if (tid < K) {
+    my_slot = sm.slot[tid];
+    cs = sm.cs[my_slot];                                 // a dead cluster has the ghost's sum
+    const double al = alpha0 + cs;                       // update_alpha, update_eqs.py:114-121
+    lp = vl_digamma(al) - S->dsum_alpha;                 // get_mean_log_pi, update_eqs.py:40-46
+    P.alpha[tid] = al;
+    P.mlp[tid] = lp;
+    q0 = (alpha0 - 1.0) * lp; q1 = (al - 1.0) * lp; q2 = lgamma(al); q3 = al; q4 = cs * lp;
+  }
+  q0 = warp_sum(q0); q1 = warp_sum(q1); q2 = warp_sum(q2); q3 = warp_sum(q3); q4 = warp_sum(q4);
+  if (lane == 0) { sm.part[warp][0] = q0; sm.part[warp][1] = q1; sm.part[warp][2] = q2; sm.part[warp][3] = q3; sm.part[warp][4] = q4; }
+  // candidate layout of the next iteration (used unless the loop stops): a cluster stays while
+  // any read gives it a non-zero responsibility (column sum > 0; the weights are positive).
+  // All others have mean_cluster[:,k] == 0 exactly, hence identical mean_haplo rows, logits and
+  // mean_log_pi, and are represented by the single ghost slot with multiplicity.
+  const bool is_cluster = tid < K;
+  const bool live = is_cluster && (S->skip == 0 || cs > 0.0);
+  const unsigned live_mask = __ballot_sync(0xffffffffu, live);
+  const unsigned dead_mask = __ballot_sync(0xffffffffu, is_cluster && !live);
+  if (lane == 0) {
+    sm.nlive[warp] = __popc(live_mask);
+    sm.fdead[warp] = dead_mask ? (warp * 32 + __ffs(dead_mask) - 1) : -1;
+  }
+  vl_bar_sync<BAR>(NT);
+
+  if (tid == 0) {
+    double sum5[5];
+#pragma unroll
+    for (int j = 0; j < 5; ++j) {
+      double v = 0.0;
+#pragma unroll
+      for (int wI = 0; wI < NT / 32; ++wI) v += sm.part[wI][j];
+      sum5[j] = v;
+    }
+    const int mode = P.mode;
+    const double z_data = sm.sc[0], z_ent = sm.sc[1], z_c = sm.sc[2], z_d = sm.sc[3];
+    const double h_ref = sm.sc[4], h_nref = sm.sc[5], h_ent = sm.sc[6];
+    const double sum_a0m1_lp = sum5[0], sum_am1_lp = sum5[1], sum_lgamma = sum5[2];
+    const double sum_alpha = sum5[3], sum_cs_lp = sum5[4];
+
+    // update_a_and_b + get_mean_log_beta_dist (update_eqs.py:103-112, 48-53)
+    const double a = S->a0 + h_ref, b = S->b0 + h_nref;
+    const double mlg0 = vl_digamma(a) - S->dsum_ab, mlg1 = vl_digamma(b) - S->dsum_ab;
+    double c = S->c0, d = S->d0, mlt0 = S->mlt0, mlt1 = S->mlt1;
+    if (mode == VL_MODE_LEP) {                             // update_c_and_d, lep update_eqs.py:174-188
+      c = S->c0 + z_c; d = S->d0 + z_d;
+      mlt0 = vl_digamma(c) - S->dsum_cd; mlt1 = vl_digamma(d) - S->dsum_cd;
+    }
+    // ELBO (elbo_eqs.py:27-31; lep elbo_eqs.py:34-39), terms added in the reference's order
+    const double t_data = (mode == VL_MODE_UQS) ? z_data : (mlt0 * z_c + (mlt1 - VL_LOG4) * z_d);
+    const double lnB_alpha = sum_lgamma - lgamma(sum_alpha);
+    const double t_pi = ((-1.0) * S->lnB0 + sum_a0m1_lp) - ((-1.0) * lnB_alpha + sum_am1_lp);
+    const double t_cluster = sum_cs_lp - z_ent;
+    const double t_haplo = (mlg0 * h_ref + (mlg1 - VL_LOG4) * h_nref) - h_ent;
+    const double t_gamma = ((S->a0 - 1.0) * mlg0 + (S->b0 - 1.0) * mlg1 - S->betaln_ab0) -
+                           ((a - 1.0) * mlg0 + (b - 1.0) * mlg1 - vl_betaln(a, b));
+    double t_theta = 0.0;
+    double elbo = t_data;
+    elbo += t_pi; elbo += t_cluster; elbo += t_haplo; elbo += t_gamma;
+    if (mode == VL_MODE_LEP) {
+      t_theta = ((S->c0 - 1.0) * mlt0 + (S->d0 - 1.0) * mlt1 - S->betaln_cd0) -
+                ((c - 1.0) * mlt0 + (d - 1.0) * mlt1 - vl_betaln(c, d));
+      elbo += t_theta;
+    }
+    S->a = a; S->b = b; S->c = c; S->d = d;
+    S->mlg0 = mlg0; S->mlg1 = mlg1; S->mlt0 = mlt0; S->mlt1 = mlt1;
+    S->elbo = elbo; S->t_data = t_data; S->t_pi = t_pi; S->t_cluster = t_cluster;
+    S->t_haplo = t_haplo; S->t_gamma = t_gamma; S->t_theta = t_theta;
+
+    // ---- loop state machine: uqs cavi.py:146-169, lep cavi.py:167-199 ----
+    int iter = S->iter, converged = S->converged, status = VL_STATUS_RUNNING;
+    int n_hist = S->n_hist;
+    double h_last = S->h_last, h_prev = S->h_prev;
+    const bool append = (mode == VL_MODE_UQS) || ((iter & 1) == 0);
+    if (append) {
+      if (n_hist < S->max_iter) P.hist[n_hist] = elbo;
+      h_prev = h_last; h_last = elbo; ++n_hist;
+    }
+    const int n_updates = S->n_updates + 1;
+    bool stop = false;
+    if (iter > 1) {
+      const double dec_tol = (mode == VL_MODE_UQS) ? 1e-5 : 1e-8;
+      const double thr = (mode == VL_MODE_UQS) ? S->thr : 1e-3;
+      if (isnan(elbo)) { status = VL_STATUS_NAN; stop = true; }
+      else if (h_prev > elbo && fabs(elbo - h_prev) > dec_tol) { status = VL_STATUS_DECREASING; stop = true; }
+      else if (fabs(elbo - h_prev) < thr) { converged = 1; if (mode == VL_MODE_LEP) iter += 1; }
+      else if (mode == VL_MODE_LEP) { iter = 0; }
+    }
+    if (!stop) {
+      iter += 1;
+      if (converged && iter >= 10) { status = VL_STATUS_CONVERGED; stop = true; }
+      else if (n_updates >= S->max_iter) { status = VL_STATUS_MAXITER; stop = true; }
+    }
+    if (!stop && iter <= 1) {   // refresh of the digamma sums for the next update, cavi.py:122-128
+      S->dsum_alpha = vl_digamma(sum_alpha);
+      S->dsum_ab = vl_digamma(a + b);
+      if (mode == VL_MODE_LEP) S->dsum_cd = vl_digamma(c + d);
+    }
+    S->iter = iter; S->converged = converged; S->n_hist = n_hist; S->n_updates = n_updates;
+    S->h_last = h_last; S->h_prev = h_prev; S->status = status;
+    S->nlay_z = nlay; S->ghost_z = ghost; S->ktl_z = ktl;
+
+    int nl = nlay, kt_new = ktl;
+    if (!stop) {
+      int n_live = 0;
+#pragma unroll
+      for (int wI = 0; wI < NT / 32; ++wI) n_live += sm.nlive[wI];
+      const int n_dead = K - n_live;
+      nl = n_live + (n_dead > 0 ? 1 : 0);
+      kt_new = (nl + 7) / 8;
+      S->ghost_mult = (double)n_dead;
+      S->nlay = nl; S->ghost = (n_dead > 0) ? n_live : -1;
+      S->ktl = kt_new;
+    } else {
+      S->active = 0;
+      atomicAdd(done_count, 1);
+    }
+    *pstat_entry = make_int4(stop ? 0 : 1, max(kt_new, ktl), nl, n_updates);
+    sm.stop = stop ? 1 : 0;
+  }
+  vl_bar_sync<BAR>(NT);
+  if (sm.stop) return 1;
+
+  // ---- write the layout of the next iteration ----
+  int n_live = 0, first_dead = -1, before = 0;
+#pragma unroll
+  for (int wI = 0; wI < NT / 32; ++wI) {
+    if (wI < warp) before += sm.nlive[wI];
+    n_live += sm.nlive[wI];
+    if (first_dead < 0) first_dead = sm.fdead[wI];
+  }
+  if (live) {
+    const int s = before + __popc(live_mask & ((1u << lane) - 1u));
+    P.lay[s] = tid; P.gat[s] = my_slot; P.mlp_lay[s] = lp;
+  }
+  if (tid == first_dead) {          // the ghost slot stands for every dead cluster
+    P.lay[n_live] = tid; P.gat[n_live] = my_slot; P.mlp_lay[n_live] = lp;
+  }
+  const int nl = n_live + (first_dead >= 0 ? 1 : 0);
+  for (int s = nl + tid; s < 8 * ((nl + 7) / 8); s += NT) { P.lay[s] = -1; P.gat[s] = 0; P.mlp_lay[s] = 0.0; }
+  return 0;
+}

@@ -10,13 +10,16 @@
 // g[k,l,b] = 1 - h[k,l,b] = sum_{b' != b} h[k,l,b']:
 //   contraction #1   sum_{l,b} E h        = ltsum[n] - Y[n,k],  Y = sum_l d[n,l] g[k,l,c[n,l]]
 //   contraction #2   sum_n w z E [b]      = (b-independent) + sum_n w z d [c[n,l] == b]
-// The b-independent part cancels in the softmax over bases.  Per position one base maj[l] is
-// singled out (the most frequent one): entries with c == maj[l] form the dense operand
-// Dm[n,l] (0 elsewhere) that is contracted on the FP64 tensor pipe with a 5x smaller
-// reduction than E; the few entries with another base are kept in two sparse lists (by read,
-// by position).  Clusters whose responsibilities underflowed to exactly 0 for every read are
-// removed from the dense work: the *layout* lists the live clusters plus one ghost slot that
-// carries the (identical) values of all dead clusters with their multiplicity.
+// The b-independent part cancels in the softmax over bases.  Both are contractions with the
+// one-hot-expanded matrix D[n,(l,b)] = d[n,l] [c[n,l] == b], which has one non-zero per called
+// (read, position).  Its *popular* columns -- the most frequent base of every position, plus
+// every other (position, base) pair that enough reads carry -- form the dense operand
+// Dm[n,j] that is contracted on the FP64 tensor pipe (about L columns instead of the 5 L of E);
+// the few remaining entries (sequencing errors, rare variants) are kept in two sparse lists
+// (by read, by (position, base)).  Clusters whose responsibilities underflowed to exactly 0
+// for every read are removed from the dense work: the *layout* lists the live clusters plus
+// one ghost slot that carries the (identical) values of all dead clusters with their
+// multiplicity.
 #pragma once
 #include <cstdint>
 #include <cuda_runtime.h>
@@ -25,7 +28,7 @@
 #define VL_LOG4 1.3862943611198906   // log(B - 1)
 
 // tile geometry (see DESIGN.md "Kernels")
-#define VL_PT 16         // positions per operand tile (= positions per haplotype-update CTA)
+#define VL_PT 16         // columns per operand tile (= columns per haplotype-update CTA)
 #define VL_ZT_READS 64   // reads per responsibility-update CTA
 #define VL_H_NC 32       // reads per stage of the haplotype-update kernel
 #define VL_STAGES 3
@@ -39,10 +42,11 @@
 // fragment hit 16 distinct 8-byte banks per half-warp.
 __host__ __device__ constexpr int vl_ks(int kt) { return 8 * kt + 4; }
 
-// Dense operand tiles: element (read n, position l) of Dm lives at
-//   ((l / 16) * Npad + n) * 16 + ((l % 16 + 4 * (n % 4)) % 16)
-// i.e. position-tile-major, one 128-byte line per read, rotated by 4 doubles per read so that
-// both fragment shapes (8 reads x 4 positions, 4 reads x 8 positions) read 16 distinct banks.
+// Dense operand tiles: element (read n, column j) of Dm lives at
+//   ((j / 16) * Npad + n) * 16 + ((j % 16 + 4 * (n % 4)) % 16)
+// i.e. column-tile-major, one 128-byte line per read, rotated by 4 doubles per read so that
+// both fragment shapes (8 reads x 4 columns, 4 reads x 8 columns) read 16 distinct banks.
+// All columns of one position lie in the same tile.
 __host__ __device__ __forceinline__ int vl_dm_col(int n, int p) { return (p + 4 * (n & 3)) & 15; }
 
 // Per-restart running state: the scalar part of state_curr_dict plus the loop variables of
@@ -70,26 +74,28 @@ struct VlState {
 // Read-only description of one (window, restart) problem.
 struct VlProblem {
   int mode, N, L, K;
-  int Npad, Ls, KT, pad0;
+  int Npad, Ls, KT, NCs;   // NCs: dense columns incl. padding, a multiple of 16
   int n_ztiles, n_htiles, window, restart;
   // window tensors (shared by the restarts of a window)
-  const double* dm;        // [Ls/16][Npad][16] dense operand, see vl_dm_col
+  const double* dm;        // [NCs/16][Npad][16] dense operand, see vl_dm_col
   const double* w;         // [Npad]  read multiplicity, 0 in the padding
   const double* ltsum;     // [Npad]  uqs: sum over called positions of log theta
   const double* mcount;    // [Npad]  number of called (non-N) positions
   const uint8_t* ref;      // [Ls]
-  const uint8_t* maj;      // [Ls]    base singled out per position
-  const int* sr_ptr;       // [Npad+1] minority entries by read ...
+  const int* col_lb;       // [NCs]   dense column -> l * 5 + b, or -1 (padding)
+  const int* poscol;       // [Ls*5]  l * 5 + b -> dense column, or -1 (pair kept in the sparse lists)
+  const int* tile_pos;     // [NCs]   the positions whose columns lie in tile j / 16, then -1
+  const int* sr_ptr;       // [Npad+1] sparse entries by read ...
   const int* sr_idx;       //   l * 5 + c
   const double* sr_d;      //   d[n,l]
-  const int* sp_ptr;       // [Ls+1]  ... and by position, sorted by (c, n)
-  const int* sp_nc;        //   n * 8 + c
+  const int* sp_ptr;       // [Ls*5+1] ... and by (position, base), reads ascending
+  const int* sp_n;         //   n
   const double* sp_wd;     //   w_n * d[n,l]
   // restart tensors; "slot" = column of the current layout
   double* z;               // [Npad][vl_ks(ktl_z)]   mean_cluster
   double* h;               // [Ls][5][vl_ks(ktl)]    mean_haplo
   double* g;               // [Ls][5][vl_ks(ktl)]    1 - mean_haplo, summed from the other bases
-  double* gm;              // [Ls][vl_ks(ktl)]       g at the singled-out base
+  double* gm;              // [NCs][vl_ks(ktl)]      g at the (position, base) of each dense column
   double* zpart;           // [n_ztiles][8*KT + VL_ZP_EXTRA]
   double* hpart;           // [n_htiles][VL_HP_STRIDE]
   double* alpha;           // [8*KT]  per cluster

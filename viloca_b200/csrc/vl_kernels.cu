@@ -13,27 +13,20 @@
 // complement table) are staged in shared memory by TMA bulk copies behind mbarriers; the
 // minority entries are added from the sparse lists; softmax / ELBO reductions are fused into
 // the epilogues.
-#include "vl_device.cuh"
+#include "vl_cavi.cuh"
 #include "vl_launch.h"
 #include "../../include/viloca_b200.h"
 
 namespace {
 
-__device__ __forceinline__ double neg_inf() { return __longlong_as_double(0xfff0000000000000LL); }
-
-__device__ __forceinline__ double warp_sum(double v) {
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-  return v;
-}
-
 // =========================================================================================
-// update_mean_haplo.  Per (position l, slot s) the logits over the bases are
-//   b = maj[l]:  T[l,s]  = sum_n w_n z[n,s] Dm[n,l]          (dense, DMMA, M = position)
-//   b other:     Cm[l,b,s] = sum_{minority entries (n,l,b)} (w_n d) z[n,s]   (sparse list)
+// update_mean_haplo.  Per (position l, base b, slot s) the logit is
+//   (l, b) a dense column j:  T[j,s]    = sum_n w_n z[n,s] Dm[n,j]              (DMMA, M = column)
+//   otherwise:                Cm[l,b,s] = sum_{sparse entries (n,l,b)} (w_n d) z[n,s]
 // plus the reference term; the part of the reference's logits that does not depend on b is
-// dropped (it cancels in the softmax).  CTA = 16 positions x all slots; warp (lg, rh) = 8
-// positions x one half of the reads of every stage; the two halves are added in fixed order.
+// dropped (it cancels in the softmax).  CTA = 16 columns (whole positions) x all slots; warp
+// (lg, rh) = 8 columns x one half of the reads of every stage; the halves are added in fixed
+// order.
 // =========================================================================================
 template <int NB, int MODE>
 __global__ void __launch_bounds__(VL_THREADS)
@@ -59,7 +52,6 @@ vl_haplo_kernel(const VlProblem* __restrict__ probs, const int2* __restrict__ ti
   const int KSz = vl_ks(ktz), KSn = vl_ks(ktl), K8 = 8 * ktl;
   const int nlay = S->nlay;
   const int nchunks = Npad / VL_H_NC;
-  const int l0 = tm.y * VL_PT;
   const double* __restrict__ dmg = P.dm + (size_t)tm.y * Npad * VL_PT;
   const double* __restrict__ zg = P.z;
   const double* __restrict__ wg = P.w;
@@ -96,24 +88,26 @@ vl_haplo_kernel(const VlProblem* __restrict__ probs, const int2* __restrict__ ti
   for (int i = 0; i < KTM; ++i) { acc[i][0] = 0.0; acc[i][1] = 0.0; }
 
   const int acol = (lg * 8 + g + 4 * q) & 15;      // vl_dm_col(row, lg*8+g) with row % 4 == q
-  for (int c = 0; c < nchunks; ++c) {
-    const int st = c % VL_STAGES;
-    if (tid == 0 && c + VL_STAGES - 1 < nchunks) issue(c + VL_STAGES - 1);
-    vl_mbar_wait(&bars[st], (c / VL_STAGES) & 1);
-    const double* dt = stg + (size_t)st * ST_STRIDE;
-    const double* wt = dt + DM_STAGE;
-    const double* zt = wt + VL_H_NC;
+  vl_dispatch_tiles<KTM>(ktl, [&](auto ktc) {
+    constexpr int KT = decltype(ktc)::value;
+    for (int c = 0; c < nchunks; ++c) {
+      const int st = c % VL_STAGES;
+      if (tid == 0 && c + VL_STAGES - 1 < nchunks) issue(c + VL_STAGES - 1);
+      vl_mbar_wait(&bars[st], (c / VL_STAGES) & 1);
+      const double* dt = stg + (size_t)st * ST_STRIDE;
+      const double* wt = dt + DM_STAGE;
+      const double* zt = wt + VL_H_NC;
 #pragma unroll
-    for (int s = 0; s < 4; ++s) {
-      const int row = rh * 16 + 4 * s + q;
-      const double a = wt[row] * dt[row * VL_PT + acol];
-      const double* zr = zt + row * KSz;
+      for (int s = 0; s < 4; ++s) {
+        const int row = rh * 16 + 4 * s + q;
+        const double a = wt[row] * dt[row * VL_PT + acol];
+        const double* zr = zt + row * KSz;
 #pragma unroll
-      for (int i = 0; i < KTM; ++i)
-        if (i < ktl) vl_dmma(acc[i], a, zr[co[i]]);
+        for (int i = 0; i < KT; ++i) vl_dmma(acc[i], a, zr[co[i]]);
+      }
+      __syncthreads();
     }
-    __syncthreads();
-  }
+  });
 
   // ---- the stage buffers are free now: T [16][K8] and Cm [16][5][K8] live in them ----
   double* T = stg;
@@ -134,10 +128,12 @@ vl_haplo_kernel(const VlProblem* __restrict__ probs, const int2* __restrict__ ti
         *tp = make_double2(acc[i][0] + o.x, acc[i][1] + o.y);
       }
   }
-  // minority entries of this tile's positions: warp = 4 positions, lanes = slots
+  // sparse entries of the positions whose columns lie in this tile: warp = 4 of them,
+  // lanes = slots
+  const int* __restrict__ tpos = P.tile_pos + (size_t)tm.y * VL_PT;
   {
     const int* __restrict__ sp_ptr = P.sp_ptr;
-    const int* __restrict__ sp_n = P.sp_nc;
+    const int* __restrict__ sp_n = P.sp_n;
     const double* __restrict__ sp_wd = P.sp_wd;
     int gl[NB];
 #pragma unroll
@@ -147,7 +143,8 @@ vl_haplo_kernel(const VlProblem* __restrict__ probs, const int2* __restrict__ ti
     }
     for (int pp = 0; pp < 4; ++pp) {
       const int pos = warp * 4 + pp;
-      const int l = l0 + pos;
+      const int l = tpos[pos];
+      if (l < 0) continue;
       for (int b = 0; b < VL_B; ++b) {
         const int e0 = sp_ptr[l * VL_B + b], e1 = sp_ptr[l * VL_B + b + 1];
         double av[NB];
@@ -176,19 +173,29 @@ vl_haplo_kernel(const VlProblem* __restrict__ probs, const int2* __restrict__ ti
   if (MODE == VL_MODE_LEP) cscale = S->mlt0 - (S->mlt1 - VL_LOG4);
   const int ghost = S->ghost;
   const double gmult = S->ghost_mult;
-  const int L = P.L;
+  const int* __restrict__ poscol = P.poscol;
+  const int* __restrict__ col_lb = P.col_lb + (size_t)tm.y * VL_PT;
+  double* __restrict__ gmt = P.gm + (size_t)tm.y * VL_PT * KSn;
   double s_ref = 0.0, s_nref = 0.0, s_ent = 0.0;
   for (int idx = tid; idx < VL_PT * K8; idx += VL_THREADS) {
     const int pos = idx / K8, slot = idx - pos * K8;
-    const int l = l0 + pos;
-    const unsigned rc = P.ref[l], mj = P.maj[l];
+    if (col_lb[pos] < 0) gmt[pos * KSn + slot] = 0.0;      // padding column of the operand
+    const int l = tpos[pos];
+    if (l < 0) continue;
+    const unsigned rc = P.ref[l];
     double* hp = P.h + (size_t)l * VL_B * KSn + slot;
     double* gp = P.g + (size_t)l * VL_B * KSn + slot;
-    if (l < L && slot < nlay) {
+    int lc[VL_B];                                          // column of (l, b) within this tile, or -1
+#pragma unroll
+    for (int b = 0; b < VL_B; ++b) {
+      const int j = poscol[l * VL_B + b];
+      lc[b] = (j < 0) ? -1 : j - tm.y * VL_PT;
+    }
+    if (slot < nlay) {
       double lgt[VL_B];
 #pragma unroll
       for (int b = 0; b < VL_B; ++b) {
-        const double cb = (mj == (unsigned)b) ? T[pos * K8 + slot] : Cm[(pos * VL_B + b) * K8 + slot];
+        const double cb = (lc[b] >= 0) ? T[lc[b] * K8 + slot] : Cm[(pos * VL_B + b) * K8 + slot];
         lgt[b] = ((MODE == VL_MODE_LEP) ? cscale * cb : cb) + ((rc == (unsigned)b) ? mlg0 : refoff);
       }
       double m = lgt[0];
@@ -199,7 +206,7 @@ vl_haplo_kernel(const VlProblem* __restrict__ probs, const int2* __restrict__ ti
       for (int b = 0; b < VL_B; ++b) { e[b] = exp(lgt[b] - m); sum += e[b]; }
       const double ls = log(sum);
       const double mu = (slot == ghost) ? gmult : 1.0;
-      double r0 = 0.0, r1 = 0.0, r2 = 0.0, gmaj = 0.0;
+      double r0 = 0.0, r1 = 0.0, r2 = 0.0;
 #pragma unroll
       for (int b = 0; b < VL_B; ++b) {
         const double hb = e[b] / sum;
@@ -211,14 +218,15 @@ vl_haplo_kernel(const VlProblem* __restrict__ probs, const int2* __restrict__ ti
         if (hb > 0.0) r2 += hb * ((lgt[b] - m) - ls);
         hp[b * KSn] = hb;
         gp[b * KSn] = gb;
-        if (mj == (unsigned)b) gmaj = gb;
+        if (lc[b] >= 0) gmt[lc[b] * KSn + slot] = gb;
       }
-      P.gm[(size_t)l * KSn + slot] = gmaj;
       s_ref += mu * r0; s_nref += mu * r1; s_ent += mu * r2;
     } else {
 #pragma unroll
-      for (int b = 0; b < VL_B; ++b) { hp[b * KSn] = 0.0; gp[b * KSn] = 0.0; }
-      P.gm[(size_t)l * KSn + slot] = 0.0;
+      for (int b = 0; b < VL_B; ++b) {
+        hp[b * KSn] = 0.0; gp[b * KSn] = 0.0;
+        if (lc[b] >= 0) gmt[lc[b] * KSn + slot] = 0.0;
+      }
     }
   }
   s_ref = warp_sum(s_ref); s_nref = warp_sum(s_nref); s_ent = warp_sum(s_ent);
@@ -259,7 +267,7 @@ vl_cluster_kernel(const VlProblem* __restrict__ probs, const int2* __restrict__ 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, q = lane & 3;
   const int Npad = P.Npad;
   const int KS = vl_ks(ktl), K8 = 8 * ktl;
-  const int nst = P.Ls / VL_PT;
+  const int nst = P.NCs / VL_PT;
   const int n0 = tm.y * VL_ZT_READS;
   const double* __restrict__ dmg = P.dm + (size_t)n0 * VL_PT;
   const double* __restrict__ gmg = P.gm;
@@ -289,30 +297,32 @@ vl_cluster_kernel(const VlProblem* __restrict__ probs, const int2* __restrict__ 
     for (int i = 0; i < KTM; ++i) { acc[mt][i][0] = 0.0; acc[mt][i][1] = 0.0; }
 
   const int r0 = warp * 16 + g;                    // rows r0 and r0 + 8 of the tile; r0 % 4 == g % 4
-  for (int c = 0; c < nst; ++c) {
-    const int st = c % VL_STAGES;
-    if (tid == 0 && c + VL_STAGES - 1 < nst) issue(c + VL_STAGES - 1);
-    vl_mbar_wait(&bars[st], (c / VL_STAGES) & 1);
-    const double* dt = stg + (size_t)st * ST_STRIDE;
-    const double* gt = dt + DM_STAGE + g;
+  vl_dispatch_tiles<KTM>(ktl, [&](auto ktc) {
+    constexpr int KT = decltype(ktc)::value;
+    for (int c = 0; c < nst; ++c) {
+      const int st = c % VL_STAGES;
+      if (tid == 0 && c + VL_STAGES - 1 < nst) issue(c + VL_STAGES - 1);
+      vl_mbar_wait(&bars[st], (c / VL_STAGES) & 1);
+      const double* dt = stg + (size_t)st * ST_STRIDE;
+      const double* gt = dt + DM_STAGE + g;
 #pragma unroll
-    for (int s = 0; s < 4; ++s) {
-      const int col = (4 * s + q + 4 * (g & 3)) & 15;
-      const double a0 = dt[r0 * VL_PT + col];
-      const double a1 = dt[(r0 + 8) * VL_PT + col];
-      const double* gr = gt + (4 * s + q) * KS;
+      for (int s = 0; s < 4; ++s) {
+        const int col = (4 * s + q + 4 * (g & 3)) & 15;
+        const double a0 = dt[r0 * VL_PT + col];
+        const double a1 = dt[(r0 + 8) * VL_PT + col];
+        const double* gr = gt + (4 * s + q) * KS;
 #pragma unroll
-      for (int i = 0; i < KTM; ++i)
-        if (i < ktl) {
+        for (int i = 0; i < KT; ++i) {
           const double bf = gr[8 * i];
           vl_dmma(acc[0][i], a0, bf);
           vl_dmma(acc[1][i], a1, bf);
         }
+      }
+      __syncthreads();
     }
-    __syncthreads();
-  }
+  });
 
-  // ---- minority entries of this thread's two reads ----
+  // ---- sparse entries of this thread's two reads ----
   {
     const int* __restrict__ sr_ptr = P.sr_ptr;
     const int* __restrict__ sr_idx = P.sr_idx;
@@ -448,179 +458,38 @@ vl_cluster_kernel(const VlProblem* __restrict__ probs, const int2* __restrict__ 
 }
 
 // =========================================================================================
-// Scalar update, ELBO, the loop state machine of run_cavi, and the next layout.
-// One CTA per scheduled restart; plist entries are (problem, tile capacity of its class).
+// Scalar update of the general path: one CTA per scheduled restart; plist entries are
+// (problem, tile capacity of its class).  Sums the per-tile partial records in fixed order and
+// hands over to vl_scalar_update (vl_cavi.cuh).
 // =========================================================================================
 __global__ void __launch_bounds__(VL_THREADS)
 vl_scalar_kernel(const VlProblem* __restrict__ probs, const int2* __restrict__ plist,
                  int* __restrict__ done_count, int4* __restrict__ pstat) {
+  static_assert(VL_THREADS == VL_MAX_CLUSTERS, "one thread per cluster");
   const int2 pe = plist[blockIdx.x];
   const VlProblem& P = probs[pe.x];
   VlState* S = P.st;
   const int ktl = S->ktl;
   if (S->active == 0 || ktl > pe.y || S->ktl_z > pe.y) return;
-  __shared__ double sh_cs[VL_MAX_CLUSTERS];       // column sums per slot
-  __shared__ double sh_ck[VL_MAX_CLUSTERS];       // column sums per cluster
-  __shared__ double sh_lp[VL_MAX_CLUSTERS];       // mean_log_pi per cluster
-  __shared__ int sh_slot[VL_MAX_CLUSTERS];        // cluster -> slot
-  __shared__ double sh_sc[8];
-  __shared__ double sh_t[5][VL_MAX_CLUSTERS];
-  __shared__ double sh_sum[5];
+  __shared__ VlScalarSmem sm;
   const int tid = threadIdx.x;
-  const int K = P.K, K8rec = 8 * P.KT, ZS = K8rec + VL_ZP_EXTRA;
-  const int nlay = S->nlay, ghost = S->ghost;
-
-  // fixed-order sums over the read tiles (column sums per slot, four scalars) and over the
-  // position tiles (three scalars)
+  const int K8rec = 8 * P.KT, ZS = K8rec + VL_ZP_EXTRA;
   for (int c = tid; c < 8 * ktl + 7; c += VL_THREADS) {
     double v = 0.0;
     if (c < 8 * ktl) {
       for (int t = 0; t < P.n_ztiles; ++t) v += P.zpart[(size_t)t * ZS + c];
-      sh_cs[c] = v;
+      sm.cs[c] = v;
     } else if (c < 8 * ktl + 4) {
       const int j = c - 8 * ktl;
       for (int t = 0; t < P.n_ztiles; ++t) v += P.zpart[(size_t)t * ZS + K8rec + j];
-      sh_sc[j] = v;
+      sm.sc[j] = v;
     } else {
       const int j = c - 8 * ktl - 4;
       for (int t = 0; t < P.n_htiles; ++t) v += P.hpart[(size_t)t * VL_HP_STRIDE + j];
-      sh_sc[4 + j] = v;
+      sm.sc[4 + j] = v;
     }
   }
-  if (tid < K) sh_slot[tid] = ghost;
-  __syncthreads();
-  if (tid < nlay && tid != ghost) sh_slot[P.lay[tid]] = tid;
-  __syncthreads();
-
-  const double alpha0 = S->alpha0;
-  if (tid < K) {
-    const double cs = sh_cs[sh_slot[tid]];               // a dead cluster has the ghost's sum
-    const double al = alpha0 + cs;                       // update_alpha, update_eqs.py:114-121
-    const double lp = vl_digamma(al) - S->dsum_alpha;    // get_mean_log_pi, update_eqs.py:40-46
-    P.alpha[tid] = al;
-    P.mlp[tid] = lp;
-    sh_ck[tid] = cs;
-    sh_lp[tid] = lp;
-    sh_t[0][tid] = (alpha0 - 1.0) * lp;
-    sh_t[1][tid] = (al - 1.0) * lp;
-    sh_t[2][tid] = lgamma(al);
-    sh_t[3][tid] = al;
-    sh_t[4][tid] = cs * lp;
-  }
-  __syncthreads();
-  if (tid < 5) {
-    double v = 0.0;
-    for (int k = 0; k < K; ++k) v += sh_t[tid][k];
-    sh_sum[tid] = v;
-  }
-  __syncthreads();
-  if (tid != 0) return;
-
-  const int mode = P.mode;
-  const double z_data = sh_sc[0], z_ent = sh_sc[1], z_c = sh_sc[2], z_d = sh_sc[3];
-  const double h_ref = sh_sc[4], h_nref = sh_sc[5], h_ent = sh_sc[6];
-  const double sum_a0m1_lp = sh_sum[0], sum_am1_lp = sh_sum[1], sum_lgamma = sh_sum[2];
-  const double sum_alpha = sh_sum[3], sum_cs_lp = sh_sum[4];
-
-  // update_a_and_b + get_mean_log_beta_dist (update_eqs.py:103-112, 48-53)
-  const double a = S->a0 + h_ref, b = S->b0 + h_nref;
-  const double mlg0 = vl_digamma(a) - S->dsum_ab, mlg1 = vl_digamma(b) - S->dsum_ab;
-  double c = S->c0, d = S->d0, mlt0 = S->mlt0, mlt1 = S->mlt1;
-  if (mode == VL_MODE_LEP) {                             // update_c_and_d, lep update_eqs.py:174-188
-    c = S->c0 + z_c; d = S->d0 + z_d;
-    mlt0 = vl_digamma(c) - S->dsum_cd; mlt1 = vl_digamma(d) - S->dsum_cd;
-  }
-  // ELBO (elbo_eqs.py:27-31; lep elbo_eqs.py:34-39), terms added in the reference's order
-  const double t_data = (mode == VL_MODE_UQS) ? z_data : (mlt0 * z_c + (mlt1 - VL_LOG4) * z_d);
-  const double lnB_alpha = sum_lgamma - lgamma(sum_alpha);
-  const double t_pi = ((-1.0) * S->lnB0 + sum_a0m1_lp) - ((-1.0) * lnB_alpha + sum_am1_lp);
-  const double t_cluster = sum_cs_lp - z_ent;
-  const double t_haplo = (mlg0 * h_ref + (mlg1 - VL_LOG4) * h_nref) - h_ent;
-  const double t_gamma = ((S->a0 - 1.0) * mlg0 + (S->b0 - 1.0) * mlg1 - S->betaln_ab0) -
-                         ((a - 1.0) * mlg0 + (b - 1.0) * mlg1 - vl_betaln(a, b));
-  double t_theta = 0.0;
-  double elbo = t_data;
-  elbo += t_pi; elbo += t_cluster; elbo += t_haplo; elbo += t_gamma;
-  if (mode == VL_MODE_LEP) {
-    t_theta = ((S->c0 - 1.0) * mlt0 + (S->d0 - 1.0) * mlt1 - S->betaln_cd0) -
-              ((c - 1.0) * mlt0 + (d - 1.0) * mlt1 - vl_betaln(c, d));
-    elbo += t_theta;
-  }
-  S->a = a; S->b = b; S->c = c; S->d = d;
-  S->mlg0 = mlg0; S->mlg1 = mlg1; S->mlt0 = mlt0; S->mlt1 = mlt1;
-  S->elbo = elbo; S->t_data = t_data; S->t_pi = t_pi; S->t_cluster = t_cluster;
-  S->t_haplo = t_haplo; S->t_gamma = t_gamma; S->t_theta = t_theta;
-
-  // ---- loop state machine: uqs cavi.py:146-169, lep cavi.py:167-199 ----
-  int iter = S->iter, converged = S->converged, status = VL_STATUS_RUNNING;
-  int n_hist = S->n_hist;
-  double h_last = S->h_last, h_prev = S->h_prev;
-  const bool append = (mode == VL_MODE_UQS) || ((iter & 1) == 0);
-  if (append) {
-    if (n_hist < S->max_iter) P.hist[n_hist] = elbo;
-    h_prev = h_last; h_last = elbo; ++n_hist;
-  }
-  const int n_updates = S->n_updates + 1;
-  bool stop = false;
-  if (iter > 1) {
-    const double dec_tol = (mode == VL_MODE_UQS) ? 1e-5 : 1e-8;
-    const double thr = (mode == VL_MODE_UQS) ? S->thr : 1e-3;
-    if (isnan(elbo)) { status = VL_STATUS_NAN; stop = true; }
-    else if (h_prev > elbo && fabs(elbo - h_prev) > dec_tol) { status = VL_STATUS_DECREASING; stop = true; }
-    else if (fabs(elbo - h_prev) < thr) { converged = 1; if (mode == VL_MODE_LEP) iter += 1; }
-    else if (mode == VL_MODE_LEP) { iter = 0; }
-  }
-  if (!stop) {
-    iter += 1;
-    if (converged && iter >= 10) { status = VL_STATUS_CONVERGED; stop = true; }
-    else if (n_updates >= S->max_iter) { status = VL_STATUS_MAXITER; stop = true; }
-  }
-  if (!stop && iter <= 1) {   // refresh of the digamma sums for the next update, cavi.py:122-128
-    S->dsum_alpha = vl_digamma(sum_alpha);
-    S->dsum_ab = vl_digamma(a + b);
-    if (mode == VL_MODE_LEP) S->dsum_cd = vl_digamma(c + d);
-  }
-  S->iter = iter; S->converged = converged; S->n_hist = n_hist; S->n_updates = n_updates;
-  S->h_last = h_last; S->h_prev = h_prev; S->status = status;
-
-  // ---- layout of the next iteration ----
-  // z is now stored in the current layout.  A cluster stays in the layout while any read gives
-  // it a non-zero responsibility (column sum > 0; the weights are positive); all others have
-  // mean_cluster[:,k] == 0 exactly, hence identical mean_haplo rows, logits and mean_log_pi,
-  // and are represented by the single ghost slot with multiplicity.
-  int nl = nlay, kt_new = ktl, gh = ghost;
-  for (int s = 0; s < 8 * ktl; ++s) P.lay_z[s] = P.lay[s];
-  S->nlay_z = nlay; S->ghost_z = ghost;
-  if (!stop) {
-    const bool skip = S->skip != 0;
-    int s = 0, first_dead = -1, n_dead = 0;
-    for (int k = 0; k < K; ++k) {
-      if (!skip || sh_ck[k] > 0.0) {
-        P.lay[s] = k; P.gat[s] = sh_slot[k]; P.mlp_lay[s] = sh_lp[k];
-        ++s;
-      } else {
-        if (first_dead < 0) first_dead = k;
-        ++n_dead;
-      }
-    }
-    gh = -1;
-    if (n_dead > 0) {
-      gh = s;
-      P.lay[s] = first_dead; P.gat[s] = sh_slot[first_dead]; P.mlp_lay[s] = sh_lp[first_dead];
-      ++s;
-    }
-    nl = s;
-    kt_new = (nl + 7) / 8;
-    for (; s < 8 * kt_new; ++s) { P.lay[s] = -1; P.gat[s] = 0; P.mlp_lay[s] = 0.0; }
-    S->ghost_mult = (double)n_dead;
-    S->nlay = nl; S->ghost = gh;
-    S->ktl_z = ktl; S->ktl = kt_new;
-  } else {
-    S->ktl_z = ktl;
-    S->active = 0;
-    atomicAdd(done_count, 1);
-  }
-  pstat[pe.x] = make_int4(stop ? 0 : 1, max(kt_new, ktl), nl, n_updates);
+  vl_scalar_update<0>(P, S, sm, tid, done_count, pstat + pe.x);
 }
 
 // One thread per problem: state_init_dict of draw_init_state (initialization.py:6-43), the
@@ -663,24 +532,24 @@ __global__ void vl_init_kernel(const VlProblem* __restrict__ probs, int n_probs,
   pstat[p] = make_int4(1, P.KT, K, 0);
 }
 
-// Dense operand of one window from the raw arrays: Dm[n,l] = d at entries whose base is the
-// singled-out one of the position (d = log theta - log((1-theta)/(B-1)) for uqs, 1 for lep),
-// 0 elsewhere (other base, 'N', padding).  One thread per (read, position) of a tile.
+// Dense operand of one window from the raw arrays: Dm[n,j] = d where read n carries base b_j at
+// position l_j (d = log theta - log((1-theta)/(B-1)) for uqs, 1 for lep), 0 elsewhere (other
+// base, 'N', padding).  One thread per (read, column) of a tile.
 __global__ void vl_prepare_dm_kernel(const uint8_t* __restrict__ codes, const double* __restrict__ lt,
-                                     const double* __restrict__ lo, const uint8_t* __restrict__ maj,
+                                     const double* __restrict__ lo, const int* __restrict__ col_lb,
                                      double* __restrict__ dm, int N, int L, int Npad, int mode) {
-  const int pt = blockIdx.y;
+  const int ct = blockIdx.y;
   const int n = blockIdx.x * (blockDim.x / VL_PT) + threadIdx.x / VL_PT;
   const int p = threadIdx.x % VL_PT;
   if (n >= Npad) return;
-  const int l = pt * VL_PT + p;
+  const int lb = col_lb[ct * VL_PT + p];
   double v = 0.0;
-  if (n < N && l < L) {
+  if (n < N && lb >= 0) {
+    const int l = lb / VL_B, b = lb - l * VL_B;
     const size_t off = (size_t)n * L + l;
-    const unsigned c = codes[off];
-    if (c < VL_B && c == maj[l]) v = (mode == VL_MODE_UQS) ? (lt[off] - lo[off]) : 1.0;
+    if (codes[off] == (unsigned)b) v = (mode == VL_MODE_UQS) ? (lt[off] - lo[off]) : 1.0;
   }
-  dm[((size_t)pt * Npad + n) * VL_PT + vl_dm_col(n, p)] = v;
+  dm[((size_t)ct * Npad + n) * VL_PT + vl_dm_col(n, p)] = v;
 }
 
 // per read: number of called positions (n_non_N of lep preparation.py:13) and, for uqs, the
@@ -829,11 +698,11 @@ cudaError_t vl_launch_init(const VlProblem* probs, int n_probs, int4* pstat, cud
   return cudaGetLastError();
 }
 
-cudaError_t vl_launch_prepare(const uint8_t* codes, const double* lt, const double* lo, const uint8_t* maj,
-                              double* dm, double* mcount, double* ltsum, int N, int L, int Npad, int Ls,
+cudaError_t vl_launch_prepare(const uint8_t* codes, const double* lt, const double* lo, const int* col_lb,
+                              double* dm, double* mcount, double* ltsum, int N, int L, int Npad, int NCs,
                               int mode, cudaStream_t stream) {
-  const dim3 grid((Npad + 15) / 16, Ls / VL_PT);
-  vl_prepare_dm_kernel<<<grid, 256, 0, stream>>>(codes, lt, lo, maj, dm, N, L, Npad, mode);
+  const dim3 grid((Npad + 15) / 16, NCs / VL_PT);
+  vl_prepare_dm_kernel<<<grid, 256, 0, stream>>>(codes, lt, lo, col_lb, dm, N, L, Npad, mode);
   vl_prepare_rows_kernel<<<(Npad + 3) / 4, 128, 0, stream>>>(codes, lt, mcount, ltsum, N, L, Npad, mode);
   return cudaGetLastError();
 }

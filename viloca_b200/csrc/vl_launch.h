@@ -8,6 +8,16 @@
 int vl_class_of_tiles(int kt);
 int vl_class_capacity(int cls);
 
+// Resident kernel (vl_resident.cu): one persistent CTA per restart, whole iterations on one SM.
+#define VL_RS_MAX_KT 4     // widest layout it handles, in 8-slot tiles
+#define VL_RS_MAX_CT 16    // most 16-column operand tiles
+size_t vl_resident_smem_bytes(int n_col_tiles, int kt);   // dynamic shared memory one restart needs
+size_t vl_resident_smem_limit();
+// per-phase cycle counters of one resident CTA; returns 2 unless built with -DVL_RS_PROFILE
+int vl_debug_resident_cycles(unsigned long long* out16, int reset);
+cudaError_t vl_launch_resident(int mode, const VlProblem* probs, const int* plist, int n, int n_iter, size_t smem,
+                               int* done_count, int4* pstat, cudaStream_t stream);
+
 cudaError_t vl_launch_haplo(int cls, int mode, const VlProblem* probs, const int2* tiles, int n_tiles,
                             cudaStream_t stream);
 cudaError_t vl_launch_cluster(int cls, int mode, const VlProblem* probs, const int2* tiles, int n_tiles,
@@ -17,8 +27,8 @@ cudaError_t vl_launch_cluster(int cls, int mode, const VlProblem* probs, const i
 cudaError_t vl_launch_scalar(const VlProblem* probs, const int2* plist, int n, int* done_count, int4* pstat,
                              cudaStream_t stream);
 cudaError_t vl_launch_init(const VlProblem* probs, int n_probs, int4* pstat, cudaStream_t stream);
-cudaError_t vl_launch_prepare(const uint8_t* codes, const double* lt, const double* lo, const uint8_t* maj,
-                              double* dm, double* mcount, double* ltsum, int N, int L, int Npad, int Ls,
+cudaError_t vl_launch_prepare(const uint8_t* codes, const double* lt, const double* lo, const int* col_lb,
+                              double* dm, double* mcount, double* ltsum, int N, int L, int Npad, int NCs,
                               int mode, cudaStream_t stream);
 cudaError_t vl_launch_export_haplo(const VlProblem* prob, double* out, size_t total, cudaStream_t stream);
 cudaError_t vl_launch_export_cluster(const VlProblem* prob, double* out, size_t total, cudaStream_t stream);

@@ -145,7 +145,7 @@ class CaviBatch:
     """All (window, restart) problems of ``windows`` on one device."""
 
     def __init__(self, windows: Sequence[Window], device: int = 0, stream: Optional[int] = None,
-                 skip_dead: bool = True):
+                 skip_dead: bool = True, resident: bool = True):
         if not windows:
             raise ValueError("empty batch")
         self.windows = list(windows)
@@ -167,6 +167,8 @@ class CaviBatch:
         self.launches = 0
         if not skip_dead:
             capi.check(capi.lib.vl_batch_set_option(self._handle, capi.OPT_SKIP_DEAD, 0))
+        if not resident:
+            capi.check(capi.lib.vl_batch_set_option(self._handle, capi.OPT_RESIDENT, 0))
 
     # -- lifetime ------------------------------------------------------------------------
     def close(self) -> None:
@@ -208,12 +210,12 @@ class CaviBatch:
 
     def profile_step(self, n_updates: int):
         """Per-kernel device time (ms) and launch counts over ``n_updates`` iterations:
-        {"haplo": (ms, n), "cluster": (ms, n), "scalar": (ms, n)}."""
-        ms = (C.c_double * 3)()
-        cnt = (C.c_int64 * 3)()
+        {"haplo": (ms, n), "cluster": (ms, n), "scalar": (ms, n), "resident": (ms, n)}."""
+        ms = (C.c_double * 4)()
+        cnt = (C.c_int64 * 4)()
         capi.check(capi.lib.vl_batch_profile_step(self._handle, int(n_updates), ms, cnt))
         self.launches += int(sum(cnt))
-        return {k: (float(ms[i]), int(cnt[i])) for i, k in enumerate(("haplo", "cluster", "scalar"))}
+        return {k: (float(ms[i]), int(cnt[i])) for i, k in enumerate(("haplo", "cluster", "scalar", "resident"))}
 
     def problem_stats(self) -> np.ndarray:
         """(n_problems, 4) int32: running, 8-cluster tiles, clusters in the layout, updates."""

@@ -209,6 +209,14 @@ int vl_batch_profile_step(vl_batch* batch, int32_t n_updates, double* ms_out, in
 int vl_batch_problem_stats(vl_batch* batch, int32_t* out, int32_t n_problems);
 
 /*
+ * Test hook: the exponential the softmax epilogues use (valid for x <= 0, -inf allowed) applied
+ * to n host values on `device`.  It replaces CUDA's exp() in the kernels because FP64 latency
+ * bounds the epilogues; tests compare it with the host's exp, including the underflow boundary
+ * that decides which responsibilities are exactly 0.
+ */
+int vl_debug_exp(int32_t device, const double* x, double* out, int32_t n);
+
+/*
  * Development aid: per-phase cycle counters of one CTA of the resident kernel (16 values).
  * Fails unless the library was built with -DVL_RS_PROFILE (python -m viloca_b200.build --profile).
  */

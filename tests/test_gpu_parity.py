@@ -135,6 +135,29 @@ def test_free_running_against_reference_run_cavi(golden_dir):
             assert b.fetch(state="none")[wi].best_restart == int(np.argmax(elbos))
 
 
+def test_softmax_exponential_matches_host_exp():
+    """The kernels' branch-free exp (x <= 0): <= 2 ulp in the normal range, correct rounding
+    behaviour in the subnormal range, and exactly 0 where the reference's np.exp underflows."""
+    from viloca_b200 import _capi as capi
+    rng = np.random.default_rng(5)
+    x = np.concatenate([
+        -np.abs(rng.standard_cauchy(200000)) * 3, -rng.random(100000) * 760, np.linspace(-746.5, -744.0, 50001),
+        np.linspace(-709.0, -707.0, 20001), -np.logspace(-300, 2.9, 20000), [0.0, -0.0, -np.inf, -745.1332191019412,
+                                                                              -745.1332191019411, -1e-320, -800.0, -1e6]])
+    x = np.ascontiguousarray(x, dtype=np.float64)
+    out = np.empty_like(x)
+    capi.check(capi.lib.vl_debug_exp(0, capi.f64_ptr(x), capi.f64_ptr(out), x.size))
+    with np.errstate(under="ignore"):
+        ref = np.exp(x)
+    assert np.array_equal(out == 0, ref == 0)
+    normal = ref > 2.3e-308
+    ulp = np.spacing(ref[normal])
+    assert np.max(np.abs(out[normal] - ref[normal]) / ulp) <= 2.0
+    sub = (ref > 0) & ~normal
+    assert np.max(np.abs(out[sub] - ref[sub])) <= 2 * 4.94e-324      # within one subnormal step of np.exp
+    assert out[np.flatnonzero(x == 0)[0]] == 1.0
+
+
 def _parse_support(path):
     from viloca_b200 import fasta
     import re

@@ -883,6 +883,19 @@ int vl_batch_merge_haplo(vl_batch* b, int32_t window, int32_t restart, const int
   return 0;
 }
 
+int vl_debug_exp(int32_t device, const double* x, double* out, int32_t n) {
+  if (!x || !out || n <= 0) return fail("bad argument");
+  VL_CUDA(cudaSetDevice(device));
+  double* d = nullptr;
+  VL_CUDA(cudaMalloc(reinterpret_cast<void**>(&d), (size_t)n * 16));
+  cudaError_t e = cudaMemcpy(d, x, (size_t)n * 8, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = vl_launch_exp_test(d, d + n, n, nullptr);
+  if (e == cudaSuccess) e = cudaMemcpy(out, d + n, (size_t)n * 8, cudaMemcpyDeviceToHost);
+  cudaFree(d);
+  VL_CUDA(e);
+  return 0;
+}
+
 int vl_debug_counters(uint64_t* out16, int32_t reset) {
   static_assert(sizeof(unsigned long long) == sizeof(uint64_t), "counter width");
   const int rc = vl_debug_resident_cycles(reinterpret_cast<unsigned long long*>(out16), reset);

@@ -14,6 +14,43 @@ __device__ __forceinline__ double warp_sum(double v) {
   return v;
 }
 
+// exp(x) for x <= 0 (the only arguments a max-subtracted softmax produces; -inf allowed), N
+// values at once.  Branch-free, so that the N evaluations are N independent instruction
+// streams: FP64 latency, not throughput, bounds the softmax epilogues when few warps run
+// (CUDA's exp() is a serial chain of ~25 dependent FP64 operations per value).
+// Cody-Waite reduction x = k ln2 + r, |r| <= ln2/2, degree-13 Taylor polynomial (truncation
+// 4e-18), scaling by 2^k in two steps so that results in the subnormal range are rounded once,
+// like a correctly rounded exp: exp(x) == 0 exactly for x < -745.14 (the zero pattern of
+// mean_cluster is part of the parity contract).  Max error about 1 ulp.
+template <int N>
+__device__ __forceinline__ void vl_exp_nonpos(const double (&x)[N], double (&out)[N]) {
+  constexpr double L2E = 1.4426950408889634074, MAGIC = 6755399441055744.0;   // 1.5 * 2^52
+  constexpr double LN2_HI = 6.93147180369123816490e-01, LN2_LO = 1.90821492927058770002e-10;
+  double r[N], p[N];
+  int k[N];
+#pragma unroll
+  for (int i = 0; i < N; ++i) {
+    const double xi = fmax(x[i], -800.0);
+    const double t = fma(xi, L2E, MAGIC);
+    k[i] = __double2loint(t);
+    const double kk = t - MAGIC;
+    r[i] = fma(kk, -LN2_LO, fma(kk, -LN2_HI, xi));
+    p[i] = 1.0 / 6227020800.0;
+  }
+  constexpr double C[13] = {1.0 / 479001600.0, 1.0 / 39916800.0, 1.0 / 3628800.0, 1.0 / 362880.0, 1.0 / 40320.0,
+                            1.0 / 5040.0, 1.0 / 720.0, 1.0 / 120.0, 1.0 / 24.0, 1.0 / 6.0, 0.5, 1.0, 1.0};
+#pragma unroll
+  for (int j = 0; j < 13; ++j)
+#pragma unroll
+    for (int i = 0; i < N; ++i) p[i] = fma(p[i], r[i], C[j]);
+#pragma unroll
+  for (int i = 0; i < N; ++i) {
+    const int k1 = k[i] >> 1, k2 = k[i] - k1;
+    const double s1 = __hiloint2double((k1 + 1023) << 20, 0), s2 = __hiloint2double((k2 + 1023) << 20, 0);
+    out[i] = (p[i] * s1) * s2;
+  }
+}
+
 // Run f(std::integral_constant<int, kt>) for the run-time tile count kt in [1, KTM].  The DMMA
 // loops are instantiated per tile count because a predicated-off DMMA still occupies the FP64
 // pipe for a full issue slot on sm_100a (measured: 2.2x on the kt = 1 loops).
@@ -43,6 +80,7 @@ struct VlScalarSmem {
   double part[VL_MAX_CLUSTERS / 32][5];
   int slot[VL_MAX_CLUSTERS];
   int nlive[VL_MAX_CLUSTERS / 32], fdead[VL_MAX_CLUSTERS / 32];
+  double fn[10];     // digamma / lgamma of the updated Beta parameters, one thread each
   int stop;
 };
 
@@ -65,6 +103,30 @@ __device__ __forceinline__ int vl_scalar_update(const VlProblem& P, VlState* S, 
   vl_bar_sync<BAR>(NT);
   if (tid < nlay && tid != ghost) sm.slot[old_lay] = tid;
   vl_bar_sync<BAR>(NT);
+
+  // the special functions of the updated Beta parameters depend only on sm.sc: the last threads
+  // of the CTA evaluate one each while the others work on their clusters
+  {
+    const int j = NT - 1 - tid;
+    if (j < ((P.mode == VL_MODE_LEP) ? 10 : 5)) {
+      const double a = S->a0 + sm.sc[4], b = S->b0 + sm.sc[5];
+      const double c = S->c0 + sm.sc[2], d = S->d0 + sm.sc[3];
+      double v;
+      switch (j) {
+        case 0: v = vl_digamma(a); break;
+        case 1: v = vl_digamma(b); break;
+        case 2: v = lgamma(a); break;
+        case 3: v = lgamma(b); break;
+        case 4: v = lgamma(a + b); break;
+        case 5: v = vl_digamma(c); break;
+        case 6: v = vl_digamma(d); break;
+        case 7: v = lgamma(c); break;
+        case 8: v = lgamma(d); break;
+        default: v = lgamma(c + d); break;
+      }
+      sm.fn[j] = v;
+    }
+  }
 
   const double alpha0 = S->alpha0;
   double cs = 0.0, lp = 0.0, q0 = 0.0, q1 = 0.0, q2 = 0.0, q3 = 0.0, q4 = 0.0;
@@ -111,11 +173,11 @@ __device__ __forceinline__ int vl_scalar_update(const VlProblem& P, VlState* S, 
 
     // update_a_and_b + get_mean_log_beta_dist (update_eqs.py:103-112, 48-53)
     const double a = S->a0 + h_ref, b = S->b0 + h_nref;
-    const double mlg0 = vl_digamma(a) - S->dsum_ab, mlg1 = vl_digamma(b) - S->dsum_ab;
+    const double mlg0 = sm.fn[0] - S->dsum_ab, mlg1 = sm.fn[1] - S->dsum_ab;
     double c = S->c0, d = S->d0, mlt0 = S->mlt0, mlt1 = S->mlt1;
     if (mode == VL_MODE_LEP) {                             // update_c_and_d, lep update_eqs.py:174-188
       c = S->c0 + z_c; d = S->d0 + z_d;
-      mlt0 = vl_digamma(c) - S->dsum_cd; mlt1 = vl_digamma(d) - S->dsum_cd;
+      mlt0 = sm.fn[5] - S->dsum_cd; mlt1 = sm.fn[6] - S->dsum_cd;
     }
     // ELBO (elbo_eqs.py:27-31; lep elbo_eqs.py:34-39), terms added in the reference's order
     const double t_data = (mode == VL_MODE_UQS) ? z_data : (mlt0 * z_c + (mlt1 - VL_LOG4) * z_d);
@@ -124,13 +186,13 @@ __device__ __forceinline__ int vl_scalar_update(const VlProblem& P, VlState* S, 
     const double t_cluster = sum_cs_lp - z_ent;
     const double t_haplo = (mlg0 * h_ref + (mlg1 - VL_LOG4) * h_nref) - h_ent;
     const double t_gamma = ((S->a0 - 1.0) * mlg0 + (S->b0 - 1.0) * mlg1 - S->betaln_ab0) -
-                           ((a - 1.0) * mlg0 + (b - 1.0) * mlg1 - vl_betaln(a, b));
+                           ((a - 1.0) * mlg0 + (b - 1.0) * mlg1 - (sm.fn[2] + sm.fn[3] - sm.fn[4]));
     double t_theta = 0.0;
     double elbo = t_data;
     elbo += t_pi; elbo += t_cluster; elbo += t_haplo; elbo += t_gamma;
     if (mode == VL_MODE_LEP) {
       t_theta = ((S->c0 - 1.0) * mlt0 + (S->d0 - 1.0) * mlt1 - S->betaln_cd0) -
-                ((c - 1.0) * mlt0 + (d - 1.0) * mlt1 - vl_betaln(c, d));
+                ((c - 1.0) * mlt0 + (d - 1.0) * mlt1 - (sm.fn[7] + sm.fn[8] - sm.fn[9]));
       elbo += t_theta;
     }
     S->a = a; S->b = b; S->c = c; S->d = d;

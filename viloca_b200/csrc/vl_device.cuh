@@ -154,10 +154,22 @@ __device__ __forceinline__ void vl_mbar_wait(uint64_t* bar, uint32_t parity) {
 }
 
 // digamma for x > 0: upward recurrence to x >= 10, then the asymptotic series
-// (scipy.special.digamma at update_eqs.py:45,51-52 and cavi.py:123-126).
+// (scipy.special.digamma at update_eqs.py:45,51-52 and cavi.py:123-126).  The (at most ten)
+// reciprocals of the recurrence are independent of each other, so they are issued together
+// and only then subtracted in order: same value as the sequential loop, a tenth of its latency.
 __device__ __forceinline__ double vl_digamma(double x) {
   double r = 0.0;
-  while (x < 10.0) { r -= 1.0 / x; x += 1.0; }
+  if (x < 10.0) {
+    double inv[10];
+#pragma unroll
+    for (int i = 0; i < 10; ++i) {
+      const bool on = x < 10.0;
+      inv[i] = on ? 1.0 / x : 0.0;
+      x = on ? x + 1.0 : x;
+    }
+#pragma unroll
+    for (int i = 0; i < 10; ++i) r -= inv[i];
+  }
   const double inv = 1.0 / x, i2 = inv * inv;
   const double s = i2 * (1.0 / 12 - i2 * (1.0 / 120 - i2 * (1.0 / 252 - i2 * (1.0 / 240 -
                    i2 * (1.0 / 132 - i2 * (691.0 / 32760 - i2 * (1.0 / 12)))))));

@@ -201,19 +201,23 @@ vl_haplo_kernel(const VlProblem* __restrict__ probs, const int2* __restrict__ ti
       double m = lgt[0];
 #pragma unroll
       for (int b = 1; b < VL_B; ++b) m = fmax(m, lgt[b]);
-      double e[VL_B], sum = 0.0;
+      double e[VL_B], xs[VL_B], sum = 0.0;
 #pragma unroll
-      for (int b = 0; b < VL_B; ++b) { e[b] = exp(lgt[b] - m); sum += e[b]; }
+      for (int b = 0; b < VL_B; ++b) xs[b] = lgt[b] - m;
+      vl_exp_nonpos<VL_B>(xs, e);
+#pragma unroll
+      for (int b = 0; b < VL_B; ++b) sum += e[b];
       const double ls = log(sum);
+      const double rsum = 1.0 / sum;
       const double mu = (slot == ghost) ? gmult : 1.0;
       double r0 = 0.0, r1 = 0.0, r2 = 0.0;
 #pragma unroll
       for (int b = 0; b < VL_B; ++b) {
-        const double hb = e[b] / sum;
+        const double hb = e[b] * rsum;
         double oth = 0.0;
 #pragma unroll
         for (int b2 = 0; b2 < VL_B; ++b2) if (b2 != b) oth += e[b2];
-        const double gb = oth / sum;
+        const double gb = oth * rsum;
         if (rc == (unsigned)b) r0 += hb; else r1 += hb;
         if (hb > 0.0) r2 += hb * ((lgt[b] - m) - ls);
         hp[b * KSn] = hb;
@@ -385,15 +389,17 @@ vl_cluster_kernel(const VlProblem* __restrict__ probs, const int2* __restrict__ 
 #pragma unroll
     for (int i = 0; i < KTM; ++i)
       if (i < ktl) {
+        const double xs[2] = {t[i][0] - m, t[i][1] - m};
+        double ev[2];
+        vl_exp_nonpos<2>(xs, ev);
 #pragma unroll
         for (int j = 0; j < 2; ++j) {
           const int s = 8 * i + 2 * q + j;
           double e = 0.0;
           if (s < nlay) {
-            const double dt = t[i][j] - m;
-            e = exp(dt);
+            e = ev[j];
             const double em = (s == ghost) ? gmult * e : e;
-            if (e > 0.0) u += em * dt;
+            if (e > 0.0) u += em * xs[j];
             v += em * acc[mt][i][j];
             sum += em;
           }
@@ -403,22 +409,23 @@ vl_cluster_kernel(const VlProblem* __restrict__ probs, const int2* __restrict__ 
     const double psum = sum;   // this thread's share of the row sum
     sum += __shfl_xor_sync(0xffffffffu, sum, 1);
     sum += __shfl_xor_sync(0xffffffffu, sum, 2);
+    const double rsum = 1.0 / sum;
     if (valid) {
       // sum_k z log z = (sum_k e_k (t_k - m)) / s - log s   (0 log 0 := 0)
-      s_ent += u / sum - ((q == 0) ? log(sum) : 0.0);
+      s_ent += u * rsum - ((q == 0) ? log(sum) : 0.0);
       if (MODE == VL_MODE_UQS) {
-        s_data += wn * (v / sum);
+        s_data += wn * (v * rsum);
       } else {
-        s_c += wn * (v / sum);
-        s_d += wn * ((mc * psum - v) / sum);
+        s_c += wn * (v * rsum);
+        s_d += wn * ((mc * psum - v) * rsum);
       }
     }
     double* zrow = P.z + (size_t)n * KS + 2 * q;
 #pragma unroll
     for (int i = 0; i < KTM; ++i)
       if (i < ktl) {
-        const double z0 = valid ? t[i][0] / sum : 0.0;
-        const double z1 = valid ? t[i][1] / sum : 0.0;
+        const double z0 = valid ? t[i][0] * rsum : 0.0;
+        const double z1 = valid ? t[i][1] * rsum : 0.0;
         *reinterpret_cast<double2*>(zrow + 8 * i) = make_double2(z0, z1);
         if (mt == 0) { cs[i][0] = wn * z0; cs[i][1] = wn * z1; }
         else { cs[i][0] += wn * z0; cs[i][1] += wn * z1; }
@@ -631,6 +638,17 @@ __global__ void vl_merge_kernel(const VlProblem* __restrict__ prob, double* __re
   }
 }
 
+// test hook: the softmax exponential on arbitrary non-positive inputs
+__global__ void vl_exp_test_kernel(const double* __restrict__ x, double* __restrict__ out, int n) {
+  const int i = 2 * (blockIdx.x * blockDim.x + threadIdx.x);
+  if (i >= n) return;
+  const double xs[2] = {x[i], (i + 1 < n) ? x[i + 1] : 0.0};
+  double ev[2];
+  vl_exp_nonpos<2>(xs, ev);
+  out[i] = ev[0];
+  if (i + 1 < n) out[i + 1] = ev[1];
+}
+
 template <int NB>
 constexpr size_t smem_haplo() {
   return (size_t)VL_STAGES * (VL_H_NC * VL_PT + VL_H_NC + VL_H_NC * vl_ks(4 * NB)) * sizeof(double);
@@ -704,6 +722,11 @@ cudaError_t vl_launch_prepare(const uint8_t* codes, const double* lt, const doub
   const dim3 grid((Npad + 15) / 16, NCs / VL_PT);
   vl_prepare_dm_kernel<<<grid, 256, 0, stream>>>(codes, lt, lo, col_lb, dm, N, L, Npad, mode);
   vl_prepare_rows_kernel<<<(Npad + 3) / 4, 128, 0, stream>>>(codes, lt, mcount, ltsum, N, L, Npad, mode);
+  return cudaGetLastError();
+}
+
+cudaError_t vl_launch_exp_test(const double* x, double* out, int n, cudaStream_t stream) {
+  vl_exp_test_kernel<<<(n / 2 + 128) / 128, 128, 0, stream>>>(x, out, n);
   return cudaGetLastError();
 }
 

@@ -34,3 +34,4 @@ cudaError_t vl_launch_export_haplo(const VlProblem* prob, double* out, size_t to
 cudaError_t vl_launch_export_cluster(const VlProblem* prob, double* out, size_t total, cudaStream_t stream);
 cudaError_t vl_launch_merge(const VlProblem* prob, double* zm, const int* group_of, int G, int KSg,
                             size_t total, cudaStream_t stream);
+cudaError_t vl_launch_exp_test(const double* x, double* out, int n, cudaStream_t stream);

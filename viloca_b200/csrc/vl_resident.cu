@@ -298,9 +298,12 @@ vl_resident_kernel(const VlProblem* __restrict__ probs, const int* __restrict__ 
           double m = lgt[0];
 #pragma unroll
           for (int b = 1; b < VL_B; ++b) m = fmax(m, lgt[b]);
-          double e[VL_B], sum = 0.0;
+          double e[VL_B], xs[VL_B], sum = 0.0;
 #pragma unroll
-          for (int b = 0; b < VL_B; ++b) { e[b] = exp(lgt[b] - m); sum += e[b]; }
+          for (int b = 0; b < VL_B; ++b) xs[b] = lgt[b] - m;
+          vl_exp_nonpos<VL_B>(xs, e);
+#pragma unroll
+          for (int b = 0; b < VL_B; ++b) sum += e[b];
           const double ls = log(sum);
           const double rsum = 1.0 / sum;
           const double mu_ = (slot == ghost) ? gmult : 1.0;
@@ -404,15 +407,17 @@ vl_resident_kernel(const VlProblem* __restrict__ probs, const int* __restrict__ 
 #pragma unroll
         for (int i = 0; i < RS_KTM; ++i)
           if (i < kt) {
+            const double xs[2] = {t[i][0] - m, t[i][1] - m};
+            double ev[2];
+            vl_exp_nonpos<2>(xs, ev);
 #pragma unroll
             for (int j = 0; j < 2; ++j) {
               const int s = 8 * i + 2 * q + j;
               double e = 0.0;
               if (s < nlay) {
-                const double dtv = t[i][j] - m;
-                e = exp(dtv);
+                e = ev[j];
                 const double em = (s == ghost) ? gmult * e : e;
-                if (e > 0.0) u += em * dtv;
+                if (e > 0.0) u += em * xs[j];
                 v += em * acc[i][j];
                 sum += em;
               }
@@ -422,13 +427,14 @@ vl_resident_kernel(const VlProblem* __restrict__ probs, const int* __restrict__ 
         const double psum = sum;
         sum += __shfl_xor_sync(0xffffffffu, sum, 1);
         sum += __shfl_xor_sync(0xffffffffu, sum, 2);
+        const double rsum = 1.0 / sum;
         if (valid) {
-          s_ent += u / sum - ((q == 0) ? log(sum) : 0.0);
+          s_ent += u * rsum - ((q == 0) ? log(sum) : 0.0);
           if (MODE == VL_MODE_UQS) {
-            s_data += wn * (v / sum);
+            s_data += wn * (v * rsum);
           } else {
-            s_c += wn * (v / sum);
-            s_d += wn * ((mc * psum - v) / sum);
+            s_c += wn * (v * rsum);
+            s_d += wn * ((mc * psum - v) * rsum);
           }
         }
         double* zrow = P.z + (size_t)n * KS + 2 * q;
@@ -436,8 +442,8 @@ vl_resident_kernel(const VlProblem* __restrict__ probs, const int* __restrict__ 
 #pragma unroll
         for (int i = 0; i < RS_KTM; ++i)
           if (i < kt) {
-            const double z0 = valid ? t[i][0] / sum : 0.0;
-            const double z1 = valid ? t[i][1] / sum : 0.0;
+            const double z0 = valid ? t[i][0] * rsum : 0.0;
+            const double z1 = valid ? t[i][1] * rsum : 0.0;
             *reinterpret_cast<double2*>(zrow + 8 * i) = make_double2(z0, z1);
             *reinterpret_cast<double2*>(wrow + 8 * i) = make_double2(wn * z0, wn * z1);
             cs[i][0] += wn * z0; cs[i][1] += wn * z1;

@@ -31,7 +31,13 @@
 #define VL_PT 16         // columns per operand tile (= columns per haplotype-update CTA)
 #define VL_ZT_READS 64   // reads per responsibility-update CTA
 #define VL_H_NC 32       // reads per stage of the haplotype-update kernel
-#define VL_STAGES 3
+#define VL_STAGES 3      // pipeline stages the shared memory of a kernel class is sized for (widest layout)
+#ifndef VL_ZSTAGES
+#define VL_ZSTAGES 3     // the same for the responsibility-update kernel
+#endif
+#ifndef VL_MAX_STAGES
+#define VL_MAX_STAGES 8  // stages a narrower layout may use in the same shared memory
+#endif
 #define VL_THREADS 128
 #define VL_MAX_KT 16     // 8-slot tiles of a layout (VL_MAX_CLUSTERS / 8)
 #define VL_ZP_EXTRA 8    // scalars appended to each per-tile column-sum record: data, ent, c, d

@@ -37,7 +37,7 @@ vl_haplo_kernel(const VlProblem* __restrict__ probs, const int2* __restrict__ ti
   constexpr int ST_STRIDE = DM_STAGE + VL_H_NC + VL_H_NC * KSM;   // dm | w | z
   extern __shared__ __align__(128) unsigned char vl_smem[];
   double* stg = reinterpret_cast<double*>(vl_smem);
-  __shared__ uint64_t bars[VL_STAGES];
+  __shared__ uint64_t bars[VL_MAX_STAGES];
   __shared__ double red[VL_THREADS / 32][4];
 
   const int2 tm = tiles[blockIdx.x];
@@ -45,6 +45,10 @@ vl_haplo_kernel(const VlProblem* __restrict__ probs, const int2* __restrict__ ti
   const VlState* S = P.st;
   const int ktl = S->ktl, ktz = S->ktl_z;
   if (S->active == 0 || ktl > KTM || ktz > KTM) return;
+  // a narrow layout has small stages: use the same shared memory for a deeper pipeline (the
+  // loop is bound by the latency of the bulk copies, not by their bandwidth, when kt is small)
+  const int st_stride = DM_STAGE + VL_H_NC + VL_H_NC * vl_ks(ktz);
+  const int nstg = min(VL_MAX_STAGES, (VL_STAGES * ST_STRIDE) / st_stride);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, q = lane & 3;
   const int lg = warp & 1, rh = warp >> 1;
@@ -60,21 +64,20 @@ vl_haplo_kernel(const VlProblem* __restrict__ probs, const int2* __restrict__ ti
   const uint32_t stage_bytes = (uint32_t)((DM_STAGE + VL_H_NC) * sizeof(double)) + z_bytes;
 
   if (tid == 0) {
-#pragma unroll
-    for (int s = 0; s < VL_STAGES; ++s) vl_mbar_init(&bars[s], 1);
+    for (int s = 0; s < nstg; ++s) vl_mbar_init(&bars[s], 1);
     vl_fence_mbar_init();
   }
   __syncthreads();
   auto issue = [&](int c) {
-    const int sn = c % VL_STAGES;
-    double* dst = stg + (size_t)sn * ST_STRIDE;
+    const int sn = c % nstg;
+    double* dst = stg + (size_t)sn * st_stride;
     vl_mbar_expect_tx(&bars[sn], stage_bytes);
     vl_tma_load_1d(dst, dmg + (size_t)c * DM_STAGE, DM_STAGE * sizeof(double), &bars[sn]);
     vl_tma_load_1d(dst + DM_STAGE, wg + (size_t)c * VL_H_NC, VL_H_NC * sizeof(double), &bars[sn]);
     vl_tma_load_1d(dst + DM_STAGE + VL_H_NC, zg + (size_t)c * VL_H_NC * KSz, z_bytes, &bars[sn]);
   };
   if (tid == 0)
-    for (int c = 0; c < VL_STAGES - 1 && c < nchunks; ++c) issue(c);
+    for (int c = 0; c < nstg - 1 && c < nchunks; ++c) issue(c);
 
   // column of the stored z each of this thread's B-fragment columns comes from
   int co[KTM];
@@ -91,10 +94,10 @@ vl_haplo_kernel(const VlProblem* __restrict__ probs, const int2* __restrict__ ti
   vl_dispatch_tiles<KTM>(ktl, [&](auto ktc) {
     constexpr int KT = decltype(ktc)::value;
     for (int c = 0; c < nchunks; ++c) {
-      const int st = c % VL_STAGES;
-      if (tid == 0 && c + VL_STAGES - 1 < nchunks) issue(c + VL_STAGES - 1);
-      vl_mbar_wait(&bars[st], (c / VL_STAGES) & 1);
-      const double* dt = stg + (size_t)st * ST_STRIDE;
+      const int st = c % nstg;
+      if (tid == 0 && c + nstg - 1 < nchunks) issue(c + nstg - 1);
+      vl_mbar_wait(&bars[st], (c / nstg) & 1);
+      const double* dt = stg + (size_t)st * st_stride;
       const double* wt = dt + DM_STAGE;
       const double* zt = wt + VL_H_NC;
 #pragma unroll
@@ -258,8 +261,8 @@ vl_cluster_kernel(const VlProblem* __restrict__ probs, const int2* __restrict__ 
   constexpr int ST_STRIDE = DM_STAGE + VL_PT * KSM;    // dm | gm
   extern __shared__ __align__(128) unsigned char vl_smem[];
   double* stg = reinterpret_cast<double*>(vl_smem);
-  double* red_cs = stg + VL_STAGES * ST_STRIDE;        // [4][K8M]
-  __shared__ uint64_t bars[VL_STAGES];
+  double* red_cs = stg + VL_ZSTAGES * ST_STRIDE;       // [4][K8M]
+  __shared__ uint64_t bars[VL_MAX_STAGES];
   __shared__ double red_sc[VL_THREADS / 32][4];
 
   const int2 tm = tiles[blockIdx.x];
@@ -277,22 +280,24 @@ vl_cluster_kernel(const VlProblem* __restrict__ probs, const int2* __restrict__ 
   const double* __restrict__ gmg = P.gm;
   const uint32_t gm_bytes = (uint32_t)(VL_PT * KS * sizeof(double));
   const uint32_t stage_bytes = (uint32_t)(DM_STAGE * sizeof(double)) + gm_bytes;
+  // narrow layouts: deeper pipeline in the same shared memory (see vl_haplo_kernel)
+  const int st_stride = DM_STAGE + VL_PT * KS;
+  const int nstg = min(VL_MAX_STAGES, (VL_ZSTAGES * ST_STRIDE) / st_stride);
 
   if (tid == 0) {
-#pragma unroll
-    for (int s = 0; s < VL_STAGES; ++s) vl_mbar_init(&bars[s], 1);
+    for (int s = 0; s < nstg; ++s) vl_mbar_init(&bars[s], 1);
     vl_fence_mbar_init();
   }
   __syncthreads();
   auto issue = [&](int c) {
-    const int sn = c % VL_STAGES;
-    double* dst = stg + (size_t)sn * ST_STRIDE;
+    const int sn = c % nstg;
+    double* dst = stg + (size_t)sn * st_stride;
     vl_mbar_expect_tx(&bars[sn], stage_bytes);
     vl_tma_load_1d(dst, dmg + (size_t)c * Npad * VL_PT, DM_STAGE * sizeof(double), &bars[sn]);
     vl_tma_load_1d(dst + DM_STAGE, gmg + (size_t)c * VL_PT * KS, gm_bytes, &bars[sn]);
   };
   if (tid == 0)
-    for (int c = 0; c < VL_STAGES - 1 && c < nst; ++c) issue(c);
+    for (int c = 0; c < nstg - 1 && c < nst; ++c) issue(c);
 
   double acc[2][KTM][2];
 #pragma unroll
@@ -304,10 +309,10 @@ vl_cluster_kernel(const VlProblem* __restrict__ probs, const int2* __restrict__ 
   vl_dispatch_tiles<KTM>(ktl, [&](auto ktc) {
     constexpr int KT = decltype(ktc)::value;
     for (int c = 0; c < nst; ++c) {
-      const int st = c % VL_STAGES;
-      if (tid == 0 && c + VL_STAGES - 1 < nst) issue(c + VL_STAGES - 1);
-      vl_mbar_wait(&bars[st], (c / VL_STAGES) & 1);
-      const double* dt = stg + (size_t)st * ST_STRIDE;
+      const int st = c % nstg;
+      if (tid == 0 && c + nstg - 1 < nst) issue(c + nstg - 1);
+      vl_mbar_wait(&bars[st], (c / nstg) & 1);
+      const double* dt = stg + (size_t)st * st_stride;
       const double* gt = dt + DM_STAGE + g;
 #pragma unroll
       for (int s = 0; s < 4; ++s) {
@@ -655,7 +660,7 @@ constexpr size_t smem_haplo() {
 }
 template <int NB>
 constexpr size_t smem_cluster() {
-  return ((size_t)VL_STAGES * (VL_ZT_READS * VL_PT + VL_PT * vl_ks(4 * NB)) + (VL_THREADS / 32) * 32 * NB) * sizeof(double);
+  return ((size_t)VL_ZSTAGES * (VL_ZT_READS * VL_PT + VL_PT * vl_ks(4 * NB)) + (VL_THREADS / 32) * 32 * NB) * sizeof(double);
 }
 
 template <int NB, int MODE>

@@ -11,8 +11,11 @@ the end of its CAVI loop.
           only the device time of the iteration loop (CUDA events) is counted
   e2e     the same through the host-buffer API: pinned host -> device copy of all inputs, the
           loop, device -> host copy of the results, every step
-  roofline  the dominant kernel's algorithmic FP64 flop rate, timed live with CUDA events,
-          against the FP64 tensor (DMMA) ceiling measured on this pool
+  roofline  the dominant kernel over a whole run, every launch bracketed by CUDA events on the
+          launching stream (a separate, untimed pass over the same workload): algorithmic HBM
+          bytes and executed / algorithmic FP64 flops per launch against the measured HBM copy
+          bandwidth (MEASURED_PEAKS.json) and the FP64 tensor (DMMA) ceiling measured on this
+          pool; the all-clusters-live first updates are reported separately (tensor bound)
   cpu_baseline  the NumPy oracle port (same einsum calls as the reference) on one host core,
           bounded sample, extrapolated with the iteration counts the GPU run took
 
@@ -73,9 +76,76 @@ def shard_items(spec, n_windows, world):
     return items, scheduler.lpt_partition(costs, world)
 
 
-def algorithmic_flops_per_contraction(windows):
-    """2*N*K*L*B per (window, restart) with N = unique reads, B = 5, unpadded."""
-    return sum(2.0 * w.n_reads * w.n_clusters * w.length * 5 * w.n_starts for w in windows)
+def operand_stats(windows):
+    """Per window: unique reads N, padded reads, dense operand columns (real / padded to tiles
+    of 16) and sparse entries, from the library's own layout planner (host only)."""
+    import ctypes as C
+    from viloca_b200 import _capi as capi
+    out = []
+    for w in windows:
+        d = w.desc()
+        ncols, nsp = C.c_int32(0), C.c_int64(0)
+        col_lb = np.full((5 * w.length + 31) // 16 * 16, -1, dtype=np.int32)
+        capi.check(capi.lib.vl_window_plan(C.byref(d), C.byref(ncols), C.byref(nsp), capi.i32_ptr(col_lb)))
+        out.append({"N": w.n_reads, "Npad": -(-w.n_reads // 64) * 64, "L": w.length, "K": w.n_clusters,
+                    "NCs": int(ncols.value), "NC": int((col_lb[:ncols.value] >= 0).sum()), "nnz": int(nsp.value)})
+    return out
+
+
+def launch_work(ops, stats):
+    """Work of ONE launch of each contraction kernel over the restarts still running
+    (stats = CaviBatch.problem_stats(): running, 8-cluster tiles, clusters in the layout).
+    executed flops: what the DMMAs do (padded reads / columns / cluster tiles);
+    algorithmic flops: 2 * N * columns * clusters-in-layout of the formulation the kernels use;
+    dense-equivalent flops: SURVEY.md 8(d)'s 2*N*K*L*B of the reference's einsum (B = 5);
+    bytes: compulsory HBM traffic of the launch (operand streamed once, responsibilities and
+    haplotype tables read / written once)."""
+    ex = alg = dense = bytes_h = bytes_z = 0.0
+    for o, (running, kt, nlay, _) in zip(ops, stats):
+        if not running:
+            continue
+        ex += 2.0 * o["Npad"] * o["NCs"] * 8 * kt
+        alg += 2.0 * o["N"] * o["NC"] * nlay
+        dense += 2.0 * o["N"] * o["K"] * o["L"] * 5
+        dm = 8.0 * o["N"] * o["NC"]
+        zb = 8.0 * o["N"] * nlay
+        tab = 8.0 * o["L"] * 5 * nlay
+        gm = 8.0 * o["NC"] * nlay
+        bytes_h += dm + zb + 8.0 * o["N"] + 2 * tab + gm + 12.0 * o["nnz"]
+        bytes_z += dm + gm + zb + 12.0 * o["nnz"]
+    return {"executed": ex, "algorithmic": alg, "dense_equivalent": dense, "bytes_haplo": bytes_h, "bytes_cluster": bytes_z}
+
+
+def profiled_run(batch, ops):
+    """One whole run with every launch timed (vl_batch_profile_step), in the chunk pattern of
+    vl_batch_run.  Returns per-kernel totals over the run and over its all-clusters-live start."""
+    batch.upload()
+    tot = {k: {"ms": 0.0, "launches": 0, "executed": 0.0, "algorithmic": 0.0, "dense_equivalent": 0.0, "bytes": 0.0}
+           for k in ("haplo", "cluster", "scalar", "resident")}
+    first = None
+    n_chunks = 0
+    while True:
+        before = batch.problem_stats()
+        if not before[:, 0].any():
+            break
+        n = 4 if n_chunks < 6 else 32
+        prof = batch.profile_step(n)
+        after = batch.problem_stats()
+        wb, wa = launch_work(ops, before), launch_work(ops, after)
+        for k in ("haplo", "cluster"):
+            ms, cnt = prof[k]
+            tot[k]["ms"] += ms
+            tot[k]["launches"] += cnt
+            for key in ("executed", "algorithmic", "dense_equivalent"):
+                tot[k][key] += n * 0.5 * (wb[key] + wa[key])
+            tot[k]["bytes"] += n * 0.5 * (wb["bytes_" + k] + wa["bytes_" + k])
+        for k in ("scalar", "resident"):
+            tot[k]["ms"] += prof[k][0]
+            tot[k]["launches"] += prof[k][1]
+        if n_chunks == 0:
+            first = {k: dict(v) for k, v in tot.items()}
+        n_chunks += 1
+    return tot, first
 
 
 class ClockSampler:
@@ -152,13 +222,13 @@ def load_iteration_table(name):
         return None
 
 
-def cpu_baseline_single_core(name, windows, n_updates, budget_s=20.0):
+def cpu_baseline_single_core(name, windows, n_updates, budget_s=12.0):
     """One core, bounded: a few dozen oracle iterations on the first windows, extrapolated to the
     whole workload with the iteration counts the GPU run actually took (cost/iteration is
     linear in N_unique)."""
     spent, read_iters, sample = 0.0, 0.0, []
-    n_iter = 12
-    for i, win in enumerate(windows[:3]):
+    n_iter = 24
+    for i, win in enumerate(windows[:8]):
         dt, n = _oracle_window_iterations(win, n_iter)
         spent += dt
         read_iters += n * win.n_reads
@@ -258,11 +328,11 @@ def run_b200_arm(args):
     ev0.record()
     for _ in range(args.steps):
         batch.upload()
-        launches += len(windows) + 1                    # mcount per window + init
+        launches += 2 * len(windows) + 1                # operand preparation (2 kernels per window) + init
         launches += batch.run()
         run_ms += batch.last_device_ms()
         outcomes = batch.fetch()
-        launches += len(windows)                        # mean_haplo export per window
+        launches += 2 * len(windows)                    # mean_haplo / mean_cluster export per window
     ev1.record()
     barrier()
     e2e_ms = ev0.elapsed_time(ev1)
@@ -271,10 +341,9 @@ def run_b200_arm(args):
         d2h += w.n_clusters * w.length * 5 * 8 + w.n_reads * w.n_clusters * 8 + 2 * w.n_clusters * 8 + 128
         d2h += sum(len(r.history_elbo) for r in o.restarts) * 8
 
-    # per-kernel roofline numbers, measured live (all restarts are still running in the first 10 updates)
-    batch.upload()
-    prof = batch.profile_step(8)
-    flops = algorithmic_flops_per_contraction(windows)
+    # per-kernel roofline numbers: a separate pass with every launch bracketed by CUDA events
+    ops = operand_stats(windows)
+    prof_tot, prof_first = profiled_run(batch, ops)
     n_updates = [o.restarts[o.best_restart].n_updates for o in outcomes]
     all_updates = [r.n_updates for o in outcomes for r in o.restarts]
     read_iters = sum(r.n_updates * w.n_reads for o, w in zip(outcomes, windows) for r in o.restarts)
@@ -300,19 +369,53 @@ def run_b200_arm(args):
         json.dump(table, open(ITER_TABLE, "w"))
 
     if rank == 0:
-        dom = "cluster" if prof["cluster"][0] >= prof["haplo"][0] else "haplo"
-        dom_ms = prof[dom][0] / max(prof[dom][1], 1)
+        kern_ms = {k: v["ms"] for k, v in prof_tot.items()}
+        dom = max(("haplo", "cluster"), key=lambda k: kern_ms[k])
         try:
-            peak = max(r["tflops"] for r in json.load(open(FP64_PEAK_FILE))["results"] if r["kind"] == "dmma884")
-            peak_src = "measured on this pool: DMMA m8n8k4 register loop, profiles/r01_fp64_peak.json (MEASURED_PEAKS.json has no FP64 entry)"
+            fp64_peak = max(r["tflops"] for r in json.load(open(FP64_PEAK_FILE))["results"] if r["kind"] == "dmma884")
+            fp64_src = "DMMA m8n8k4 register loop measured on this pool, profiles/r01_fp64_peak.json"
         except (OSError, ValueError, KeyError):
-            peak, peak_src = 37.0, "fallback: nominal B200 FP64 tensor peak"
+            fp64_peak, fp64_src = 37.0, "fallback: nominal B200 FP64 tensor peak"
+        try:
+            hbm_peak = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
+            hbm_src = "MEASURED_PEAKS.json hbm_gbs (burst copy)"
+        except (OSError, ValueError, KeyError):
+            hbm_peak, hbm_src = 6550.0, "fallback of B200_PROFILING.md"
         traffic = None
         try:
             traffic = json.load(open(TRAFFIC_FILE)).get(args.workload, {}).get(dom)
         except (OSError, ValueError):
             pass
-        achieved = flops / (dom_ms * 1e-3) * 1e-12
+
+        def rates(t):
+            sec = max(t["ms"], 1e-9) * 1e-3
+            return {"ms_per_launch": t["ms"] / max(t["launches"], 1), "launches": t["launches"],
+                    "gbytes_per_s": t["bytes"] / sec * 1e-9, "executed_tflops": t["executed"] / sec * 1e-12,
+                    "algorithmic_tflops": t["algorithmic"] / sec * 1e-12,
+                    "dense_equivalent_tflops": t["dense_equivalent"] / sec * 1e-12}
+
+        whole, start = rates(prof_tot[dom]), rates(prof_first[dom])
+        frac_hbm, frac_fp = whole["gbytes_per_s"] / hbm_peak, whole["executed_tflops"] / fp64_peak
+        bound = "hbm" if frac_hbm >= frac_fp else "tensor"
+        roofline = {
+            "bound": bound, "kernel": f"vl_{dom}_kernel",
+            "achieved": whole["gbytes_per_s"] if bound == "hbm" else whole["executed_tflops"],
+            "peak": hbm_peak if bound == "hbm" else fp64_peak, "unit": "GB/s" if bound == "hbm" else "TFLOP/s",
+            "frac": max(frac_hbm, frac_fp), "traffic": traffic,
+            "peak_source": hbm_src if bound == "hbm" else fp64_src,
+            "whole_run": {**whole, "frac_hbm": frac_hbm, "frac_fp64_executed": frac_fp,
+                          "share_of_kernel_time": kern_ms[dom] / max(sum(kern_ms.values()), 1e-9)},
+            "all_clusters_live_start": {**start, "frac_fp64_executed": start["executed_tflops"] / fp64_peak,
+                                        "frac_hbm": start["gbytes_per_s"] / hbm_peak,
+                                        "note": "first 4 updates, every one of the K clusters still in the layout: tensor bound"},
+            "fp64_peak_tflops": fp64_peak, "fp64_peak_source": fp64_src, "hbm_peak_gbs": hbm_peak,
+            "kernel_ms_whole_run": kern_ms,
+            "convention": "every launch of a separate whole-run pass timed with CUDA events on the launching stream; "
+                          "bytes = compulsory HBM bytes per launch (dense operand N x columns x 8 streamed once, "
+                          "responsibilities / haplotype tables once); executed flops = DMMA work incl. padding; "
+                          "algorithmic flops = 2 N columns clusters-in-layout; dense-equivalent = SURVEY 8(d)'s "
+                          "2 N K L B (B = 5) of the reference's einsum, which this formulation does not execute",
+        }
         line = {
             "metric": METRIC, "value": total_problems * args.steps / (run_ms_max * 1e-3), "unit": UNIT,
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": run_ms_max / args.steps,
@@ -321,6 +424,8 @@ def run_b200_arm(args):
                        "window_length": spec.window_length, "windows_per_gpu": len(windows), "coverage": spec.coverage,
                        "n_unique_mean": float(np.mean([w.n_reads for w in windows])), "n_clusters": spec.n_clusters,
                        "n_starts": spec.n_starts, "haplotypes": spec.n_haplotypes, "parallelism": f"windows x{world}",
+                       "dense_columns_mean": float(np.mean([o["NC"] for o in ops])),
+                       "sparse_entries_mean": float(np.mean([o["nnz"] for o in ops])),
                        "l2": "inputs larger than L2 (working set %.0f MB per GPU, re-uploaded every step)" % (batch.workspace_bytes / 1e6)},
             "e2e": {"value": total_problems * args.steps / (e2e_ms_max * 1e-3), "unit": UNIT,
                     "h2d_bytes_per_step": int(float(tsum[6])), "d2h_bytes_per_step": int(float(tsum[7])),
@@ -330,11 +435,7 @@ def run_b200_arm(args):
             "raw_read_iterations_per_sec": float(tsum[4]) * args.steps / (run_ms_max * 1e-3),
             "iterations": {"mean": float(np.mean(all_updates)), "max": int(max(all_updates)), "min": int(min(all_updates))},
             "clocks": clocks,
-            "roofline": {"bound": "tensor", "kernel": f"vl_{dom}_kernel", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
-                         "frac": achieved / peak, "traffic": traffic, "flops_per_launch": flops,
-                         "ms_per_launch": dom_ms, "peak_source": peak_src,
-                         "other_kernels_ms_per_launch": {k: v[0] / max(v[1], 1) for k, v in prof.items() if k != dom},
-                         "convention": "algorithmic 2*N_unique*K*L*B flops per contraction (B = 5, unpadded), all restarts active"},
+            "roofline": roofline,
         }
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline_single_core(args.workload, windows, n_updates)

@@ -150,9 +150,11 @@ void vl_batch_destroy(vl_batch* batch);
  */
 #define VL_OPT_SKIP_DEAD 1
 /*
- * VL_OPT_RESIDENT (default 1): restarts whose live clusters fit 4 tiles and whose operand fits
- * one SM's shared memory iterate inside a persistent one-CTA-per-restart kernel; 0 keeps every
- * restart on the three per-iteration kernels.  May be changed between runs.
+ * VL_OPT_RESIDENT (default 0): 1 lets restarts whose live clusters fit 4 tiles and whose operand
+ * fits one SM's shared memory iterate inside a persistent one-CTA-per-restart kernel (one pass
+ * over the operand per update, no launches); 0 keeps every restart on the three per-iteration
+ * kernels.  Same results to rounding; pays off when the batch holds many more restarts than the
+ * GPU has SMs.  May be changed between runs.
  */
 #define VL_OPT_RESIDENT 2
 int vl_batch_set_option(vl_batch* batch, int32_t option, int32_t value);

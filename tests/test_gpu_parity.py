@@ -208,6 +208,53 @@ def test_free_running_against_oracle(mode, n_raw, L, K):
     assert br.rel_err(out.state["mean_cluster"], traj.state["mean_cluster"]) < SPEC_TOL
 
 
+@pytest.mark.parametrize("mode,n_raw,L,K,R", [("uqs", 400, 201, 100, 1), ("lep", 300, 120, 24, 1), ("uqs", 300, 150, 30, 3),
+                                              ("lep", 400, 201, 100, 2), ("uqs", 90, 40, 8, 1)])
+def test_resident_kernel_against_oracle(mode, n_raw, L, K, R):
+    """The persistent one-CTA-per-restart kernel (VL_OPT_RESIDENT): restarts enter it as soon as
+    their layout fits 4 cluster tiles (from the first update when K <= 32) and may alternate with
+    the per-iteration kernels at chunk boundaries; same trajectories as the reference."""
+    from viloca_b200 import synthetic
+    engine = _engine()
+    spec = dataclasses.replace(_spec(mode, K, int(L * 0.75)), n_starts=R)
+    win = synthetic.make_window(spec, 5, n_reads=n_raw, length=L)
+    with engine.CaviBatch([win], resident=True) as b:
+        b.upload()
+        b.run()
+        for r in range(R):
+            out = b.fetch(state=r)[0]
+            traj = br.oracle_run(win, restart=r)
+            rr = out.restarts[r]
+            assert (rr.n_iterations, rr.n_updates, rr.exit_message) == (traj.n_iterations, traj.n_updates, traj.exit_message)
+            assert br.rel_err(rr.history_elbo, np.array(traj.history_elbo)) < ENG_TOL
+            assert orc.haplotype_strings(out.state["mean_haplo"]) == orc.haplotype_strings(traj.state["mean_haplo"])
+            assert np.array_equal(out.state["mean_cluster"] == 0, traj.state["mean_cluster"] == 0)
+            assert br.rel_err(out.state["mean_cluster"], traj.state["mean_cluster"]) < SPEC_TOL
+            assert br.rel_err(out.state["mean_haplo"], traj.state["mean_haplo"]) < SPEC_TOL
+            assert br.rel_err(out.state["alpha"], traj.state["alpha"]) < ENG_TOL
+
+
+def test_dead_cluster_skipping_is_exact():
+    """Taking the clusters whose responsibilities are exactly 0 out of the contractions
+    (VL_OPT_SKIP_DEAD, the default) changes nothing but the summation order: same iteration
+    counts and exit states as the all-K computation, ELBO history equal to 1e-12, identical zero
+    pattern of mean_cluster."""
+    from viloca_b200 import synthetic
+    engine = _engine()
+    wins = [synthetic.make_window(_spec(m, K, int(L * 0.75)), 11 + i, n_reads=n, length=L)
+            for i, (m, n, L, K) in enumerate([("uqs", 400, 201, 100), ("lep", 300, 120, 40), ("uqs", 200, 64, 128)])]
+    skip = engine.run_windows(wins, skip_dead=True)
+    dense = engine.run_windows(wins, skip_dead=False)
+    for a, b in zip(skip, dense):
+        ra, rb = a.restarts[0], b.restarts[0]
+        assert (ra.n_iterations, ra.n_updates, ra.status) == (rb.n_iterations, rb.n_updates, rb.status)
+        assert br.rel_err(ra.history_elbo, rb.history_elbo) < 1e-12
+        assert np.array_equal(a.state["mean_cluster"] == 0, b.state["mean_cluster"] == 0)
+        assert br.rel_err(a.state["mean_cluster"], b.state["mean_cluster"]) < 1e-9
+        assert br.rel_err(a.state["mean_haplo"], b.state["mean_haplo"]) < 1e-9
+        assert (a.state["mean_cluster"].sum(axis=0) > 0).sum() < a.state["mean_cluster"].shape[1]   # some cluster died
+
+
 def test_ragged_mixed_batch_equals_single_window_runs():
     """Windows of different N, L, K and mode in one batch give bit-identical results to
     running each alone (problems are independent; the reductions are order-fixed)."""

@@ -20,7 +20,7 @@ def main():
     nw = int(sys.argv[2]) if len(sys.argv) > 2 else None
     wins = synthetic.make_workload(name, nw)
     rows = []
-    resident = os.environ.get("VL_RESIDENT", "1") != "0"
+    resident = os.environ.get("VL_RESIDENT", "0") != "0"
     with engine.CaviBatch(wins, resident=resident) as b:
         b.upload()
         done = 0

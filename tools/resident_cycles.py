@@ -12,7 +12,7 @@ nw = int(sys.argv[2]) if len(sys.argv) > 2 and int(sys.argv[2]) > 0 else None
 wins = [w.pin() for w in synthetic.make_workload(name, nw)]
 labels = ["T sweep", "T->smem", "haplo epilogue", "pass1 dmma", "pass1 sparse", "pass1 softmax", "bar a", "pass2 dmma",
           "bar b", "reduce", "scalar", "", "", "", "iterations", "sum kt"]
-with engine.CaviBatch(wins) as b:
+with engine.CaviBatch(wins, resident=True) as b:
     b.upload()
     buf = (C.c_uint64 * 16)()
     capi.check(capi.lib.vl_debug_counters(buf, 1))

@@ -281,7 +281,7 @@ struct vl_batch {
   size_t off_ht[VL_N_CLASSES][2] = {}, off_zt[VL_N_CLASSES][2] = {};
   int n_sched = 0;
   bool sched_dirty = true;
-  int skip_dead = 1, resident = 1;
+  int skip_dead = 1, resident = 0;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   double last_ms = 0.0;
   bool uploaded = false;

@@ -145,7 +145,7 @@ class CaviBatch:
     """All (window, restart) problems of ``windows`` on one device."""
 
     def __init__(self, windows: Sequence[Window], device: int = 0, stream: Optional[int] = None,
-                 skip_dead: bool = True, resident: bool = True):
+                 skip_dead: bool = True, resident: bool = False):
         if not windows:
             raise ValueError("empty batch")
         self.windows = list(windows)
@@ -167,8 +167,7 @@ class CaviBatch:
         self.launches = 0
         if not skip_dead:
             capi.check(capi.lib.vl_batch_set_option(self._handle, capi.OPT_SKIP_DEAD, 0))
-        if not resident:
-            capi.check(capi.lib.vl_batch_set_option(self._handle, capi.OPT_RESIDENT, 0))
+        capi.check(capi.lib.vl_batch_set_option(self._handle, capi.OPT_RESIDENT, 1 if resident else 0))
 
     # -- lifetime ------------------------------------------------------------------------
     def close(self) -> None:
@@ -325,9 +324,10 @@ class CaviBatch:
         return out
 
 
-def run_windows(windows: Sequence[Window], device: int = 0) -> list:
-    """upload + run + fetch of one batch: the end-to-end call with host buffers."""
-    with CaviBatch(windows, device=device) as batch:
+def run_windows(windows: Sequence[Window], device: int = 0, **options) -> list:
+    """upload + run + fetch of one batch: the end-to-end call with host buffers.  ``options``
+    are the keyword options of :class:`CaviBatch` (skip_dead, resident)."""
+    with CaviBatch(windows, device=device, **options) as batch:
         batch.upload()
         batch.run()
         return batch.fetch()

@@ -197,8 +197,9 @@ int vl_batch_merge_haplo(vl_batch* batch, int32_t window, int32_t restart,
 /*
  * Like vl_batch_step, but brackets every launch with CUDA events on the launching stream and
  * returns the summed device time per kernel (ms) and the launch counts, arrays of 4:
- * [0] haplotype update, [1] responsibility update, [2] scalar update (general path, one launch
- * each per update), [3] resident kernel (one launch does all n_updates of its restarts).
+ * [0] haplotype update, [1] responsibility update incl. the scalar update its last CTA per
+ * restart performs (general path, one launch each per update), [2] unused (0), [3] resident
+ * kernel (one launch does all n_updates of its restarts).
  * Used by bench.py for the live roofline numbers; not a fast path.
  */
 int vl_batch_profile_step(vl_batch* batch, int32_t n_updates, double* ms_out, int64_t* n_out);

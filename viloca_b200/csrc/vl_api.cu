@@ -53,7 +53,7 @@ struct Layout {
   int n_problems = 0;
   size_t data_begin = 0, data_end = 0;   // zero-filled on upload
   size_t probs = 0, states = 0, done = 0, pstat = 0;
-  size_t htiles = 0, ztiles = 0, plist = 0, rlist = 0;
+  size_t htiles = 0, ztiles = 0, rlist = 0;
   size_t raw_codes = 0, raw_lt = 0, raw_lo = 0;      // staging of one window's raw arrays
   size_t export_h = 0, export_z = 0;
   size_t tmp_z = 0, tmp_h = 0, tmp_g = 0, tmp_gm = 0, tmp_hpart = 0, tmp_group = 0, tmp_prob = 0,
@@ -237,7 +237,6 @@ int build_layout(const vl_window_desc* w, int n, Layout& lay, std::string& err) 
   lay.pstat = take((size_t)lay.n_problems * sizeof(int4));
   lay.htiles = take(lay.n_htiles_total * sizeof(int2));
   lay.ztiles = take(lay.n_ztiles_total * sizeof(int2));
-  lay.plist = take((size_t)lay.n_problems * sizeof(int2));
   lay.rlist = take((size_t)lay.n_problems * sizeof(int));
   lay.raw_codes = take(max_nl);
   lay.raw_lt = take(max_nl * 8);
@@ -273,7 +272,7 @@ struct vl_batch {
   std::vector<VlState> states;         // host mirror filled by fetch / upload
   std::vector<int4> pstat;             // host mirror: (running, tiles needed, valid slots, updates)
   // pinned staging of the per-chunk schedule
-  int2* h_htiles = nullptr; int2* h_ztiles = nullptr; int2* h_plist = nullptr; int4* h_pstat = nullptr;
+  int2* h_htiles = nullptr; int2* h_ztiles = nullptr; int4* h_pstat = nullptr;
   int* h_rlist = nullptr;
   int n_res[2] = {};                   // restarts scheduled on the resident kernel, per mode
   size_t off_res[2] = {}, smem_res[2] = {};
@@ -317,7 +316,7 @@ int schedule(vl_batch* b) {
     }
     for (int t = 0; t < P.n_htiles; ++t) ht[cls][m].push_back(make_int2(p, t));
     for (int t = 0; t < P.n_ztiles; ++t) zt[cls][m].push_back(make_int2(p, t));
-    b->h_plist[b->n_sched++] = make_int2(p, vl_class_capacity(cls));
+    ++b->n_sched;
   }
   size_t ho = 0, zo = 0, ro = 0;
   for (int c = 0; c < VL_N_CLASSES; ++c)
@@ -336,7 +335,6 @@ int schedule(vl_batch* b) {
   cudaStream_t s = b->stream;
   if (ho) VL_CUDA(cudaMemcpyAsync(b->dev<int2>(L.htiles), b->h_htiles, ho * sizeof(int2), cudaMemcpyHostToDevice, s));
   if (zo) VL_CUDA(cudaMemcpyAsync(b->dev<int2>(L.ztiles), b->h_ztiles, zo * sizeof(int2), cudaMemcpyHostToDevice, s));
-  if (b->n_sched) VL_CUDA(cudaMemcpyAsync(b->dev<int2>(L.plist), b->h_plist, (size_t)b->n_sched * sizeof(int2), cudaMemcpyHostToDevice, s));
   if (ro) VL_CUDA(cudaMemcpyAsync(b->dev<int>(L.rlist), b->h_rlist, ro * sizeof(int), cudaMemcpyHostToDevice, s));
   b->sched_dirty = false;
   return 0;
@@ -364,21 +362,18 @@ int launch_phase(vl_batch* b, int phase, int64_t* launches) {
         *launches += 1;
       }
       if (phase == 1 && b->n_zt[c][m] > 0) {
-        VL_CUDA(vl_launch_cluster(c, mode, b->d_probs(), b->dev<int2>(L.ztiles) + b->off_zt[c][m], b->n_zt[c][m], b->stream));
+        VL_CUDA(vl_launch_cluster(c, mode, b->d_probs(), b->dev<int2>(L.ztiles) + b->off_zt[c][m], b->n_zt[c][m],
+                                  b->d_done(), b->d_pstat(), b->stream));
         *launches += 1;
       }
     }
-  if (phase == 2 && b->n_sched > 0) {
-    VL_CUDA(vl_launch_scalar(b->d_probs(), b->dev<int2>(L.plist), b->n_sched, b->d_done(), b->d_pstat(), b->stream));
-    *launches += 1;
-  }
   return 0;
 }
 
 int run_iterations(vl_batch* b, int n_iter, int64_t* launches) {
   if (launch_resident(b, n_iter, launches)) return 1;
   for (int it = 0; it < n_iter; ++it)
-    for (int phase = 0; phase < 3; ++phase)
+    for (int phase = 0; phase < 2; ++phase)
       if (launch_phase(b, phase, launches)) return 1;
   return 0;
 }
@@ -513,7 +508,6 @@ int vl_batch_create(vl_batch** out, int32_t device, const vl_window_desc* window
   } while (0)
   VL_CREATE_CUDA(cudaMallocHost(reinterpret_cast<void**>(&b->h_htiles), std::max<size_t>(L.n_htiles_total, 1) * sizeof(int2)));
   VL_CREATE_CUDA(cudaMallocHost(reinterpret_cast<void**>(&b->h_ztiles), std::max<size_t>(L.n_ztiles_total, 1) * sizeof(int2)));
-  VL_CREATE_CUDA(cudaMallocHost(reinterpret_cast<void**>(&b->h_plist), (size_t)L.n_problems * sizeof(int2)));
   VL_CREATE_CUDA(cudaMallocHost(reinterpret_cast<void**>(&b->h_pstat), (size_t)L.n_problems * sizeof(int4)));
   VL_CREATE_CUDA(cudaMallocHost(reinterpret_cast<void**>(&b->h_rlist), (size_t)L.n_problems * sizeof(int)));
   VL_CREATE_CUDA(cudaEventCreate(&b->ev0));
@@ -531,7 +525,6 @@ void vl_batch_destroy(vl_batch* b) {
   cudaSetDevice(b->device);
   if (b->h_htiles) cudaFreeHost(b->h_htiles);
   if (b->h_ztiles) cudaFreeHost(b->h_ztiles);
-  if (b->h_plist) cudaFreeHost(b->h_plist);
   if (b->h_pstat) cudaFreeHost(b->h_pstat);
   if (b->h_rlist) cudaFreeHost(b->h_rlist);
   if (b->ev0) cudaEventDestroy(b->ev0);
@@ -695,7 +688,7 @@ int vl_batch_profile_step(vl_batch* b, int32_t n_updates, double* ms_out, int64_
   // the resident restarts do all n_updates in one launch; the general path is timed per kernel
   if (timed(3, [&](int64_t* n) { return launch_resident(b, n_updates, n); })) return 1;
   for (int it = 0; it < n_updates; ++it)
-    for (int phase = 0; phase < 3; ++phase)
+    for (int phase = 0; phase < 2; ++phase)
       if (timed(phase, [&](int64_t* n) { return launch_phase(b, phase, n); })) return 1;
   if (sync_status(b, nullptr)) return 1;
   for (auto& e : ev) cudaEventDestroy(e);

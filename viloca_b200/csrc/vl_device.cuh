@@ -75,6 +75,8 @@ struct VlState {
   int nlay_z, ghost_z;   // the same for the layout z (and the last h) are stored in
   int skip;       // 1 = remove dead clusters from the layout (exact), 0 = always dense
   int stalled;    // layout grew past the kernel class this restart is scheduled in
+  int ticket;     // read tiles of the current responsibility update that have finished
+  int pad_;
 };
 
 // Read-only description of one (window, restart) problem.

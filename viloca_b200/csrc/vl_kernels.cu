@@ -1,12 +1,13 @@
-// CAVI kernels for sm_100a.  One iteration of a (window, restart) problem = three launches
+// CAVI kernels for sm_100a.  One iteration of a (window, restart) problem = two launches
 // over the whole batch:
 //   vl_haplo_kernel    update_mean_haplo   (uqs update_eqs.py:73-101, lep update_eqs.py:115-159)
 //                      + the sums update_a_and_b / elbo_haplo need (update_eqs.py:103-112,
 //                      elbo_eqs.py:65-78)
 //   vl_cluster_kernel  update_mean_cluster (uqs update_eqs.py:55-71, lep update_eqs.py:90-112)
-//                      + the sums update_alpha / elbo_data / elbo_cluster / update_c_and_d need
-//   vl_scalar_kernel   alpha, mean_log_pi, a, b, (c, d), the ELBO, the loop state machine of
-//                      run_cavi (cavi.py:120-169) and the next live-cluster layout
+//                      + the sums update_alpha / elbo_data / elbo_cluster / update_c_and_d need;
+//                      the CTA of a restart that finishes last then does the scalar update
+//                      (vl_cavi.cuh): alpha, mean_log_pi, a, b, (c, d), the ELBO, the loop state
+//                      machine of run_cavi (cavi.py:120-169) and the next live-cluster layout
 //
 // Both contractions run on the FP64 tensor pipe (DMMA m8n8k4) over the dense majority operand
 // Dm (vl_device.cuh), whose tiles and the other operand (responsibilities or the haplotype
@@ -254,7 +255,8 @@ vl_haplo_kernel(const VlProblem* __restrict__ probs, const int2* __restrict__ ti
 // =========================================================================================
 template <int NB, int MODE>
 __global__ void __launch_bounds__(VL_THREADS)
-vl_cluster_kernel(const VlProblem* __restrict__ probs, const int2* __restrict__ tiles) {
+vl_cluster_kernel(const VlProblem* __restrict__ probs, const int2* __restrict__ tiles,
+                  int* __restrict__ done_count, int4* __restrict__ pstat) {
   constexpr int KTM = 4 * NB;
   constexpr int KSM = vl_ks(KTM), K8M = 8 * KTM;
   constexpr int DM_STAGE = VL_ZT_READS * VL_PT;        // doubles
@@ -453,8 +455,8 @@ vl_cluster_kernel(const VlProblem* __restrict__ probs, const int2* __restrict__ 
     red_sc[warp][0] = s_data; red_sc[warp][1] = s_ent; red_sc[warp][2] = s_c; red_sc[warp][3] = s_d;
   }
   __syncthreads();
-  const int K8rec = 8 * P.KT;
-  double* zp = P.zpart + (size_t)tm.y * (K8rec + VL_ZP_EXTRA);
+  const int K8rec = 8 * P.KT, ZS = K8rec + VL_ZP_EXTRA;
+  double* zp = P.zpart + (size_t)tm.y * ZS;
   for (int k = tid; k < K8 + 4; k += VL_THREADS) {
     double v = 0.0;
     if (k < K8) {
@@ -467,41 +469,36 @@ vl_cluster_kernel(const VlProblem* __restrict__ probs, const int2* __restrict__ 
       zp[K8rec + (k - K8)] = v;
     }
   }
-}
 
-// =========================================================================================
-// Scalar update of the general path: one CTA per scheduled restart; plist entries are
-// (problem, tile capacity of its class).  Sums the per-tile partial records in fixed order and
-// hands over to vl_scalar_update (vl_cavi.cuh).
-// =========================================================================================
-__global__ void __launch_bounds__(VL_THREADS)
-vl_scalar_kernel(const VlProblem* __restrict__ probs, const int2* __restrict__ plist,
-                 int* __restrict__ done_count, int4* __restrict__ pstat) {
+  // ---- the read tile that finishes last closes the iteration of its restart: fixed-order sums
+  // of the per-tile records, then the scalar update (no separate launch, no host decision) ----
   static_assert(VL_THREADS == VL_MAX_CLUSTERS, "one thread per cluster");
-  const int2 pe = plist[blockIdx.x];
-  const VlProblem& P = probs[pe.x];
-  VlState* S = P.st;
-  const int ktl = S->ktl;
-  if (S->active == 0 || ktl > pe.y || S->ktl_z > pe.y) return;
+  __shared__ int s_last;
   __shared__ VlScalarSmem sm;
-  const int tid = threadIdx.x;
-  const int K8rec = 8 * P.KT, ZS = K8rec + VL_ZP_EXTRA;
-  for (int c = tid; c < 8 * ktl + 7; c += VL_THREADS) {
+  VlState* Sw = P.st;
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) s_last = (atomicAdd(&Sw->ticket, 1) == P.n_ztiles - 1);
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  if (tid == 0) Sw->ticket = 0;
+  for (int c = tid; c < K8 + 7; c += VL_THREADS) {
     double v = 0.0;
-    if (c < 8 * ktl) {
-      for (int t = 0; t < P.n_ztiles; ++t) v += P.zpart[(size_t)t * ZS + c];
+    if (c < K8) {
+      for (int t = 0; t < P.n_ztiles; ++t) v += __ldcg(P.zpart + (size_t)t * ZS + c);
       sm.cs[c] = v;
-    } else if (c < 8 * ktl + 4) {
-      const int j = c - 8 * ktl;
-      for (int t = 0; t < P.n_ztiles; ++t) v += P.zpart[(size_t)t * ZS + K8rec + j];
+    } else if (c < K8 + 4) {
+      const int j = c - K8;
+      for (int t = 0; t < P.n_ztiles; ++t) v += __ldcg(P.zpart + (size_t)t * ZS + K8rec + j);
       sm.sc[j] = v;
     } else {
-      const int j = c - 8 * ktl - 4;
+      const int j = c - K8 - 4;
       for (int t = 0; t < P.n_htiles; ++t) v += P.hpart[(size_t)t * VL_HP_STRIDE + j];
       sm.sc[4 + j] = v;
     }
   }
-  vl_scalar_update<0>(P, S, sm, tid, done_count, pstat + pe.x);
+  vl_scalar_update<0>(P, Sw, sm, tid, done_count, pstat + tm.x);
 }
 
 // One thread per problem: state_init_dict of draw_init_state (initialization.py:6-43), the
@@ -540,7 +537,7 @@ __global__ void vl_init_kernel(const VlProblem* __restrict__ probs, int n_probs,
   S->iter = 0; S->n_updates = 0; S->n_hist = 0; S->converged = 0;
   S->status = VL_STATUS_RUNNING; S->active = 1;
   S->ktl = P.KT; S->ktl_z = P.KT; S->nlay = K; S->ghost = -1; S->ghost_mult = 0.0; S->stalled = 0;
-  S->nlay_z = K; S->ghost_z = -1;
+  S->nlay_z = K; S->ghost_z = -1; S->ticket = 0;
   pstat[p] = make_int4(1, P.KT, K, 0);
 }
 
@@ -674,11 +671,12 @@ cudaError_t launch_haplo(const VlProblem* probs, const int2* tiles, int n, cudaS
   return cudaGetLastError();
 }
 template <int NB, int MODE>
-cudaError_t launch_cluster(const VlProblem* probs, const int2* tiles, int n, cudaStream_t stream) {
+cudaError_t launch_cluster(const VlProblem* probs, const int2* tiles, int n, int* done_count, int4* pstat,
+                           cudaStream_t stream) {
   cudaError_t e = cudaFuncSetAttribute(vl_cluster_kernel<NB, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)smem_cluster<NB>());
   if (e != cudaSuccess) return e;
-  vl_cluster_kernel<NB, MODE><<<n, VL_THREADS, smem_cluster<NB>(), stream>>>(probs, tiles);
+  vl_cluster_kernel<NB, MODE><<<n, VL_THREADS, smem_cluster<NB>(), stream>>>(probs, tiles, done_count, pstat);
   return cudaGetLastError();
 }
 
@@ -705,15 +703,9 @@ cudaError_t vl_launch_haplo(int cls, int mode, const VlProblem* probs, const int
 }
 
 cudaError_t vl_launch_cluster(int cls, int mode, const VlProblem* probs, const int2* tiles, int n_tiles,
-                              cudaStream_t stream) {
+                              int* done_count, int4* pstat, cudaStream_t stream) {
   if (n_tiles <= 0) return cudaSuccess;
-  VL_DISPATCH(launch_cluster, probs, tiles, n_tiles, stream)
-}
-
-cudaError_t vl_launch_scalar(const VlProblem* probs, const int2* plist, int n, int* done_count, int4* pstat,
-                             cudaStream_t stream) {
-  if (n > 0) vl_scalar_kernel<<<n, VL_THREADS, 0, stream>>>(probs, plist, done_count, pstat);
-  return cudaGetLastError();
+  VL_DISPATCH(launch_cluster, probs, tiles, n_tiles, done_count, pstat, stream)
 }
 
 cudaError_t vl_launch_init(const VlProblem* probs, int n_probs, int4* pstat, cudaStream_t stream) {

@@ -20,12 +20,10 @@ cudaError_t vl_launch_resident(int mode, const VlProblem* probs, const int* plis
 
 cudaError_t vl_launch_haplo(int cls, int mode, const VlProblem* probs, const int2* tiles, int n_tiles,
                             cudaStream_t stream);
+// pstat[p] receives (still running, tiles needed next, valid slots, updates done) from the scalar
+// update that the last read tile of restart p performs
 cudaError_t vl_launch_cluster(int cls, int mode, const VlProblem* probs, const int2* tiles, int n_tiles,
-                              cudaStream_t stream);
-// plist entries: (problem, tile capacity of the class it is scheduled in); pstat[p] receives
-// (still running, tiles needed next, valid slots, updates done)
-cudaError_t vl_launch_scalar(const VlProblem* probs, const int2* plist, int n, int* done_count, int4* pstat,
-                             cudaStream_t stream);
+                              int* done_count, int4* pstat, cudaStream_t stream);
 cudaError_t vl_launch_init(const VlProblem* probs, int n_probs, int4* pstat, cudaStream_t stream);
 cudaError_t vl_launch_prepare(const uint8_t* codes, const double* lt, const double* lo, const int* col_lb,
                               double* dm, double* mcount, double* ltsum, int N, int L, int Npad, int NCs,

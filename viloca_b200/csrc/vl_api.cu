@@ -7,6 +7,7 @@
 #include <cstdio>
 #include <cstring>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/viloca_b200.h"
@@ -44,6 +45,8 @@ struct WindowLayout {
   size_t nnz_cap;
   int NCs;
   size_t dm, w, ltsum, mcount, ref, col_lb, poscol, tile_pos, sr_ptr, sr_idx, sr_d, sp_ptr, sp_n, sp_wd;
+  size_t meta_end;      // ref .. meta_end is one contiguous block of small per-window arrays
+  size_t arena_off;     // its place in the pinned host arena
   std::vector<RestartLayout> rs;
   int first_problem;
 };
@@ -60,6 +63,7 @@ struct Layout {
          tmp_state = 0, tmp_tiles = 0, tmp_lay = 0, tmp_gat = 0, tmp_mlp = 0;
   size_t total = 0;
   size_t n_htiles_total = 0, n_ztiles_total = 0;
+  size_t arena_bytes = 0;
 };
 
 // What the kernels need to know about the bases of one window (vl_device.cuh): which
@@ -161,6 +165,7 @@ int build_layout(const vl_window_desc* w, int n, Layout& lay, std::string& err) 
   lay.wins.resize(n);
   lay.n_problems = 0;
   lay.data_begin = 0;
+  lay.arena_bytes = 0;
   size_t max_nl = 0, max_exp_h = 0, max_exp_z = 0, max_z = 0, max_h = 0, max_gm = 0;
   int max_htiles = 0;
   WindowAnalysis plan;
@@ -199,6 +204,9 @@ int build_layout(const vl_window_desc* w, int n, Layout& lay, std::string& err) 
     W.sp_ptr = take(((size_t)W.Ls * VL_N_BASES + 1) * 4);
     W.sp_n = take(W.nnz_cap * 4);
     W.sp_wd = take(W.nnz_cap * 8);
+    W.meta_end = off;
+    W.arena_off = lay.arena_bytes;
+    lay.arena_bytes += W.meta_end - W.ref;
     W.rs.resize(W.R);
     W.first_problem = lay.n_problems;
     for (int r = 0; r < W.R; ++r) {
@@ -274,6 +282,7 @@ struct vl_batch {
   // pinned staging of the per-chunk schedule
   int2* h_htiles = nullptr; int2* h_ztiles = nullptr; int4* h_pstat = nullptr;
   int* h_rlist = nullptr;
+  unsigned char* h_arena = nullptr;    // pinned image of every window's small arrays (maps, sparse lists)
   int n_res[2] = {};                   // restarts scheduled on the resident kernel, per mode
   size_t off_res[2] = {}, smem_res[2] = {};
   int n_ht[VL_N_CLASSES][2] = {}, n_zt[VL_N_CLASSES][2] = {};
@@ -510,6 +519,7 @@ int vl_batch_create(vl_batch** out, int32_t device, const vl_window_desc* window
   VL_CREATE_CUDA(cudaMallocHost(reinterpret_cast<void**>(&b->h_ztiles), std::max<size_t>(L.n_ztiles_total, 1) * sizeof(int2)));
   VL_CREATE_CUDA(cudaMallocHost(reinterpret_cast<void**>(&b->h_pstat), (size_t)L.n_problems * sizeof(int4)));
   VL_CREATE_CUDA(cudaMallocHost(reinterpret_cast<void**>(&b->h_rlist), (size_t)L.n_problems * sizeof(int)));
+  VL_CREATE_CUDA(cudaMallocHost(reinterpret_cast<void**>(&b->h_arena), std::max<size_t>(L.arena_bytes, 1)));
   VL_CREATE_CUDA(cudaEventCreate(&b->ev0));
   VL_CREATE_CUDA(cudaEventCreate(&b->ev1));
   VL_CREATE_CUDA(cudaMemcpyAsync(b->d_probs(), b->probs.data(), b->probs.size() * sizeof(VlProblem),
@@ -527,6 +537,7 @@ void vl_batch_destroy(vl_batch* b) {
   if (b->h_ztiles) cudaFreeHost(b->h_ztiles);
   if (b->h_pstat) cudaFreeHost(b->h_pstat);
   if (b->h_rlist) cudaFreeHost(b->h_rlist);
+  if (b->h_arena) cudaFreeHost(b->h_arena);
   if (b->ev0) cudaEventDestroy(b->ev0);
   if (b->ev1) cudaEventDestroy(b->ev1);
   delete b;
@@ -546,8 +557,6 @@ int vl_batch_upload(vl_batch* b, const vl_window_desc* windows, int32_t n_window
   VL_CUDA(cudaSetDevice(b->device));
   cudaStream_t s = b->stream;
   VL_CUDA(cudaMemsetAsync(b->ws + L.data_begin, 0, L.data_end - L.data_begin, s));
-  WindowAnalysis A;
-  std::vector<uint8_t> ref;
   for (int i = 0; i < n_windows; ++i) {
     const vl_window_desc& d = windows[i];
     const WindowLayout& W = L.wins[i];
@@ -555,38 +564,63 @@ int vl_batch_upload(vl_batch* b, const vl_window_desc* windows, int32_t n_window
       return fail("window shape differs from the one the batch was created with");
     if (!d.codes || !d.weights || !d.ref_codes || !d.init_cluster || !d.init_scalars)
       return fail("window input pointer is NULL");
-    const bool uqs = W.mode == VL_MODE_UQS;
-    if (uqs && (!d.log_hit || !d.log_off)) return fail("uqs window without log_hit/log_off");
-    analyze_window(d, W.Npad, W.Ls, A);
-    if (A.nnz > W.nnz_cap || A.NCs != W.NCs) {
-      char buf[240];
-      snprintf(buf, sizeof buf, "window %d: %d dense columns / %zu sparse entries, but the batch was created for %d / %zu; "
-               "create a new batch for these reads", i, A.NCs, A.nnz, W.NCs, W.nnz_cap);
+    if (W.mode == VL_MODE_UQS && (!d.log_hit || !d.log_off)) return fail("uqs window without log_hit/log_off");
+  }
+  // window analysis (dense columns, sparse lists) on host threads, written into the pinned arena
+  // in the device layout of the block [ref .. sp_wd] so that one copy per window uploads it
+  std::vector<int> bad(n_windows, 0);
+  {
+    const int n_threads = std::max(1, std::min<int>({(int)std::thread::hardware_concurrency(), 16, n_windows}));
+    auto work = [&](int t) {
+      WindowAnalysis A;
+      for (int i = t; i < n_windows; i += n_threads) {
+        const vl_window_desc& d = windows[i];
+        const WindowLayout& W = L.wins[i];
+        analyze_window(d, W.Npad, W.Ls, A);
+        if (A.nnz > W.nnz_cap || A.NCs != W.NCs) { bad[i] = 1; continue; }
+        unsigned char* base = b->h_arena + W.arena_off;
+        auto at = [&](size_t ws_off) { return base + (ws_off - W.ref); };
+        std::memset(base, 0, W.meta_end - W.ref);
+        std::memset(at(W.ref), VL_CODE_N, W.Ls);
+        std::memcpy(at(W.ref), d.ref_codes, W.L);
+        std::memcpy(at(W.col_lb), A.col_lb.data(), (size_t)W.NCs * 4);
+        std::memcpy(at(W.poscol), A.poscol.data(), A.poscol.size() * 4);
+        std::memcpy(at(W.tile_pos), A.tile_pos.data(), (size_t)W.NCs * 4);
+        std::memcpy(at(W.sr_ptr), A.sr_ptr.data(), A.sr_ptr.size() * 4);
+        std::memcpy(at(W.sp_ptr), A.sp_ptr.data(), A.sp_ptr.size() * 4);
+        if (A.nnz) {
+          std::memcpy(at(W.sr_idx), A.sr_idx.data(), A.nnz * 4);
+          std::memcpy(at(W.sr_d), A.sr_d.data(), A.nnz * 8);
+          std::memcpy(at(W.sp_n), A.sp_n.data(), A.nnz * 4);
+          std::memcpy(at(W.sp_wd), A.sp_wd.data(), A.nnz * 8);
+        }
+      }
+    };
+    std::vector<std::thread> pool;
+    for (int t = 1; t < n_threads; ++t) pool.emplace_back(work, t);
+    work(0);
+    for (auto& th : pool) th.join();
+  }
+  for (int i = 0; i < n_windows; ++i)
+    if (bad[i]) {
+      char buf[200];
+      snprintf(buf, sizeof buf, "window %d: its reads need more dense columns / sparse entries than the batch was "
+               "created for; create a new batch for these reads", i);
       return fail(buf);
     }
+  for (int i = 0; i < n_windows; ++i) {
+    const vl_window_desc& d = windows[i];
+    const WindowLayout& W = L.wins[i];
+    const bool uqs = W.mode == VL_MODE_UQS;
     const size_t nl = (size_t)W.N * W.L;
-    // the staging area is reused window after window; stream order keeps that safe, but the
-    // host vectors of the analysis are reused too, hence the synchronize at the end of the body
+    // the staging area of the raw arrays is reused window after window; stream order keeps that safe
     VL_CUDA(cudaMemcpyAsync(b->ws + L.raw_codes, d.codes, nl, cudaMemcpyHostToDevice, s));
     if (uqs) {
       VL_CUDA(cudaMemcpyAsync(b->ws + L.raw_lt, d.log_hit, nl * 8, cudaMemcpyHostToDevice, s));
       VL_CUDA(cudaMemcpyAsync(b->ws + L.raw_lo, d.log_off, nl * 8, cudaMemcpyHostToDevice, s));
     }
-    ref.assign(W.Ls, VL_CODE_N);
-    std::memcpy(ref.data(), d.ref_codes, W.L);
-    VL_CUDA(cudaMemcpyAsync(b->ws + W.ref, ref.data(), W.Ls, cudaMemcpyHostToDevice, s));
-    VL_CUDA(cudaMemcpyAsync(b->ws + W.col_lb, A.col_lb.data(), (size_t)W.NCs * 4, cudaMemcpyHostToDevice, s));
-    VL_CUDA(cudaMemcpyAsync(b->ws + W.poscol, A.poscol.data(), A.poscol.size() * 4, cudaMemcpyHostToDevice, s));
-    VL_CUDA(cudaMemcpyAsync(b->ws + W.tile_pos, A.tile_pos.data(), (size_t)W.NCs * 4, cudaMemcpyHostToDevice, s));
+    VL_CUDA(cudaMemcpyAsync(b->ws + W.ref, b->h_arena + W.arena_off, W.meta_end - W.ref, cudaMemcpyHostToDevice, s));
     VL_CUDA(cudaMemcpyAsync(b->ws + W.w, d.weights, (size_t)W.N * 8, cudaMemcpyHostToDevice, s));
-    VL_CUDA(cudaMemcpyAsync(b->ws + W.sr_ptr, A.sr_ptr.data(), A.sr_ptr.size() * 4, cudaMemcpyHostToDevice, s));
-    VL_CUDA(cudaMemcpyAsync(b->ws + W.sp_ptr, A.sp_ptr.data(), A.sp_ptr.size() * 4, cudaMemcpyHostToDevice, s));
-    if (A.nnz) {
-      VL_CUDA(cudaMemcpyAsync(b->ws + W.sr_idx, A.sr_idx.data(), A.nnz * 4, cudaMemcpyHostToDevice, s));
-      VL_CUDA(cudaMemcpyAsync(b->ws + W.sr_d, A.sr_d.data(), A.nnz * 8, cudaMemcpyHostToDevice, s));
-      VL_CUDA(cudaMemcpyAsync(b->ws + W.sp_n, A.sp_n.data(), A.nnz * 4, cudaMemcpyHostToDevice, s));
-      VL_CUDA(cudaMemcpyAsync(b->ws + W.sp_wd, A.sp_wd.data(), A.nnz * 8, cudaMemcpyHostToDevice, s));
-    }
     VL_CUDA(vl_launch_prepare(b->dev<uint8_t>(L.raw_codes), b->dev<double>(L.raw_lt), b->dev<double>(L.raw_lo),
                               b->dev<int>(W.col_lb), b->dev<double>(W.dm), b->dev<double>(W.mcount),
                               b->dev<double>(W.ltsum), W.N, W.L, W.Npad, W.NCs, W.mode, s));
@@ -602,7 +636,6 @@ int vl_batch_upload(vl_batch* b, const vl_window_desc* windows, int32_t n_window
       S.max_iter = W.max_iter;
       S.skip = b->skip_dead;
     }
-    VL_CUDA(cudaStreamSynchronize(s));
   }
   VL_CUDA(cudaMemcpyAsync(b->d_states(), b->states.data(), b->states.size() * sizeof(VlState), cudaMemcpyHostToDevice, s));
   VL_CUDA(cudaMemsetAsync(b->d_done(), 0, 64, s));
@@ -753,24 +786,21 @@ int vl_batch_fetch(vl_batch* b, vl_window_result* results, int32_t n_windows) {
     const RestartLayout& RL = W.rs[sr];
     const int p = W.first_problem + sr;
     const VlState& S = b->states[p];
-    bool used_export = false;
     if (R.mean_haplo) {
       const size_t total = (size_t)W.K * W.L * VL_N_BASES;
       VL_CUDA(vl_launch_export_haplo(b->d_probs() + p, b->dev<double>(L.export_h), total, s));
       VL_CUDA(cudaMemcpyAsync(R.mean_haplo, b->ws + L.export_h, total * 8, cudaMemcpyDeviceToHost, s));
-      used_export = true;
     }
     if (R.mean_cluster) {
       const size_t total = (size_t)W.N * W.K;
       VL_CUDA(vl_launch_export_cluster(b->d_probs() + p, b->dev<double>(L.export_z), total, s));
       VL_CUDA(cudaMemcpyAsync(R.mean_cluster, b->ws + L.export_z, total * 8, cudaMemcpyDeviceToHost, s));
-      used_export = true;
     }
     if (R.alpha) VL_CUDA(cudaMemcpyAsync(R.alpha, b->ws + RL.alpha, (size_t)W.K * 8, cudaMemcpyDeviceToHost, s));
     if (R.mean_log_pi) VL_CUDA(cudaMemcpyAsync(R.mean_log_pi, b->ws + RL.mlp, (size_t)W.K * 8, cudaMemcpyDeviceToHost, s));
     if (R.scalars) fill_scalars(S, R.scalars);
-    // the export buffers are reused by the next window
-    if (used_export) VL_CUDA(cudaStreamSynchronize(s));
+    // the export buffers are reused by the next window: the next export kernel is ordered after
+    // these copies on the same stream
   }
   VL_CUDA(cudaStreamSynchronize(s));
   return 0;

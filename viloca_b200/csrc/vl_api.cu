@@ -35,7 +35,7 @@ inline size_t align_up(size_t x, size_t a = kAlign) { return (x + a - 1) / a * a
 inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
 
 struct RestartLayout {
-  size_t z, h, g, gm, zpart, hpart, alpha, mlp, mlp_lay, lay, gat, lay_z, hist;
+  size_t z, wz, h, g, gm, zpart, hpart, alpha, mlp, mlp_lay, lay, gat, lay_z, hist;
 };
 
 struct WindowLayout {
@@ -59,7 +59,7 @@ struct Layout {
   size_t htiles = 0, ztiles = 0, rlist = 0;
   size_t raw_codes = 0, raw_lt = 0, raw_lo = 0;      // staging of one window's raw arrays
   size_t export_h = 0, export_z = 0;
-  size_t tmp_z = 0, tmp_h = 0, tmp_g = 0, tmp_gm = 0, tmp_hpart = 0, tmp_group = 0, tmp_prob = 0,
+  size_t tmp_z = 0, tmp_wz = 0, tmp_h = 0, tmp_g = 0, tmp_gm = 0, tmp_hpart = 0, tmp_group = 0, tmp_prob = 0,
          tmp_state = 0, tmp_tiles = 0, tmp_lay = 0, tmp_gat = 0, tmp_mlp = 0;
   size_t total = 0;
   size_t n_htiles_total = 0, n_ztiles_total = 0;
@@ -149,11 +149,10 @@ void analyze_window(const vl_window_desc& d, int Npad, int Ls, WindowAnalysis& A
   A.sp_wd.assign(A.nnz, 0.0);
   std::vector<int> fill(A.sp_ptr.begin(), A.sp_ptr.end() - 1);
   for (int n = 0; n < N; ++n) {
-    const double wn = d.weights[n];
     for (int e = A.sr_ptr[n]; e < A.sr_ptr[n + 1]; ++e) {
       const int at = fill[A.sr_idx[e]]++;
       A.sp_n[at] = n;
-      A.sp_wd[at] = wn * A.sr_d[e];
+      A.sp_wd[at] = A.sr_d[e];
     }
   }
 }
@@ -212,6 +211,7 @@ int build_layout(const vl_window_desc* w, int n, Layout& lay, std::string& err) 
     for (int r = 0; r < W.R; ++r) {
       RestartLayout& RL = W.rs[r];
       RL.z = take((size_t)W.Npad * W.KS * 8);
+      RL.wz = take((size_t)W.Npad * W.KS * 8);
       RL.h = take((size_t)W.Ls * VL_N_BASES * W.KS * 8);
       RL.g = take((size_t)W.Ls * VL_N_BASES * W.KS * 8);
       RL.gm = take((size_t)W.NCs * W.KS * 8);
@@ -252,6 +252,7 @@ int build_layout(const vl_window_desc* w, int n, Layout& lay, std::string& err) 
   lay.export_h = take(max_exp_h);
   lay.export_z = take(max_exp_z);
   lay.tmp_z = take(max_z);
+  lay.tmp_wz = take(max_z);
   lay.tmp_h = take(max_h);
   lay.tmp_g = take(max_h);
   lay.tmp_gm = take(max_gm);
@@ -491,9 +492,9 @@ int vl_batch_create(vl_batch** out, int32_t device, const vl_window_desc* window
       P.ref = b->dev<uint8_t>(W.ref);
       P.col_lb = b->dev<int>(W.col_lb); P.poscol = b->dev<int>(W.poscol); P.tile_pos = b->dev<int>(W.tile_pos);
       P.sr_ptr = b->dev<int>(W.sr_ptr); P.sr_idx = b->dev<int>(W.sr_idx); P.sr_d = b->dev<double>(W.sr_d);
-      P.sp_ptr = b->dev<int>(W.sp_ptr); P.sp_n = b->dev<int>(W.sp_n); P.sp_wd = b->dev<double>(W.sp_wd);
+      P.sp_ptr = b->dev<int>(W.sp_ptr); P.sp_n = b->dev<int>(W.sp_n); P.sp_d = b->dev<double>(W.sp_wd);
       const RestartLayout& RL = W.rs[r];
-      P.z = b->dev<double>(RL.z); P.h = b->dev<double>(RL.h);
+      P.z = b->dev<double>(RL.z); P.wz = b->dev<double>(RL.wz); P.h = b->dev<double>(RL.h);
       P.g = b->dev<double>(RL.g); P.gm = b->dev<double>(RL.gm);
       P.zpart = b->dev<double>(RL.zpart); P.hpart = b->dev<double>(RL.hpart);
       P.alpha = b->dev<double>(RL.alpha); P.mlp = b->dev<double>(RL.mlp);
@@ -627,6 +628,7 @@ int vl_batch_upload(vl_batch* b, const vl_window_desc* windows, int32_t n_window
     for (int r = 0; r < W.R; ++r) {
       VL_CUDA(cudaMemcpy2DAsync(b->ws + W.rs[r].z, (size_t)W.KS * 8, d.init_cluster + (size_t)r * W.N * W.K,
                                 (size_t)W.K * 8, (size_t)W.K * 8, W.N, cudaMemcpyHostToDevice, s));
+      VL_CUDA(vl_launch_scale_rows(b->dev<double>(W.rs[r].z), b->dev<double>(W.w), b->dev<double>(W.rs[r].wz), W.Npad, W.KS, s));
       VlState& S = b->states[W.first_problem + r];
       std::memset(&S, 0, sizeof S);
       const double* in = d.init_scalars + (size_t)r * VL_INIT_STRIDE;
@@ -826,6 +828,7 @@ int vl_batch_set_state(vl_batch* b, int32_t window, int32_t restart, const doubl
   std::memcpy(lp.data(), mean_log_pi, (size_t)W.K * 8);
   VL_CUDA(cudaMemsetAsync(b->ws + RL.z, 0, (size_t)W.Npad * W.KS * 8, s));
   VL_CUDA(cudaMemcpy2DAsync(b->ws + RL.z, (size_t)W.KS * 8, mean_cluster, (size_t)W.K * 8, (size_t)W.K * 8, W.N, cudaMemcpyHostToDevice, s));
+  VL_CUDA(vl_launch_scale_rows(b->dev<double>(RL.z), b->dev<double>(W.w), b->dev<double>(RL.wz), W.Npad, W.KS, s));
   VL_CUDA(cudaMemcpyAsync(b->ws + RL.mlp, lp.data(), (size_t)W.K8 * 8, cudaMemcpyHostToDevice, s));
   VL_CUDA(cudaMemcpyAsync(b->ws + RL.mlp_lay, lp.data(), (size_t)W.K8 * 8, cudaMemcpyHostToDevice, s));
   VL_CUDA(cudaMemcpyAsync(b->ws + RL.lay, lay.data(), (size_t)W.K8 * 4, cudaMemcpyHostToDevice, s));
@@ -866,13 +869,13 @@ int vl_batch_merge_haplo(vl_batch* b, int32_t window, int32_t restart, const int
   const int p = W.first_problem + restart;
   const int G = n_groups, KTg = (G + 7) / 8, KSg = vl_ks(KTg);
   VL_CUDA(cudaMemcpyAsync(b->ws + L.tmp_group, group_of, (size_t)W.K * sizeof(int), cudaMemcpyHostToDevice, s));
-  VL_CUDA(vl_launch_merge(b->d_probs() + p, b->dev<double>(L.tmp_z), b->dev<int>(L.tmp_group), G, KSg,
-                          (size_t)W.Npad * KSg, s));
+  VL_CUDA(vl_launch_merge(b->d_probs() + p, b->dev<double>(L.tmp_z), b->dev<double>(L.tmp_wz), b->dev<int>(L.tmp_group),
+                          G, KSg, (size_t)W.Npad * KSg, s));
   // a one-problem batch: same window tensors, merged responsibilities in an identity layout
   // over the G groups, scratch outputs
   VlProblem T = b->probs[p];
   T.K = G; T.KT = KTg;
-  T.z = b->dev<double>(L.tmp_z);
+  T.z = b->dev<double>(L.tmp_z); T.wz = b->dev<double>(L.tmp_wz);
   T.h = b->dev<double>(L.tmp_h); T.g = b->dev<double>(L.tmp_g); T.gm = b->dev<double>(L.tmp_gm);
   T.hpart = b->dev<double>(L.tmp_hpart);
   T.lay = b->dev<int>(L.tmp_lay); T.lay_z = b->dev<int>(L.tmp_lay); T.gat = b->dev<int>(L.tmp_gat);

@@ -30,7 +30,7 @@
 // tile geometry (see DESIGN.md "Kernels")
 #define VL_PT 16         // columns per operand tile (= columns per haplotype-update CTA)
 #define VL_ZT_READS 64   // reads per responsibility-update CTA
-#define VL_H_NC 32       // reads per stage of the haplotype-update kernel
+#define VL_H_NC 32       // reads per stage of the haplotype-update kernel (8 per warp)
 #define VL_STAGES 3      // pipeline stages the shared memory of a kernel class is sized for (widest layout)
 #ifndef VL_ZSTAGES
 #define VL_ZSTAGES 3     // the same for the responsibility-update kernel
@@ -98,9 +98,10 @@ struct VlProblem {
   const double* sr_d;      //   d[n,l]
   const int* sp_ptr;       // [Ls*5+1] ... and by (position, base), reads ascending
   const int* sp_n;         //   n
-  const double* sp_wd;     //   w_n * d[n,l]
+  const double* sp_d;      //   d[n,l]
   // restart tensors; "slot" = column of the current layout
   double* z;               // [Npad][vl_ks(ktl_z)]   mean_cluster
+  double* wz;              // [Npad][vl_ks(ktl_z)]   w_n * mean_cluster (operand of the haplotype update)
   double* h;               // [Ls][5][vl_ks(ktl)]    mean_haplo
   double* g;               // [Ls][5][vl_ks(ktl)]    1 - mean_haplo, summed from the other bases
   double* gm;              // [NCs][vl_ks(ktl)]      g at the (position, base) of each dense column

@@ -35,7 +35,7 @@ vl_haplo_kernel(const VlProblem* __restrict__ probs, const int2* __restrict__ ti
   constexpr int KTM = 4 * NB;
   constexpr int KSM = vl_ks(KTM);
   constexpr int DM_STAGE = VL_H_NC * VL_PT;            // doubles
-  constexpr int ST_STRIDE = DM_STAGE + VL_H_NC + VL_H_NC * KSM;   // dm | w | z
+  constexpr int ST_STRIDE = DM_STAGE + VL_H_NC * KSM;   // dm | wz
   extern __shared__ __align__(128) unsigned char vl_smem[];
   double* stg = reinterpret_cast<double*>(vl_smem);
   __shared__ uint64_t bars[VL_MAX_STAGES];
@@ -46,23 +46,20 @@ vl_haplo_kernel(const VlProblem* __restrict__ probs, const int2* __restrict__ ti
   const VlState* S = P.st;
   const int ktl = S->ktl, ktz = S->ktl_z;
   if (S->active == 0 || ktl > KTM || ktz > KTM) return;
-  // a narrow layout has small stages: use the same shared memory for a deeper pipeline (the
-  // loop is bound by the latency of the bulk copies, not by their bandwidth, when kt is small)
-  const int st_stride = DM_STAGE + VL_H_NC + VL_H_NC * vl_ks(ktz);
+  // a narrow layout has small stages: use the same shared memory for a deeper pipeline
+  const int st_stride = DM_STAGE + VL_H_NC * vl_ks(ktz);
   const int nstg = min(VL_MAX_STAGES, (VL_STAGES * ST_STRIDE) / st_stride);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, q = lane & 3;
-  const int lg = warp & 1, rh = warp >> 1;
   const int Npad = P.Npad;
   const int KSz = vl_ks(ktz), KSn = vl_ks(ktl), K8 = 8 * ktl;
   const int nlay = S->nlay;
   const int nchunks = Npad / VL_H_NC;
   const double* __restrict__ dmg = P.dm + (size_t)tm.y * Npad * VL_PT;
-  const double* __restrict__ zg = P.z;
-  const double* __restrict__ wg = P.w;
+  const double* __restrict__ wzg = P.wz;
   const int* __restrict__ gat = P.gat;
   const uint32_t z_bytes = (uint32_t)(VL_H_NC * KSz * sizeof(double));
-  const uint32_t stage_bytes = (uint32_t)((DM_STAGE + VL_H_NC) * sizeof(double)) + z_bytes;
+  const uint32_t stage_bytes = (uint32_t)(DM_STAGE * sizeof(double)) + z_bytes;
 
   if (tid == 0) {
     for (int s = 0; s < nstg; ++s) vl_mbar_init(&bars[s], 1);
@@ -74,24 +71,27 @@ vl_haplo_kernel(const VlProblem* __restrict__ probs, const int2* __restrict__ ti
     double* dst = stg + (size_t)sn * st_stride;
     vl_mbar_expect_tx(&bars[sn], stage_bytes);
     vl_tma_load_1d(dst, dmg + (size_t)c * DM_STAGE, DM_STAGE * sizeof(double), &bars[sn]);
-    vl_tma_load_1d(dst + DM_STAGE, wg + (size_t)c * VL_H_NC, VL_H_NC * sizeof(double), &bars[sn]);
-    vl_tma_load_1d(dst + DM_STAGE + VL_H_NC, zg + (size_t)c * VL_H_NC * KSz, z_bytes, &bars[sn]);
+    vl_tma_load_1d(dst + DM_STAGE, wzg + (size_t)c * VL_H_NC * KSz, z_bytes, &bars[sn]);
   };
   if (tid == 0)
     for (int c = 0; c < nstg - 1 && c < nchunks; ++c) issue(c);
 
-  // column of the stored z each of this thread's B-fragment columns comes from
+  // column of the stored w z each of this thread's B-fragment columns comes from
   int co[KTM];
 #pragma unroll
   for (int i = 0; i < KTM; ++i) {
     const int s = 8 * i + g;
     co[i] = (i < ktl && s < nlay) ? gat[s] : 0;
   }
-  double acc[KTM][2];
+  // warp = all 16 columns (two m-tiles) x 8 of the 32 reads of every stage: one w z fragment
+  // feeds two DMMAs
+  double acc[2][KTM][2];
 #pragma unroll
-  for (int i = 0; i < KTM; ++i) { acc[i][0] = 0.0; acc[i][1] = 0.0; }
+  for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+    for (int i = 0; i < KTM; ++i) { acc[mt][i][0] = 0.0; acc[mt][i][1] = 0.0; }
 
-  const int acol = (lg * 8 + g + 4 * q) & 15;      // vl_dm_col(row, lg*8+g) with row % 4 == q
+  const int acol0 = (g + 4 * q) & 15, acol1 = (8 + g + 4 * q) & 15;   // vl_dm_col(row, g / 8 + g), row % 4 == q
   vl_dispatch_tiles<KTM>(ktl, [&](auto ktc) {
     constexpr int KT = decltype(ktc)::value;
     for (int c = 0; c < nchunks; ++c) {
@@ -99,38 +99,42 @@ vl_haplo_kernel(const VlProblem* __restrict__ probs, const int2* __restrict__ ti
       if (tid == 0 && c + nstg - 1 < nchunks) issue(c + nstg - 1);
       vl_mbar_wait(&bars[st], (c / nstg) & 1);
       const double* dt = stg + (size_t)st * st_stride;
-      const double* wt = dt + DM_STAGE;
-      const double* zt = wt + VL_H_NC;
+      const double* zt = dt + DM_STAGE;
 #pragma unroll
-      for (int s = 0; s < 4; ++s) {
-        const int row = rh * 16 + 4 * s + q;
-        const double a = wt[row] * dt[row * VL_PT + acol];
+      for (int s = 0; s < VL_H_NC / 16; ++s) {
+        const int row = warp * (VL_H_NC / 4) + 4 * s + q;
+        const double a0 = dt[row * VL_PT + acol0];
+        const double a1 = dt[row * VL_PT + acol1];
         const double* zr = zt + row * KSz;
 #pragma unroll
-        for (int i = 0; i < KT; ++i) vl_dmma(acc[i], a, zr[co[i]]);
+        for (int i = 0; i < KT; ++i) {
+          const double bf = zr[co[i]];
+          vl_dmma(acc[0][i], a0, bf);
+          vl_dmma(acc[1][i], a1, bf);
+        }
       }
       __syncthreads();
     }
   });
 
-  // ---- the stage buffers are free now: T [16][K8] and Cm [16][5][K8] live in them ----
+  // ---- the stage buffers are free now: T [16][K8] and Cm [16][5][K8] live in them; the four
+  // warps add their partial sums over the reads into T one after the other (fixed order) ----
   double* T = stg;
   double* Cm = stg + VL_PT * K8;
-  if (rh == 1) {
+  for (int turn = 0; turn < VL_THREADS / 32; ++turn) {
+    if (warp == turn) {
 #pragma unroll
-    for (int i = 0; i < KTM; ++i)
-      if (i < ktl)
-        *reinterpret_cast<double2*>(T + (lg * 8 + g) * K8 + 8 * i + 2 * q) = make_double2(acc[i][0], acc[i][1]);
-  }
-  __syncthreads();
-  if (rh == 0) {
+      for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
-    for (int i = 0; i < KTM; ++i)
-      if (i < ktl) {
-        double2* tp = reinterpret_cast<double2*>(T + (lg * 8 + g) * K8 + 8 * i + 2 * q);
-        const double2 o = *tp;
-        *tp = make_double2(acc[i][0] + o.x, acc[i][1] + o.y);
-      }
+        for (int i = 0; i < KTM; ++i)
+          if (i < ktl) {
+            double2* tp = reinterpret_cast<double2*>(T + (mt * 8 + g) * K8 + 8 * i + 2 * q);
+            double2 o = make_double2(0.0, 0.0);
+            if (turn > 0) o = *tp;
+            *tp = make_double2(o.x + acc[mt][i][0], o.y + acc[mt][i][1]);
+          }
+    }
+    if (turn + 1 < VL_THREADS / 32) __syncthreads();
   }
   // sparse entries of the positions whose columns lie in this tile: warp = 4 of them,
   // lanes = slots
@@ -138,7 +142,7 @@ vl_haplo_kernel(const VlProblem* __restrict__ probs, const int2* __restrict__ ti
   {
     const int* __restrict__ sp_ptr = P.sp_ptr;
     const int* __restrict__ sp_n = P.sp_n;
-    const double* __restrict__ sp_wd = P.sp_wd;
+    const double* __restrict__ sp_d = P.sp_d;
     int gl[NB];
 #pragma unroll
     for (int j = 0; j < NB; ++j) {
@@ -156,8 +160,8 @@ vl_haplo_kernel(const VlProblem* __restrict__ probs, const int2* __restrict__ ti
         for (int j = 0; j < NB; ++j) av[j] = 0.0;
 #pragma unroll 4
         for (int e = e0; e < e1; ++e) {
-          const double wd = sp_wd[e];
-          const double* zr = zg + (size_t)sp_n[e] * KSz;
+          const double wd = sp_d[e];
+          const double* zr = wzg + (size_t)sp_n[e] * KSz;
 #pragma unroll
           for (int j = 0; j < NB; ++j) av[j] += wd * zr[gl[j]];
         }
@@ -428,14 +432,17 @@ vl_cluster_kernel(const VlProblem* __restrict__ probs, const int2* __restrict__ 
       }
     }
     double* zrow = P.z + (size_t)n * KS + 2 * q;
+    double* wzrow = P.wz + (size_t)n * KS + 2 * q;
 #pragma unroll
     for (int i = 0; i < KTM; ++i)
       if (i < ktl) {
         const double z0 = valid ? t[i][0] * rsum : 0.0;
         const double z1 = valid ? t[i][1] * rsum : 0.0;
+        const double wz0 = wn * z0, wz1 = wn * z1;
         *reinterpret_cast<double2*>(zrow + 8 * i) = make_double2(z0, z1);
-        if (mt == 0) { cs[i][0] = wn * z0; cs[i][1] = wn * z1; }
-        else { cs[i][0] += wn * z0; cs[i][1] += wn * z1; }
+        *reinterpret_cast<double2*>(wzrow + 8 * i) = make_double2(wz0, wz1);
+        if (mt == 0) { cs[i][0] = wz0; cs[i][1] = wz1; }
+        else { cs[i][0] += wz0; cs[i][1] += wz1; }
       }
   }
 #pragma unroll
@@ -624,7 +631,7 @@ __global__ void vl_export_cluster_kernel(const VlProblem* __restrict__ prob, dou
 // merge_cluster_assignments (analyze_results.py:160-167): members added in ascending k;
 // output rows have the stride of an identity layout over G groups
 __global__ void vl_merge_kernel(const VlProblem* __restrict__ prob, double* __restrict__ zm,
-                                const int* __restrict__ group_of, int G, int KSg) {
+                                double* __restrict__ wzm, const int* __restrict__ group_of, int G, int KSg) {
   __shared__ int slot_of[VL_MAX_CLUSTERS];
   const VlProblem& P = *prob;
   build_slot_table(P, slot_of);
@@ -637,7 +644,16 @@ __global__ void vl_merge_kernel(const VlProblem* __restrict__ prob, double* __re
     if (j < G && n < (size_t)P.N)
       for (int k = 0; k < P.K; ++k) if (group_of[k] == j) s += P.z[n * KS + slot_of[k]];
     zm[i] = s;
+    wzm[i] = P.w[n] * s;
   }
+}
+
+// w z of a responsibility matrix that arrived from the host (initial state, teacher forcing)
+__global__ void vl_scale_rows_kernel(const double* __restrict__ z, const double* __restrict__ w,
+                                     double* __restrict__ wz, int Npad, int KS) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (size_t)Npad * KS) return;
+  wz[i] = w[i / KS] * z[i];
 }
 
 // test hook: the softmax exponential on arbitrary non-positive inputs
@@ -653,7 +669,7 @@ __global__ void vl_exp_test_kernel(const double* __restrict__ x, double* __restr
 
 template <int NB>
 constexpr size_t smem_haplo() {
-  return (size_t)VL_STAGES * (VL_H_NC * VL_PT + VL_H_NC + VL_H_NC * vl_ks(4 * NB)) * sizeof(double);
+  return (size_t)VL_STAGES * (VL_H_NC * VL_PT + VL_H_NC * vl_ks(4 * NB)) * sizeof(double);
 }
 template <int NB>
 constexpr size_t smem_cluster() {
@@ -722,6 +738,12 @@ cudaError_t vl_launch_prepare(const uint8_t* codes, const double* lt, const doub
   return cudaGetLastError();
 }
 
+cudaError_t vl_launch_scale_rows(const double* z, const double* w, double* wz, int Npad, int KS, cudaStream_t stream) {
+  const size_t total = (size_t)Npad * KS;
+  vl_scale_rows_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(z, w, wz, Npad, KS);
+  return cudaGetLastError();
+}
+
 cudaError_t vl_launch_exp_test(const double* x, double* out, int n, cudaStream_t stream) {
   vl_exp_test_kernel<<<(n / 2 + 128) / 128, 128, 0, stream>>>(x, out, n);
   return cudaGetLastError();
@@ -741,8 +763,8 @@ cudaError_t vl_launch_export_cluster(const VlProblem* prob, double* out, size_t 
   return cudaGetLastError();
 }
 
-cudaError_t vl_launch_merge(const VlProblem* prob, double* zm, const int* group_of, int G, int KSg,
+cudaError_t vl_launch_merge(const VlProblem* prob, double* zm, double* wzm, const int* group_of, int G, int KSg,
                             size_t total, cudaStream_t stream) {
-  vl_merge_kernel<<<export_grid(total), 256, 0, stream>>>(prob, zm, group_of, G, KSg);
+  vl_merge_kernel<<<export_grid(total), 256, 0, stream>>>(prob, zm, wzm, group_of, G, KSg);
   return cudaGetLastError();
 }

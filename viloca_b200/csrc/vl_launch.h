@@ -30,6 +30,7 @@ cudaError_t vl_launch_prepare(const uint8_t* codes, const double* lt, const doub
                               int mode, cudaStream_t stream);
 cudaError_t vl_launch_export_haplo(const VlProblem* prob, double* out, size_t total, cudaStream_t stream);
 cudaError_t vl_launch_export_cluster(const VlProblem* prob, double* out, size_t total, cudaStream_t stream);
-cudaError_t vl_launch_merge(const VlProblem* prob, double* zm, const int* group_of, int G, int KSg,
+cudaError_t vl_launch_merge(const VlProblem* prob, double* zm, double* wzm, const int* group_of, int G, int KSg,
                             size_t total, cudaStream_t stream);
+cudaError_t vl_launch_scale_rows(const double* z, const double* w, double* wz, int Npad, int KS, cudaStream_t stream);
 cudaError_t vl_launch_exp_test(const double* x, double* out, int n, cudaStream_t stream);

@@ -205,7 +205,7 @@ vl_resident_kernel(const VlProblem* __restrict__ probs, const int* __restrict__ 
         for (int idx = tid; idx < VL_ZT_READS * K8; idx += RS_CONSUMERS) {
           const int row = idx / K8, s = idx - row * K8;
           const int n = rt * VL_ZT_READS + row;
-          wz_s[row * KS + s] = (s < nlay) ? wg[n] * P.z[(size_t)n * KSz + gat[s]] : 0.0;
+          wz_s[row * KS + s] = (s < nlay) ? P.wz[(size_t)n * KSz + gat[s]] : 0.0;
         }
         vl_bar_sync<BAR_ALL>(RS_CONSUMERS);
         pass2(kt, KS, true);
@@ -291,7 +291,7 @@ vl_resident_kernel(const VlProblem* __restrict__ probs, const int* __restrict__ 
             } else {
               cb = 0.0;
               for (int e = cur.ep[b]; e < cur.ep[b + 1]; ++e)
-                cb += P.sp_wd[e] * P.z[(size_t)P.sp_n[e] * KSz + zcol];
+                cb += P.sp_d[e] * P.wz[(size_t)P.sp_n[e] * KSz + zcol];
             }
             lgt[b] = ((MODE == VL_MODE_LEP) ? cscale * cb : cb) + ((rc == (unsigned)b) ? mlg0 : refoff);
           }
@@ -438,6 +438,7 @@ vl_resident_kernel(const VlProblem* __restrict__ probs, const int* __restrict__ 
           }
         }
         double* zrow = P.z + (size_t)n * KS + 2 * q;
+        double* wzrow = P.wz + (size_t)n * KS + 2 * q;
         double* wrow = wz_s + r0 * KS + 2 * q;
 #pragma unroll
         for (int i = 0; i < RS_KTM; ++i)
@@ -445,6 +446,7 @@ vl_resident_kernel(const VlProblem* __restrict__ probs, const int* __restrict__ 
             const double z0 = valid ? t[i][0] * rsum : 0.0;
             const double z1 = valid ? t[i][1] * rsum : 0.0;
             *reinterpret_cast<double2*>(zrow + 8 * i) = make_double2(z0, z1);
+            *reinterpret_cast<double2*>(wzrow + 8 * i) = make_double2(wn * z0, wn * z1);
             *reinterpret_cast<double2*>(wrow + 8 * i) = make_double2(wn * z0, wn * z1);
             cs[i][0] += wn * z0; cs[i][1] += wn * z1;
           }

@@ -157,6 +157,13 @@ void vl_batch_destroy(vl_batch* batch);
  * GPU has SMs.  May be changed between runs.
  */
 #define VL_OPT_RESIDENT 2
+/*
+ * VL_OPT_FUSED_CHUNKS (default 1): vl_batch_run enqueues a whole chunk of updates of a kernel
+ * class as ONE launch whose blocks wait on per-restart counters in device memory, instead of two
+ * launches per update; 0 restores the per-update launches (vl_batch_step and
+ * vl_batch_profile_step always use those).  Same arithmetic, bit-identical results.
+ */
+#define VL_OPT_FUSED_CHUNKS 3
 int vl_batch_set_option(vl_batch* batch, int32_t option, int32_t value);
 
 /* Host -> device copy of every window's inputs and initial state; resets all restarts. */
@@ -220,10 +227,12 @@ int vl_batch_problem_stats(vl_batch* batch, int32_t* out, int32_t n_problems);
 int vl_debug_exp(int32_t device, const double* x, double* out, int32_t n);
 
 /*
- * Development aid: per-phase cycle counters of one CTA of the resident kernel (16 values).
- * Fails unless the library was built with -DVL_RS_PROFILE (python -m viloca_b200.build --profile).
+ * Development aid: per-phase cycle counters, 36 values: [0..15] one CTA of the resident kernel,
+ * [16..35] tile 0 of restart 0 in the general-path kernels (slot meanings in vl_resident.cu /
+ * vl_kernels.cu).  Fails unless the library was built with -DVL_RS_PROFILE
+ * (python -m viloca_b200.build --profile).
  */
-int vl_debug_counters(uint64_t* out16, int32_t reset);
+int vl_debug_counters(uint64_t* out36, int32_t reset);
 
 /* Milliseconds the last vl_batch_run / vl_batch_step spent on the device (CUDA events). */
 double vl_batch_last_device_ms(const vl_batch* batch);

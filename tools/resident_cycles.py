@@ -14,7 +14,7 @@ labels = ["T sweep", "T->smem", "haplo epilogue", "pass1 dmma", "pass1 sparse", 
           "bar b", "reduce", "scalar", "", "", "", "iterations", "sum kt"]
 with engine.CaviBatch(wins, resident=True) as b:
     b.upload()
-    buf = (C.c_uint64 * 16)()
+    buf = (C.c_uint64 * 36)()
     capi.check(capi.lib.vl_debug_counters(buf, 1))
     t0 = time.perf_counter(); b.run(); t1 = time.perf_counter()
     capi.check(capi.lib.vl_debug_counters(buf, 0))

@@ -14,7 +14,8 @@ nw = int(sys.argv[2]) if len(sys.argv) > 2 and int(sys.argv[2]) > 0 else None
 rep = int(sys.argv[3]) if len(sys.argv) > 3 else 1
 wins = [w.pin() for w in synthetic.make_workload(name, nw)]
 resident = os.environ.get("VL_RESIDENT", "0") != "0"
-with engine.CaviBatch(wins, resident=resident) as b:
+fused = os.environ.get("VL_FUSED", "1") != "0"
+with engine.CaviBatch(wins, resident=resident, fused_chunks=fused) as b:
     for _ in range(rep):
         t0 = time.perf_counter(); b.upload(); t1 = time.perf_counter()
         n = b.run(); t2 = time.perf_counter()

@@ -16,6 +16,10 @@ LIB_DIR = os.path.join(HERE, "lib")
 LIB_PATH = os.path.join(LIB_DIR, "libviloca_b200.so")
 SOURCES = ["vl_kernels.cu", "vl_resident.cu", "vl_api.cu"]
 HEADERS = ["vl_device.cuh", "vl_cavi.cuh", "vl_launch.h", os.path.join("..", "..", "include", "viloca_b200.h")]
+# vl_kernels.cu: vl_chunk_kernel runs many dependent updates in one launch, so state written by
+# one CTA is read by later CTAs of the same launch, possibly on an SM whose L1 still holds the old
+# line: global loads of that file are cached in L2 only (the operand streams through TMA anyway).
+EXTRA_FLAGS = {"vl_kernels.cu": ["-Xptxas", "-dlcm=cg"]}
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
     "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden",
@@ -46,7 +50,8 @@ def build(force: bool = False, verbose: bool = False, profile: bool = False) -> 
         obj = os.path.join(LIB_DIR, src.replace(".cu", ".o"))
         objs.append(obj)
         if force or _stale(obj, [src_path] + headers):
-            cmd = [_nvcc()] + NVCC_FLAGS + (["-DVL_RS_PROFILE"] if profile else []) + ["-c", src_path, "-o", obj]
+            cmd = [_nvcc()] + NVCC_FLAGS + (["-DVL_RS_PROFILE"] if profile else []) + EXTRA_FLAGS.get(src, []) + \
+                ["-c", src_path, "-o", obj]
             if verbose:
                 cmd.insert(1, "-Xptxas=-v")
                 print(" ".join(cmd), file=sys.stderr)

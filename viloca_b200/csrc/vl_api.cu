@@ -3,6 +3,8 @@
 // driver with its per-chunk kernel-class scheduling, and result export.  No process-global
 // state other than a thread-local error string.
 #include <algorithm>
+#include <chrono>
+#include <cstdlib>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
@@ -56,7 +58,7 @@ struct Layout {
   int n_problems = 0;
   size_t data_begin = 0, data_end = 0;   // zero-filled on upload
   size_t probs = 0, states = 0, done = 0, pstat = 0;
-  size_t htiles = 0, ztiles = 0, rlist = 0;
+  size_t htiles = 0, ztiles = 0, rlist = 0, cbase = 0, hticket = 0;
   size_t raw_codes = 0, raw_lt = 0, raw_lo = 0;      // staging of one window's raw arrays
   size_t export_h = 0, export_z = 0;
   size_t tmp_z = 0, tmp_wz = 0, tmp_h = 0, tmp_g = 0, tmp_gm = 0, tmp_hpart = 0, tmp_group = 0, tmp_prob = 0,
@@ -246,6 +248,8 @@ int build_layout(const vl_window_desc* w, int n, Layout& lay, std::string& err) 
   lay.htiles = take(lay.n_htiles_total * sizeof(int2));
   lay.ztiles = take(lay.n_ztiles_total * sizeof(int2));
   lay.rlist = take((size_t)lay.n_problems * sizeof(int));
+  lay.cbase = take((size_t)lay.n_problems * sizeof(int));
+  lay.hticket = take((size_t)lay.n_problems * sizeof(int));
   lay.raw_codes = take(max_nl);
   lay.raw_lt = take(max_nl * 8);
   lay.raw_lo = take(max_nl * 8);
@@ -283,6 +287,7 @@ struct vl_batch {
   // pinned staging of the per-chunk schedule
   int2* h_htiles = nullptr; int2* h_ztiles = nullptr; int4* h_pstat = nullptr;
   int* h_rlist = nullptr;
+  int* h_cbase = nullptr;
   unsigned char* h_arena = nullptr;    // pinned image of every window's small arrays (maps, sparse lists)
   int n_res[2] = {};                   // restarts scheduled on the resident kernel, per mode
   size_t off_res[2] = {}, smem_res[2] = {};
@@ -290,7 +295,7 @@ struct vl_batch {
   size_t off_ht[VL_N_CLASSES][2] = {}, off_zt[VL_N_CLASSES][2] = {};
   int n_sched = 0;
   bool sched_dirty = true;
-  int skip_dead = 1, resident = 0;
+  int skip_dead = 1, resident = 0, fused = 1;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   double last_ms = 0.0;
   bool uploaded = false;
@@ -377,6 +382,25 @@ int launch_phase(vl_batch* b, int phase, int64_t* launches) {
         *launches += 1;
       }
     }
+  return 0;
+}
+
+// n_iter updates of every scheduled restart with one launch per kernel class (vl_chunk_kernel)
+int run_chunk_fused(vl_batch* b, int n_iter, int64_t* launches) {
+  const Layout& L = b->lay;
+  const int np = L.n_problems;
+  for (int p = 0; p < np; ++p) b->h_cbase[p] = b->pstat[p].w;
+  VL_CUDA(cudaMemcpyAsync(b->dev<int>(L.cbase), b->h_cbase, (size_t)np * sizeof(int), cudaMemcpyHostToDevice, b->stream));
+  VL_CUDA(cudaMemsetAsync(b->dev<int>(L.hticket), 0, (size_t)np * sizeof(int), b->stream));
+  if (launch_resident(b, n_iter, launches)) return 1;
+  for (int c = 0; c < VL_N_CLASSES; ++c)
+    for (int m = 0; m < 2; ++m)
+      if (b->n_ht[c][m] > 0) {
+        VL_CUDA(vl_launch_chunk(c, m ? VL_MODE_LEP : VL_MODE_UQS, b->d_probs(), b->dev<int2>(L.htiles) + b->off_ht[c][m],
+                                b->n_ht[c][m], b->dev<int2>(L.ztiles) + b->off_zt[c][m], b->n_zt[c][m], n_iter,
+                                b->dev<int>(L.cbase), b->dev<int>(L.hticket), b->d_done(), b->d_pstat(), b->stream));
+        *launches += 1;
+      }
   return 0;
 }
 
@@ -520,6 +544,7 @@ int vl_batch_create(vl_batch** out, int32_t device, const vl_window_desc* window
   VL_CREATE_CUDA(cudaMallocHost(reinterpret_cast<void**>(&b->h_ztiles), std::max<size_t>(L.n_ztiles_total, 1) * sizeof(int2)));
   VL_CREATE_CUDA(cudaMallocHost(reinterpret_cast<void**>(&b->h_pstat), (size_t)L.n_problems * sizeof(int4)));
   VL_CREATE_CUDA(cudaMallocHost(reinterpret_cast<void**>(&b->h_rlist), (size_t)L.n_problems * sizeof(int)));
+  VL_CREATE_CUDA(cudaMallocHost(reinterpret_cast<void**>(&b->h_cbase), (size_t)L.n_problems * sizeof(int)));
   VL_CREATE_CUDA(cudaMallocHost(reinterpret_cast<void**>(&b->h_arena), std::max<size_t>(L.arena_bytes, 1)));
   VL_CREATE_CUDA(cudaEventCreate(&b->ev0));
   VL_CREATE_CUDA(cudaEventCreate(&b->ev1));
@@ -538,6 +563,7 @@ void vl_batch_destroy(vl_batch* b) {
   if (b->h_ztiles) cudaFreeHost(b->h_ztiles);
   if (b->h_pstat) cudaFreeHost(b->h_pstat);
   if (b->h_rlist) cudaFreeHost(b->h_rlist);
+  if (b->h_cbase) cudaFreeHost(b->h_cbase);
   if (b->h_arena) cudaFreeHost(b->h_arena);
   if (b->ev0) cudaEventDestroy(b->ev0);
   if (b->ev1) cudaEventDestroy(b->ev1);
@@ -548,6 +574,7 @@ int vl_batch_set_option(vl_batch* b, int32_t option, int32_t value) {
   if (!b) return fail("batch is NULL");
   if (option == VL_OPT_SKIP_DEAD) { b->skip_dead = value ? 1 : 0; return 0; }
   if (option == VL_OPT_RESIDENT) { b->resident = value ? 1 : 0; b->sched_dirty = true; return 0; }
+  if (option == VL_OPT_FUSED_CHUNKS) { b->fused = value ? 1 : 0; return 0; }
   return fail("unknown option");
 }
 
@@ -663,10 +690,18 @@ int vl_batch_run(vl_batch* b, int64_t* n_launches_out) {
     // (a fixed function of the chunk index: the path a restart takes never depends on the
     // other windows of the batch, so results are independent of the batch composition)
     const int chunk = n_chunks < 6 ? 4 : (n_chunks < 14 ? 32 : 256);
+    static const bool trace = std::getenv("VL_TRACE") != nullptr;    // development aid: chunk timeline on stderr
+    const auto t0 = std::chrono::steady_clock::now();
+    const int before = running;
     if (b->sched_dirty && schedule(b)) return 1;
-    if (run_iterations(b, chunk, &launches)) return 1;
+    if (b->fused ? run_chunk_fused(b, chunk, &launches) : run_iterations(b, chunk, &launches)) return 1;
     if (sync_status(b, &running)) return 1;
     done_iters += chunk;
+    if (trace) {
+      const double us = std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t0).count();
+      fprintf(stderr, "chunk %3d: %3d updates, running %d -> %d, %.0f us (%.1f us/update)\n", n_chunks, chunk, before, running,
+              us, us / chunk);
+    }
   }
   VL_CUDA(cudaEventRecord(b->ev1, b->stream));
   VL_CUDA(cudaEventSynchronize(b->ev1));
@@ -922,9 +957,10 @@ int vl_debug_exp(int32_t device, const double* x, double* out, int32_t n) {
   return 0;
 }
 
-int vl_debug_counters(uint64_t* out16, int32_t reset) {
+int vl_debug_counters(uint64_t* out36, int32_t reset) {
   static_assert(sizeof(unsigned long long) == sizeof(uint64_t), "counter width");
-  const int rc = vl_debug_resident_cycles(reinterpret_cast<unsigned long long*>(out16), reset);
+  int rc = vl_debug_resident_cycles(reinterpret_cast<unsigned long long*>(out36), reset);
+  if (rc == 0) rc = vl_debug_general_cycles(reinterpret_cast<unsigned long long*>(out36 + 16), reset);
   if (rc == 2) return fail("library built without -DVL_RS_PROFILE");
   return rc ? fail("cudaMemcpyFromSymbol failed") : 0;
 }

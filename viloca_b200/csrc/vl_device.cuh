@@ -76,7 +76,7 @@ struct VlState {
   int skip;       // 1 = remove dead clusters from the layout (exact), 0 = always dense
   int stalled;    // layout grew past the kernel class this restart is scheduled in
   int ticket;     // read tiles of the current responsibility update that have finished
-  int pad_;
+  int pub;        // updates completed AND visible: written last by the scalar update (fused chunks poll it)
 };
 
 // Read-only description of one (window, restart) problem.
@@ -185,6 +185,43 @@ __device__ __forceinline__ double vl_digamma(double x) {
   return r + (log(x) - 0.5 * inv - s);
 }
 
+// digamma and log-gamma of x > 0 together (scipy.special.digamma / gammaln / betaln of
+// update_eqs.py:40-53, elbo_eqs.py:56-62,81-88): both shift x upward to y >= 10 and use their
+// asymptotic series there; they share the reciprocals of the shift and log(y), and the shift of
+// lgamma is one log of the product (x)(x+1)...(y-1) <= 3.4e11.  FP64 latency bounds the scalar
+// update of an iteration (a handful of warps, serial chains), and CUDA's lgamma() alone is a
+// several-thousand-cycle chain; this pair costs two overlapping logs and a short series.
+// Absolute error about 1e-15 (truncation of the Stirling series at y^-13: 3e-17).
+__device__ __forceinline__ void vl_psi_lgamma(double x, double& psi, double& lg) {
+  double r = 0.0, prod = 1.0;
+  if (x < 10.0) {
+    double inv[10];
+#pragma unroll
+    for (int i = 0; i < 10; ++i) {
+      const bool on = x < 10.0;
+      inv[i] = on ? 1.0 / x : 0.0;
+      prod = on ? prod * x : prod;
+      x = on ? x + 1.0 : x;
+    }
+#pragma unroll
+    for (int i = 0; i < 10; ++i) r -= inv[i];
+  }
+  const double ly = log(x), lp = log(prod);
+  const double inv = 1.0 / x, i2 = inv * inv;
+  const double sp = i2 * (1.0 / 12 - i2 * (1.0 / 120 - i2 * (1.0 / 252 - i2 * (1.0 / 240 -
+                    i2 * (1.0 / 132 - i2 * (691.0 / 32760 - i2 * (1.0 / 12)))))));
+  psi = r + (ly - 0.5 * inv - sp);
+  const double sl = inv * (1.0 / 12 - i2 * (1.0 / 360 - i2 * (1.0 / 1260 - i2 * (1.0 / 1680 -
+                    i2 * (1.0 / 1188 - i2 * (691.0 / 360360 - i2 * (1.0 / 156)))))));
+  lg = ((x - 0.5) * ly - x + 0.91893853320467274178 + sl) - lp;
+}
+
+__device__ __forceinline__ double vl_lgamma(double x) {
+  double psi, lg;
+  vl_psi_lgamma(x, psi, lg);
+  return lg;
+}
+
 __device__ __forceinline__ double vl_betaln(double a, double b) {
-  return lgamma(a) + lgamma(b) - lgamma(a + b);
+  return vl_lgamma(a) + vl_lgamma(b) - vl_lgamma(a + b);
 }

@@ -14,9 +14,36 @@
 // complement table) are staged in shared memory by TMA bulk copies behind mbarriers; the
 // minority entries are added from the sparse lists; softmax / ELBO reductions are fused into
 // the epilogues.
+#ifdef VL_RS_PROFILE
+#define VL_SU_PROFILE
+__device__ unsigned long long vl_su_cycles[8];     // vl_scalar_update phases of restart 0 (vl_cavi.cuh)
+#endif
 #include "vl_cavi.cuh"
+#include <cstdio>
+
 #include "vl_launch.h"
 #include "../../include/viloca_b200.h"
+
+// Per-phase cycle counters of restart 0's tile 0 (development aid, -DVL_RS_PROFILE):
+// haplotype tile: 0 prologue, 1 operand loop, 2 warp reduction, 3 sparse, 4 softmax epilogue, 5 sums;
+// read tile: 8 prologue, 9 operand loop, 10 sparse, 11 softmax epilogue, 12 records + ticket,
+// 13 scalar update (whichever tile is last); chunk kernel: 6 wait published (haplotype tile),
+// 7 signal, 14 wait published (read tile), 15 wait haplotype tiles; 16 / 17 samples.
+#ifdef VL_RS_PROFILE
+__device__ unsigned long long vl_gk_cycles[20];
+#define GK_DECL(cond) const bool gk_on_ = (cond) && threadIdx.x == 0; long long gk_t_ = clock64()
+#define GK_TICK(slot)                                                                   \
+  do {                                                                                  \
+    if (gk_on_) {                                                                       \
+      const long long n_ = clock64();                                                   \
+      atomicAdd(&vl_gk_cycles[slot], (unsigned long long)(n_ - gk_t_));                 \
+      gk_t_ = clock64();                                                                \
+    }                                                                                   \
+  } while (0)
+#else
+#define GK_DECL(cond) do { } while (0)
+#define GK_TICK(slot) do { } while (0)
+#endif
 
 namespace {
 
@@ -30,8 +57,7 @@ namespace {
 // order.
 // =========================================================================================
 template <int NB, int MODE>
-__global__ void __launch_bounds__(VL_THREADS)
-vl_haplo_kernel(const VlProblem* __restrict__ probs, const int2* __restrict__ tiles) {
+__device__ __forceinline__ bool vl_haplo_body(const VlProblem* __restrict__ probs, const int2 tm) {
   constexpr int KTM = 4 * NB;
   constexpr int KSM = vl_ks(KTM);
   constexpr int DM_STAGE = VL_H_NC * VL_PT;            // doubles
@@ -41,29 +67,47 @@ vl_haplo_kernel(const VlProblem* __restrict__ probs, const int2* __restrict__ ti
   __shared__ uint64_t bars[VL_MAX_STAGES];
   __shared__ double red[VL_THREADS / 32][4];
 
-  const int2 tm = tiles[blockIdx.x];
+  GK_DECL(tm.x == 0 && tm.y == 0);
   const VlProblem& P = probs[tm.x];
-  const VlState* S = P.st;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, q = lane & 3;
+  // the restart's state and this tile's static maps go to shared memory up front: one memory
+  // latency each, overlapped with the first bulk copies, instead of dependent loads later
+  __shared__ VlState sS;
+  __shared__ int s_tpos[VL_PT], s_collb[VL_PT], s_poscol[VL_PT][VL_B], s_ep[VL_PT][VL_B + 1];
+  __shared__ unsigned s_refb[VL_PT];
+  vl_load_state(&sS, P.st, tid);
+  if (tid < VL_PT) {
+    s_tpos[tid] = P.tile_pos[(size_t)tm.y * VL_PT + tid];
+    s_collb[tid] = P.col_lb[(size_t)tm.y * VL_PT + tid];
+  }
+  __syncthreads();
+  const VlState* S = &sS;
   const int ktl = S->ktl, ktz = S->ktl_z;
-  if (S->active == 0 || ktl > KTM || ktz > KTM) return;
+  if (S->active == 0 || ktl > KTM || ktz > KTM) return false;
   // a narrow layout has small stages: use the same shared memory for a deeper pipeline
   const int st_stride = DM_STAGE + VL_H_NC * vl_ks(ktz);
   const int nstg = min(VL_MAX_STAGES, (VL_STAGES * ST_STRIDE) / st_stride);
 
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, q = lane & 3;
   const int Npad = P.Npad;
   const int KSz = vl_ks(ktz), KSn = vl_ks(ktl), K8 = 8 * ktl;
   const int nlay = S->nlay;
   const int nchunks = Npad / VL_H_NC;
   const double* __restrict__ dmg = P.dm + (size_t)tm.y * Npad * VL_PT;
-  const double* __restrict__ wzg = P.wz;
-  const int* __restrict__ gat = P.gat;
+  const double* wzg = P.wz;     // (mutable state: no __restrict__, these must stay coherent loads)
+  const int* gat = P.gat;
   const uint32_t z_bytes = (uint32_t)(VL_H_NC * KSz * sizeof(double));
   const uint32_t stage_bytes = (uint32_t)(DM_STAGE * sizeof(double)) + z_bytes;
 
   if (tid == 0) {
     for (int s = 0; s < nstg; ++s) vl_mbar_init(&bars[s], 1);
     vl_fence_mbar_init();
+  }
+  if (tid < VL_PT * (VL_B + 1)) {
+    const int pos = tid / (VL_B + 1), j = tid - pos * (VL_B + 1);
+    const int l = s_tpos[pos];
+    s_ep[pos][j] = (l >= 0) ? P.sp_ptr[l * VL_B + j] : 0;
+    if (j < VL_B) s_poscol[pos][j] = (l >= 0) ? P.poscol[l * VL_B + j] : -1;
+    if (j == VL_B) s_refb[pos] = (l >= 0) ? P.ref[l] : 255u;
   }
   __syncthreads();
   auto issue = [&](int c) {
@@ -92,6 +136,7 @@ vl_haplo_kernel(const VlProblem* __restrict__ probs, const int2* __restrict__ ti
     for (int i = 0; i < KTM; ++i) { acc[mt][i][0] = 0.0; acc[mt][i][1] = 0.0; }
 
   const int acol0 = (g + 4 * q) & 15, acol1 = (8 + g + 4 * q) & 15;   // vl_dm_col(row, g / 8 + g), row % 4 == q
+  GK_TICK(0);
   vl_dispatch_tiles<KTM>(ktl, [&](auto ktc) {
     constexpr int KT = decltype(ktc)::value;
     for (int c = 0; c < nchunks; ++c) {
@@ -119,6 +164,7 @@ vl_haplo_kernel(const VlProblem* __restrict__ probs, const int2* __restrict__ ti
 
   // ---- the stage buffers are free now: T [16][K8] and Cm [16][5][K8] live in them; the four
   // warps add their partial sums over the reads into T one after the other (fixed order) ----
+  GK_TICK(1);
   double* T = stg;
   double* Cm = stg + VL_PT * K8;
   for (int turn = 0; turn < VL_THREADS / 32; ++turn) {
@@ -136,11 +182,10 @@ vl_haplo_kernel(const VlProblem* __restrict__ probs, const int2* __restrict__ ti
     }
     if (turn + 1 < VL_THREADS / 32) __syncthreads();
   }
+  GK_TICK(2);
   // sparse entries of the positions whose columns lie in this tile: warp = 4 of them,
   // lanes = slots
-  const int* __restrict__ tpos = P.tile_pos + (size_t)tm.y * VL_PT;
   {
-    const int* __restrict__ sp_ptr = P.sp_ptr;
     const int* __restrict__ sp_n = P.sp_n;
     const double* __restrict__ sp_d = P.sp_d;
     int gl[NB];
@@ -151,10 +196,9 @@ vl_haplo_kernel(const VlProblem* __restrict__ probs, const int2* __restrict__ ti
     }
     for (int pp = 0; pp < 4; ++pp) {
       const int pos = warp * 4 + pp;
-      const int l = tpos[pos];
-      if (l < 0) continue;
+      if (s_tpos[pos] < 0) continue;
       for (int b = 0; b < VL_B; ++b) {
-        const int e0 = sp_ptr[l * VL_B + b], e1 = sp_ptr[l * VL_B + b + 1];
+        const int e0 = s_ep[pos][b], e1 = s_ep[pos][b + 1];
         double av[NB];
 #pragma unroll
         for (int j = 0; j < NB; ++j) av[j] = 0.0;
@@ -175,28 +219,27 @@ vl_haplo_kernel(const VlProblem* __restrict__ probs, const int2* __restrict__ ti
   }
   __syncthreads();
 
+  GK_TICK(3);
   // ---- epilogue: + ref_part, softmax over b, the three sums, store h, g, gm ----
   const double mlg0 = S->mlg0, refoff = S->mlg1 - VL_LOG4;
   double cscale = 1.0;
   if (MODE == VL_MODE_LEP) cscale = S->mlt0 - (S->mlt1 - VL_LOG4);
   const int ghost = S->ghost;
   const double gmult = S->ghost_mult;
-  const int* __restrict__ poscol = P.poscol;
-  const int* __restrict__ col_lb = P.col_lb + (size_t)tm.y * VL_PT;
   double* __restrict__ gmt = P.gm + (size_t)tm.y * VL_PT * KSn;
   double s_ref = 0.0, s_nref = 0.0, s_ent = 0.0;
   for (int idx = tid; idx < VL_PT * K8; idx += VL_THREADS) {
     const int pos = idx / K8, slot = idx - pos * K8;
-    if (col_lb[pos] < 0) gmt[pos * KSn + slot] = 0.0;      // padding column of the operand
-    const int l = tpos[pos];
+    if (s_collb[pos] < 0) gmt[pos * KSn + slot] = 0.0;     // padding column of the operand
+    const int l = s_tpos[pos];
     if (l < 0) continue;
-    const unsigned rc = P.ref[l];
+    const unsigned rc = s_refb[pos];
     double* hp = P.h + (size_t)l * VL_B * KSn + slot;
     double* gp = P.g + (size_t)l * VL_B * KSn + slot;
     int lc[VL_B];                                          // column of (l, b) within this tile, or -1
 #pragma unroll
     for (int b = 0; b < VL_B; ++b) {
-      const int j = poscol[l * VL_B + b];
+      const int j = s_poscol[pos][b];
       lc[b] = (j < 0) ? -1 : j - tm.y * VL_PT;
     }
     if (slot < nlay) {
@@ -241,6 +284,7 @@ vl_haplo_kernel(const VlProblem* __restrict__ probs, const int2* __restrict__ ti
       }
     }
   }
+  GK_TICK(4);
   s_ref = warp_sum(s_ref); s_nref = warp_sum(s_nref); s_ent = warp_sum(s_ent);
   if (lane == 0) { red[warp][0] = s_ref; red[warp][1] = s_nref; red[warp][2] = s_ent; }
   __syncthreads();
@@ -250,6 +294,17 @@ vl_haplo_kernel(const VlProblem* __restrict__ probs, const int2* __restrict__ ti
     for (int wI = 0; wI < VL_THREADS / 32; ++wI) v += red[wI][tid];
     P.hpart[(size_t)tm.y * VL_HP_STRIDE + tid] = v;
   }
+  GK_TICK(5);
+#ifdef VL_RS_PROFILE
+  if (gk_on_) atomicAdd(&vl_gk_cycles[16], 1ull);
+#endif
+  return true;
+}
+
+template <int NB, int MODE>
+__global__ void __launch_bounds__(VL_THREADS)
+vl_haplo_kernel(const VlProblem* __restrict__ probs, const int2* __restrict__ tiles) {
+  vl_haplo_body<NB, MODE>(probs, tiles[blockIdx.x]);
 }
 
 // =========================================================================================
@@ -258,9 +313,8 @@ vl_haplo_kernel(const VlProblem* __restrict__ probs, const int2* __restrict__ ti
 // ghost slot counted ghost_mult times.  CTA = 64 reads x all slots; warp = 16 reads.
 // =========================================================================================
 template <int NB, int MODE>
-__global__ void __launch_bounds__(VL_THREADS)
-vl_cluster_kernel(const VlProblem* __restrict__ probs, const int2* __restrict__ tiles,
-                  int* __restrict__ done_count, int4* __restrict__ pstat) {
+__device__ __forceinline__ void vl_cluster_body(const VlProblem* __restrict__ probs, const int2 tm,
+                                                int* __restrict__ done_count, int4* __restrict__ pstat) {
   constexpr int KTM = 4 * NB;
   constexpr int KSM = vl_ks(KTM), K8M = 8 * KTM;
   constexpr int DM_STAGE = VL_ZT_READS * VL_PT;        // doubles
@@ -271,19 +325,25 @@ vl_cluster_kernel(const VlProblem* __restrict__ probs, const int2* __restrict__ 
   __shared__ uint64_t bars[VL_MAX_STAGES];
   __shared__ double red_sc[VL_THREADS / 32][4];
 
-  const int2 tm = tiles[blockIdx.x];
+  GK_DECL(tm.x == 0 && tm.y == 0);
   const VlProblem& P = probs[tm.x];
-  const VlState* S = P.st;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, q = lane & 3;
+  // state and mean_log_pi of the slots in shared memory: one latency, off the epilogue's path
+  __shared__ VlState sS;
+  __shared__ double s_mlp[VL_MAX_CLUSTERS];
+  vl_load_state(&sS, P.st, tid);
+  s_mlp[tid] = (tid < 8 * P.KT) ? __ldcg(P.mlp_lay + tid) : 0.0;
+  __syncthreads();
+  const VlState* S = &sS;
   const int ktl = S->ktl;
   if (S->active == 0 || ktl > KTM || S->ktl_z > KTM) return;
 
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, q = lane & 3;
   const int Npad = P.Npad;
   const int KS = vl_ks(ktl), K8 = 8 * ktl;
   const int nst = P.NCs / VL_PT;
   const int n0 = tm.y * VL_ZT_READS;
   const double* __restrict__ dmg = P.dm + (size_t)n0 * VL_PT;
-  const double* __restrict__ gmg = P.gm;
+  const double* gmg = P.gm;
   const uint32_t gm_bytes = (uint32_t)(VL_PT * KS * sizeof(double));
   const uint32_t stage_bytes = (uint32_t)(DM_STAGE * sizeof(double)) + gm_bytes;
   // narrow layouts: deeper pipeline in the same shared memory (see vl_haplo_kernel)
@@ -312,6 +372,19 @@ vl_cluster_kernel(const VlProblem* __restrict__ probs, const int2* __restrict__ 
     for (int i = 0; i < KTM; ++i) { acc[mt][i][0] = 0.0; acc[mt][i][1] = 0.0; }
 
   const int r0 = warp * 16 + g;                    // rows r0 and r0 + 8 of the tile; r0 % 4 == g % 4
+  // per-read scalars: requested now, needed after the operand loop
+  double wn_r[2], mc_r[2], lt_r[2];
+  int se0[2], se1[2];
+#pragma unroll
+  for (int mt = 0; mt < 2; ++mt) {
+    const int n = n0 + r0 + 8 * mt;
+    wn_r[mt] = P.w[n];
+    mc_r[mt] = P.mcount[n];
+    lt_r[mt] = (MODE == VL_MODE_UQS) ? P.ltsum[n] : 0.0;
+    se0[mt] = P.sr_ptr[n];
+    se1[mt] = P.sr_ptr[n + 1];
+  }
+  GK_TICK(8);
   vl_dispatch_tiles<KTM>(ktl, [&](auto ktc) {
     constexpr int KT = decltype(ktc)::value;
     for (int c = 0; c < nst; ++c) {
@@ -337,17 +410,15 @@ vl_cluster_kernel(const VlProblem* __restrict__ probs, const int2* __restrict__ 
     }
   });
 
+  GK_TICK(9);
   // ---- sparse entries of this thread's two reads ----
   {
-    const int* __restrict__ sr_ptr = P.sr_ptr;
     const int* __restrict__ sr_idx = P.sr_idx;
     const double* __restrict__ sr_d = P.sr_d;
-    const double* __restrict__ gtab = P.g;
+    const double* gtab = P.g;
 #pragma unroll
     for (int mt = 0; mt < 2; ++mt) {
-      const int n = n0 + r0 + 8 * mt;
-      const int e0 = sr_ptr[n], e1 = sr_ptr[n + 1];
-      for (int e = e0; e < e1; ++e) {
+      for (int e = se0[mt]; e < se1[mt]; ++e) {
         const double d = sr_d[e];
         const double* gp = gtab + (size_t)sr_idx[e] * KS + 2 * q;
 #pragma unroll
@@ -361,8 +432,9 @@ vl_cluster_kernel(const VlProblem* __restrict__ probs, const int2* __restrict__ 
     }
   }
 
+  GK_TICK(10);
   // ---- epilogue: logits, softmax over the slots, the reductions, store mean_cluster ----
-  const double* __restrict__ mlpl = P.mlp_lay;
+  const double* mlpl = s_mlp;
   const int N = P.N, nlay = S->nlay, ghost = S->ghost;
   const double gmult = S->ghost_mult;
   double b1 = 0.0, b2 = 0.0;
@@ -374,9 +446,9 @@ vl_cluster_kernel(const VlProblem* __restrict__ probs, const int2* __restrict__ 
   for (int mt = 0; mt < 2; ++mt) {
     const int n = n0 + r0 + 8 * mt;
     const bool valid = n < N;
-    const double wn = P.w[n];
-    const double mc = P.mcount[n];
-    const double base = (MODE == VL_MODE_UQS) ? P.ltsum[n] : mc;
+    const double wn = wn_r[mt];
+    const double mc = mc_r[mt];
+    const double base = (MODE == VL_MODE_UQS) ? lt_r[mt] : mc;
     double t[KTM][2];
     double m = neg_inf();
 #pragma unroll
@@ -445,6 +517,7 @@ vl_cluster_kernel(const VlProblem* __restrict__ probs, const int2* __restrict__ 
         else { cs[i][0] += wz0; cs[i][1] += wz1; }
       }
   }
+  GK_TICK(11);
 #pragma unroll
   for (int i = 0; i < KTM; ++i)
     if (i < ktl) {
@@ -487,25 +560,111 @@ vl_cluster_kernel(const VlProblem* __restrict__ probs, const int2* __restrict__ 
   __syncthreads();
   if (tid == 0) s_last = (atomicAdd(&Sw->ticket, 1) == P.n_ztiles - 1);
   __syncthreads();
+  GK_TICK(12);
+#ifdef VL_RS_PROFILE
+  if (gk_on_) atomicAdd(&vl_gk_cycles[17], 1ull);
+  const bool gk_last_ = tm.x == 0 && threadIdx.x == 0;
+  long long gk_t2_ = clock64();
+#endif
   if (!s_last) return;
   __threadfence();
   if (tid == 0) Sw->ticket = 0;
   for (int c = tid; c < K8 + 7; c += VL_THREADS) {
-    double v = 0.0;
-    if (c < K8) {
-      for (int t = 0; t < P.n_ztiles; ++t) v += __ldcg(P.zpart + (size_t)t * ZS + c);
-      sm.cs[c] = v;
-    } else if (c < K8 + 4) {
-      const int j = c - K8;
-      for (int t = 0; t < P.n_ztiles; ++t) v += __ldcg(P.zpart + (size_t)t * ZS + K8rec + j);
-      sm.sc[j] = v;
-    } else {
-      const int j = c - K8 - 4;
-      for (int t = 0; t < P.n_htiles; ++t) v += P.hpart[(size_t)t * VL_HP_STRIDE + j];
-      sm.sc[4 + j] = v;
-    }
+    if (c < K8) sm.cs[c] = vl_ordered_sum(P.zpart + c, ZS, P.n_ztiles);
+    else if (c < K8 + 4) sm.sc[c - K8] = vl_ordered_sum(P.zpart + K8rec + (c - K8), ZS, P.n_ztiles);
+    else sm.sc[4 + (c - K8 - 4)] = vl_ordered_sum(P.hpart + (c - K8 - 4), VL_HP_STRIDE, P.n_htiles);
   }
-  vl_scalar_update<0>(P, Sw, sm, tid, done_count, pstat + tm.x);
+  vl_scalar_update<0>(P, sS, Sw, sm, tid, done_count, pstat + tm.x);
+#ifdef VL_RS_PROFILE
+  if (gk_last_) atomicAdd(&vl_gk_cycles[13], (unsigned long long)(clock64() - gk_t2_));
+#endif
+}
+
+template <int NB, int MODE>
+__global__ void __launch_bounds__(VL_THREADS)
+vl_cluster_kernel(const VlProblem* __restrict__ probs, const int2* __restrict__ tiles,
+                  int* __restrict__ done_count, int4* __restrict__ pstat) {
+  vl_cluster_body<NB, MODE>(probs, tiles[blockIdx.x], done_count, pstat);
+}
+
+// =========================================================================================
+// A whole chunk of updates of one kernel class in ONE launch.  Block b works on update
+// b / (n_ht + n_zt) of the chunk: first the haplotype tiles of every scheduled restart, then
+// their read tiles.  Dependencies are per restart and point to lower block indices only (blocks
+// are dispatched in index order): a haplotype tile of update u waits until the restart has
+// published u completed updates (VlState::pub, written last by the scalar update), a read tile
+// additionally until all haplotype tiles of its update have signalled (hticket).  No launch
+// latency and no kernel boundary between the steps, and restarts advance independently of each
+// other inside the chunk.
+// =========================================================================================
+__device__ __forceinline__ bool vl_wait_published(const VlState* S, int target) {
+  __shared__ int ok;
+  if (threadIdx.x == 0) {
+    const volatile int* pub = &S->pub;
+    const volatile int* act = &S->active;
+    int r = 1;
+    for (unsigned spin = 0; *pub < target; ++spin) {
+      if (*act == 0) { r = 0; break; }
+      __nanosleep(40);
+      if (spin > (1u << 26)) __trap();       // bounded: a lost dependency is an error, not a hang
+    }
+    if (*act == 0) r = 0;
+    ok = r;
+    __threadfence();
+  }
+  __syncthreads();
+  const int r = ok;
+  __syncthreads();
+  return r != 0;
+}
+
+template <int NB, int MODE>
+__global__ void __launch_bounds__(VL_THREADS)
+vl_chunk_kernel(const VlProblem* __restrict__ probs, const int2* __restrict__ htiles, int n_ht,
+                const int2* __restrict__ ztiles, int n_zt, const int* __restrict__ chunk_base,
+                int* hticket, int* __restrict__ done_count, int4* __restrict__ pstat) {
+  constexpr int KTM = 4 * NB;
+  const int per_update = n_ht + n_zt;
+  const int it = blockIdx.x / per_update, r = blockIdx.x - it * per_update;
+  const bool is_h = r < n_ht;
+  const int2 tm = is_h ? htiles[r] : ztiles[r - n_ht];
+  const VlProblem& P = probs[tm.x];
+  const VlState* S = P.st;
+  GK_DECL(tm.x == 0 && tm.y == 0);
+  if (!vl_wait_published(S, chunk_base[tm.x] + it)) return;        // the restart left its loop
+  GK_TICK(is_h ? 6 : 14);
+  if (is_h) {
+    asm volatile("fence.proxy.async;\n" ::: "memory");   // bulk copies below read what other CTAs wrote
+    if (!vl_haplo_body<NB, MODE>(probs, tm)) return;
+#ifdef VL_RS_PROFILE
+    gk_t_ = clock64();
+#endif
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) atomicAdd(&hticket[tm.x], 1);
+    GK_TICK(7);
+  } else {
+    {
+      const volatile int* kt = &S->ktl;
+      const volatile int* ktz = &S->ktl_z;
+      if (*kt > KTM || *ktz > KTM) return;       // layout outgrew this class: its haplotype tiles bail out too
+    }
+    __shared__ int go;
+    if (threadIdx.x == 0) {
+      const volatile int* t = &hticket[tm.x];
+      const int want = (it + 1) * P.n_htiles;
+      for (unsigned spin = 0; *t < want; ++spin) {
+        __nanosleep(40);
+        if (spin > (1u << 26)) __trap();
+      }
+      __threadfence();
+      go = 1;
+    }
+    __syncthreads();
+    GK_TICK(15);
+    asm volatile("fence.proxy.async;\n" ::: "memory");
+    vl_cluster_body<NB, MODE>(probs, tm, done_count, pstat);
+  }
 }
 
 // One thread per problem: state_init_dict of draw_init_state (initialization.py:6-43), the
@@ -529,7 +688,7 @@ __global__ void vl_init_kernel(const VlProblem* __restrict__ probs, int n_probs,
     P.lay_z[k] = (k < K) ? k : -1;
     P.gat[k] = (k < K) ? k : 0;
   }
-  S->lnB0 = K * lgamma(alpha0) - lgamma(sum_alpha);
+  S->lnB0 = K * vl_lgamma(alpha0) - vl_lgamma(sum_alpha);
   S->betaln_ab0 = vl_betaln(S->a0, S->b0);
   S->a = S->a0; S->b = S->b0; S->c = S->c0; S->d = S->d0;
   S->dsum_alpha = ds;
@@ -544,7 +703,7 @@ __global__ void vl_init_kernel(const VlProblem* __restrict__ probs, int n_probs,
   S->iter = 0; S->n_updates = 0; S->n_hist = 0; S->converged = 0;
   S->status = VL_STATUS_RUNNING; S->active = 1;
   S->ktl = P.KT; S->ktl_z = P.KT; S->nlay = K; S->ghost = -1; S->ghost_mult = 0.0; S->stalled = 0;
-  S->nlay_z = K; S->ghost_z = -1; S->ticket = 0;
+  S->nlay_z = K; S->ghost_z = -1; S->ticket = 0; S->pub = 0;
   pstat[p] = make_int4(1, P.KT, K, 0);
 }
 
@@ -696,6 +855,20 @@ cudaError_t launch_cluster(const VlProblem* probs, const int2* tiles, int n, int
   return cudaGetLastError();
 }
 
+template <int NB, int MODE>
+cudaError_t launch_chunk(const VlProblem* probs, const int2* htiles, int n_ht, const int2* ztiles, int n_zt,
+                         int n_updates, const int* chunk_base, int* hticket, int* done_count, int4* pstat,
+                         cudaStream_t stream) {
+  const size_t smem = std::max(smem_haplo<NB>(), smem_cluster<NB>());
+  cudaError_t e = cudaFuncSetAttribute(vl_chunk_kernel<NB, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  const long long blocks = (long long)n_updates * (n_ht + n_zt);
+  if (blocks > 0x7fffffffLL) return cudaErrorInvalidValue;
+  vl_chunk_kernel<NB, MODE><<<(unsigned)blocks, VL_THREADS, smem, stream>>>(probs, htiles, n_ht, ztiles, n_zt, chunk_base,
+                                                                            hticket, done_count, pstat);
+  return cudaGetLastError();
+}
+
 }  // namespace
 
 int vl_class_of_tiles(int kt) { return kt <= 4 ? 0 : (kt <= 8 ? 1 : 2); }
@@ -724,6 +897,13 @@ cudaError_t vl_launch_cluster(int cls, int mode, const VlProblem* probs, const i
   VL_DISPATCH(launch_cluster, probs, tiles, n_tiles, done_count, pstat, stream)
 }
 
+cudaError_t vl_launch_chunk(int cls, int mode, const VlProblem* probs, const int2* htiles, int n_ht,
+                            const int2* ztiles, int n_zt, int n_updates, const int* chunk_base, int* hticket,
+                            int* done_count, int4* pstat, cudaStream_t stream) {
+  if (n_ht <= 0 || n_zt <= 0 || n_updates <= 0) return cudaSuccess;
+  VL_DISPATCH(launch_chunk, probs, htiles, n_ht, ztiles, n_zt, n_updates, chunk_base, hticket, done_count, pstat, stream)
+}
+
 cudaError_t vl_launch_init(const VlProblem* probs, int n_probs, int4* pstat, cudaStream_t stream) {
   if (n_probs > 0) vl_init_kernel<<<(n_probs + 127) / 128, 128, 0, stream>>>(probs, n_probs, pstat);
   return cudaGetLastError();
@@ -736,6 +916,27 @@ cudaError_t vl_launch_prepare(const uint8_t* codes, const double* lt, const doub
   vl_prepare_dm_kernel<<<grid, 256, 0, stream>>>(codes, lt, lo, col_lb, dm, N, L, Npad, mode);
   vl_prepare_rows_kernel<<<(Npad + 3) / 4, 128, 0, stream>>>(codes, lt, mcount, ltsum, N, L, Npad, mode);
   return cudaGetLastError();
+}
+
+int vl_debug_general_cycles(unsigned long long* out20, int reset) {
+#ifdef VL_RS_PROFILE
+  if (cudaMemcpyFromSymbol(out20, vl_gk_cycles, sizeof(vl_gk_cycles)) != cudaSuccess) return 1;
+  {   // the scalar-update phases travel in slots 18, 19 (+ stderr dump): development aid only
+    unsigned long long su[8];
+    if (cudaMemcpyFromSymbol(su, vl_su_cycles, sizeof su) != cudaSuccess) return 1;
+    fprintf(stderr, "scalar update phases (cycles, summed): slots %llu | per-cluster %llu | barrier %llu | thread0 %llu | layout %llu | publish %llu\n",
+            su[0], su[1], su[2], su[3], su[4], su[5]);
+    if (reset) { unsigned long long z8[8] = {}; cudaMemcpyToSymbol(vl_su_cycles, z8, sizeof z8); }
+  }
+  if (reset) {
+    unsigned long long z[20] = {};
+    if (cudaMemcpyToSymbol(vl_gk_cycles, z, sizeof z) != cudaSuccess) return 1;
+  }
+  return 0;
+#else
+  (void)out20; (void)reset;
+  return 2;
+#endif
 }
 
 cudaError_t vl_launch_scale_rows(const double* z, const double* w, double* wz, int Npad, int KS, cudaStream_t stream) {

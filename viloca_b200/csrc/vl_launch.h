@@ -24,6 +24,11 @@ cudaError_t vl_launch_haplo(int cls, int mode, const VlProblem* probs, const int
 // update that the last read tile of restart p performs
 cudaError_t vl_launch_cluster(int cls, int mode, const VlProblem* probs, const int2* tiles, int n_tiles,
                               int* done_count, int4* pstat, cudaStream_t stream);
+// n_updates updates of one kernel class in one launch (vl_chunk_kernel): chunk_base[p] = updates
+// restart p had completed when the chunk was scheduled, hticket[p] zeroed by the caller
+cudaError_t vl_launch_chunk(int cls, int mode, const VlProblem* probs, const int2* htiles, int n_ht,
+                            const int2* ztiles, int n_zt, int n_updates, const int* chunk_base, int* hticket,
+                            int* done_count, int4* pstat, cudaStream_t stream);
 cudaError_t vl_launch_init(const VlProblem* probs, int n_probs, int4* pstat, cudaStream_t stream);
 cudaError_t vl_launch_prepare(const uint8_t* codes, const double* lt, const double* lo, const int* col_lb,
                               double* dm, double* mcount, double* ltsum, int N, int L, int Npad, int NCs,
@@ -34,3 +39,5 @@ cudaError_t vl_launch_merge(const VlProblem* prob, double* zm, double* wzm, cons
                             size_t total, cudaStream_t stream);
 cudaError_t vl_launch_scale_rows(const double* z, const double* w, double* wz, int Npad, int KS, cudaStream_t stream);
 cudaError_t vl_launch_exp_test(const double* x, double* out, int n, cudaStream_t stream);
+// per-phase cycle counters of restart 0 in the general-path kernels (see vl_kernels.cu); 2 unless -DVL_RS_PROFILE
+int vl_debug_general_cycles(unsigned long long* out20, int reset);

@@ -60,6 +60,7 @@ struct ResidentShared {
   double red_cs[RS_WARPS][8 * RS_KTM];
   double red_sc[RS_WARPS][8];
   int inv[8 * RS_KTM];       // slot of the layout T was accumulated in -> slot of the current one
+  VlState st;                // the restart's state as of the start of the current update
   volatile int cmd;          // consumers -> producer: 1 = stream one sweep over the reads, 0 = exit
 };
 
@@ -190,6 +191,10 @@ vl_resident_kernel(const VlProblem* __restrict__ probs, const int* __restrict__ 
   };
 
   for (int it = 0; it < n_iter; ++it) {
+    vl_bar_sync<BAR_ALL>(RS_CONSUMERS);
+    vl_load_state(&rs.st, S, tid);
+    vl_bar_sync<BAR_ALL>(RS_CONSUMERS);
+    const VlState* S = &rs.st;                // (shadows the global state: reads come from the copy)
     const int kt = S->ktl, ktz = S->ktl_z, nlay = S->nlay, ghost = S->ghost;
     const double gmult = S->ghost_mult;
     const int KS = vl_ks(kt), KSz = vl_ks(ktz), K8 = 8 * kt;
@@ -493,15 +498,15 @@ vl_resident_kernel(const VlProblem* __restrict__ probs, const int* __restrict__ 
     }
     vl_bar_sync<BAR_ALL>(RS_CONSUMERS);
     RS_TICK(9);
-    if (tid < VL_MAX_CLUSTERS) vl_scalar_update<BAR_SCALAR>(P, S, rs.sc, tid, done_count, pstat + pid);
+    if (tid < VL_MAX_CLUSTERS) vl_scalar_update<BAR_SCALAR>(P, rs.st, P.st, rs.sc, tid, done_count, pstat + pid);
     if (tid < 8 * RS_KTM) rs.inv[tid] = -1;
     vl_bar_sync<BAR_ALL>(RS_CONSUMERS);
     RS_TICK(10);
 #ifdef VL_RS_PROFILE
     if (blockIdx.x == 0 && tid == 0) { vl_rs_cycles[14] += 1; vl_rs_cycles[15] += (unsigned long long)kt; }
 #endif
-    if (rs.sc.stop || S->ktl > RS_KTM) break;
-    if (tid < S->nlay) rs.inv[gat[tid]] = tid;       // current layout <- layout of z and T
+    if (rs.sc.stop || P.st->ktl > RS_KTM) break;
+    if (tid < P.st->nlay) rs.inv[gat[tid]] = tid;    // current layout <- layout of z and T
   }
   signal_producer(0);
 }

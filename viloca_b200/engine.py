@@ -145,7 +145,7 @@ class CaviBatch:
     """All (window, restart) problems of ``windows`` on one device."""
 
     def __init__(self, windows: Sequence[Window], device: int = 0, stream: Optional[int] = None,
-                 skip_dead: bool = True, resident: bool = False):
+                 skip_dead: bool = True, resident: bool = False, fused_chunks: bool = True):
         if not windows:
             raise ValueError("empty batch")
         self.windows = list(windows)
@@ -168,6 +168,7 @@ class CaviBatch:
         if not skip_dead:
             capi.check(capi.lib.vl_batch_set_option(self._handle, capi.OPT_SKIP_DEAD, 0))
         capi.check(capi.lib.vl_batch_set_option(self._handle, capi.OPT_RESIDENT, 1 if resident else 0))
+        capi.check(capi.lib.vl_batch_set_option(self._handle, capi.OPT_FUSED_CHUNKS, 1 if fused_chunks else 0))
 
     # -- lifetime ------------------------------------------------------------------------
     def close(self) -> None:
@@ -326,7 +327,7 @@ class CaviBatch:
 
 def run_windows(windows: Sequence[Window], device: int = 0, **options) -> list:
     """upload + run + fetch of one batch: the end-to-end call with host buffers.  ``options``
-    are the keyword options of :class:`CaviBatch` (skip_dead, resident)."""
+    are the keyword options of :class:`CaviBatch` (skip_dead, resident, fused_chunks)."""
     with CaviBatch(windows, device=device, **options) as batch:
         batch.upload()
         batch.run()

@@ -689,7 +689,7 @@ int vl_batch_run(vl_batch* b, int64_t* n_launches_out) {
     // in the narrowest kernel class that fits them
     // (a fixed function of the chunk index: the path a restart takes never depends on the
     // other windows of the batch, so results are independent of the batch composition)
-    const int chunk = n_chunks < 6 ? 4 : (n_chunks < 14 ? 32 : 256);
+    const int chunk = n_chunks < 6 ? 4 : (n_chunks < 14 ? 32 : (n_chunks < 46 ? 64 : 256));
     static const bool trace = std::getenv("VL_TRACE") != nullptr;    // development aid: chunk timeline on stderr
     const auto t0 = std::chrono::steady_clock::now();
     const int before = running;

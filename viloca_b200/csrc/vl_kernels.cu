@@ -45,6 +45,10 @@ __device__ unsigned long long vl_gk_cycles[20];
 #define GK_TICK(slot) do { } while (0)
 #endif
 
+// CTAs per SM each kernel class is compiled for (bounds the registers per thread): the work of a
+// narrow layout is latency bound, so residency matters more than registers there
+constexpr int vl_min_ctas(int ktm) { return ktm <= 2 ? 6 : (ktm <= 4 ? 5 : (ktm <= 8 ? 3 : 2)); }
+
 namespace {
 
 // =========================================================================================
@@ -56,9 +60,9 @@ namespace {
 // (lg, rh) = 8 columns x one half of the reads of every stage; the halves are added in fixed
 // order.
 // =========================================================================================
-template <int NB, int MODE>
+template <int KTM, int MODE>
 __device__ __forceinline__ bool vl_haplo_body(const VlProblem* __restrict__ probs, const int2 tm) {
-  constexpr int KTM = 4 * NB;
+  constexpr int NB = (8 * KTM + 31) / 32;        // 32-slot groups (lanes = slots in the sparse part)
   constexpr int KSM = vl_ks(KTM);
   constexpr int DM_STAGE = VL_H_NC * VL_PT;            // doubles
   constexpr int ST_STRIDE = DM_STAGE + VL_H_NC * KSM;   // dm | wz
@@ -301,10 +305,10 @@ __device__ __forceinline__ bool vl_haplo_body(const VlProblem* __restrict__ prob
   return true;
 }
 
-template <int NB, int MODE>
-__global__ void __launch_bounds__(VL_THREADS)
+template <int KTM, int MODE>
+__global__ void __launch_bounds__(VL_THREADS, vl_min_ctas(KTM))
 vl_haplo_kernel(const VlProblem* __restrict__ probs, const int2* __restrict__ tiles) {
-  vl_haplo_body<NB, MODE>(probs, tiles[blockIdx.x]);
+  vl_haplo_body<KTM, MODE>(probs, tiles[blockIdx.x]);
 }
 
 // =========================================================================================
@@ -312,10 +316,9 @@ vl_haplo_kernel(const VlProblem* __restrict__ probs, const int2* __restrict__ ti
 // entries of read n; uqs logits = ltsum[n] - Y + mean_log_pi, softmax over the slots with the
 // ghost slot counted ghost_mult times.  CTA = 64 reads x all slots; warp = 16 reads.
 // =========================================================================================
-template <int NB, int MODE>
+template <int KTM, int MODE>
 __device__ __forceinline__ void vl_cluster_body(const VlProblem* __restrict__ probs, const int2 tm,
                                                 int* __restrict__ done_count, int4* __restrict__ pstat) {
-  constexpr int KTM = 4 * NB;
   constexpr int KSM = vl_ks(KTM), K8M = 8 * KTM;
   constexpr int DM_STAGE = VL_ZT_READS * VL_PT;        // doubles
   constexpr int ST_STRIDE = DM_STAGE + VL_PT * KSM;    // dm | gm
@@ -580,11 +583,11 @@ __device__ __forceinline__ void vl_cluster_body(const VlProblem* __restrict__ pr
 #endif
 }
 
-template <int NB, int MODE>
-__global__ void __launch_bounds__(VL_THREADS)
+template <int KTM, int MODE>
+__global__ void __launch_bounds__(VL_THREADS, vl_min_ctas(KTM))
 vl_cluster_kernel(const VlProblem* __restrict__ probs, const int2* __restrict__ tiles,
                   int* __restrict__ done_count, int4* __restrict__ pstat) {
-  vl_cluster_body<NB, MODE>(probs, tiles[blockIdx.x], done_count, pstat);
+  vl_cluster_body<KTM, MODE>(probs, tiles[blockIdx.x], done_count, pstat);
 }
 
 // =========================================================================================
@@ -618,12 +621,11 @@ __device__ __forceinline__ bool vl_wait_published(const VlState* S, int target) 
   return r != 0;
 }
 
-template <int NB, int MODE>
-__global__ void __launch_bounds__(VL_THREADS)
+template <int KTM, int MODE>
+__global__ void __launch_bounds__(VL_THREADS, vl_min_ctas(KTM))
 vl_chunk_kernel(const VlProblem* __restrict__ probs, const int2* __restrict__ htiles, int n_ht,
                 const int2* __restrict__ ztiles, int n_zt, const int* __restrict__ chunk_base,
                 int* hticket, int* __restrict__ done_count, int4* __restrict__ pstat) {
-  constexpr int KTM = 4 * NB;
   const int per_update = n_ht + n_zt;
   const int it = blockIdx.x / per_update, r = blockIdx.x - it * per_update;
   const bool is_h = r < n_ht;
@@ -635,7 +637,7 @@ vl_chunk_kernel(const VlProblem* __restrict__ probs, const int2* __restrict__ ht
   GK_TICK(is_h ? 6 : 14);
   if (is_h) {
     asm volatile("fence.proxy.async;\n" ::: "memory");   // bulk copies below read what other CTAs wrote
-    if (!vl_haplo_body<NB, MODE>(probs, tm)) return;
+    if (!vl_haplo_body<KTM, MODE>(probs, tm)) return;
 #ifdef VL_RS_PROFILE
     gk_t_ = clock64();
 #endif
@@ -663,7 +665,7 @@ vl_chunk_kernel(const VlProblem* __restrict__ probs, const int2* __restrict__ ht
     __syncthreads();
     GK_TICK(15);
     asm volatile("fence.proxy.async;\n" ::: "memory");
-    vl_cluster_body<NB, MODE>(probs, tm, done_count, pstat);
+    vl_cluster_body<KTM, MODE>(probs, tm, done_count, pstat);
   }
 }
 
@@ -826,62 +828,64 @@ __global__ void vl_exp_test_kernel(const double* __restrict__ x, double* __restr
   if (i + 1 < n) out[i + 1] = ev[1];
 }
 
-template <int NB>
+template <int KTM>
 constexpr size_t smem_haplo() {
-  return (size_t)VL_STAGES * (VL_H_NC * VL_PT + VL_H_NC * vl_ks(4 * NB)) * sizeof(double);
+  return (size_t)VL_STAGES * (VL_H_NC * VL_PT + VL_H_NC * vl_ks(KTM)) * sizeof(double);
 }
-template <int NB>
+template <int KTM>
 constexpr size_t smem_cluster() {
-  return ((size_t)VL_ZSTAGES * (VL_ZT_READS * VL_PT + VL_PT * vl_ks(4 * NB)) + (VL_THREADS / 32) * 32 * NB) * sizeof(double);
+  return ((size_t)VL_ZSTAGES * (VL_ZT_READS * VL_PT + VL_PT * vl_ks(KTM)) + (VL_THREADS / 32) * 8 * KTM) * sizeof(double);
 }
 
-template <int NB, int MODE>
+template <int KTM, int MODE>
 cudaError_t launch_haplo(const VlProblem* probs, const int2* tiles, int n, cudaStream_t stream) {
   // the post-loop tables T [16][K8] + Cm [16][5][K8] reuse the stage buffers
-  static_assert(smem_haplo<NB>() >= (size_t)VL_PT * 6 * 32 * NB * sizeof(double), "haplo smem union");
-  cudaError_t e = cudaFuncSetAttribute(vl_haplo_kernel<NB, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       (int)smem_haplo<NB>());
+  static_assert(smem_haplo<KTM>() >= (size_t)VL_PT * 6 * 8 * KTM * sizeof(double), "haplo smem union");
+  cudaError_t e = cudaFuncSetAttribute(vl_haplo_kernel<KTM, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)smem_haplo<KTM>());
   if (e != cudaSuccess) return e;
-  vl_haplo_kernel<NB, MODE><<<n, VL_THREADS, smem_haplo<NB>(), stream>>>(probs, tiles);
+  vl_haplo_kernel<KTM, MODE><<<n, VL_THREADS, smem_haplo<KTM>(), stream>>>(probs, tiles);
   return cudaGetLastError();
 }
-template <int NB, int MODE>
+template <int KTM, int MODE>
 cudaError_t launch_cluster(const VlProblem* probs, const int2* tiles, int n, int* done_count, int4* pstat,
                            cudaStream_t stream) {
-  cudaError_t e = cudaFuncSetAttribute(vl_cluster_kernel<NB, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       (int)smem_cluster<NB>());
+  cudaError_t e = cudaFuncSetAttribute(vl_cluster_kernel<KTM, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)smem_cluster<KTM>());
   if (e != cudaSuccess) return e;
-  vl_cluster_kernel<NB, MODE><<<n, VL_THREADS, smem_cluster<NB>(), stream>>>(probs, tiles, done_count, pstat);
+  vl_cluster_kernel<KTM, MODE><<<n, VL_THREADS, smem_cluster<KTM>(), stream>>>(probs, tiles, done_count, pstat);
   return cudaGetLastError();
 }
 
-template <int NB, int MODE>
+template <int KTM, int MODE>
 cudaError_t launch_chunk(const VlProblem* probs, const int2* htiles, int n_ht, const int2* ztiles, int n_zt,
                          int n_updates, const int* chunk_base, int* hticket, int* done_count, int4* pstat,
                          cudaStream_t stream) {
-  const size_t smem = std::max(smem_haplo<NB>(), smem_cluster<NB>());
-  cudaError_t e = cudaFuncSetAttribute(vl_chunk_kernel<NB, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  const size_t smem = std::max(smem_haplo<KTM>(), smem_cluster<KTM>());
+  cudaError_t e = cudaFuncSetAttribute(vl_chunk_kernel<KTM, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   const long long blocks = (long long)n_updates * (n_ht + n_zt);
   if (blocks > 0x7fffffffLL) return cudaErrorInvalidValue;
-  vl_chunk_kernel<NB, MODE><<<(unsigned)blocks, VL_THREADS, smem, stream>>>(probs, htiles, n_ht, ztiles, n_zt, chunk_base,
+  vl_chunk_kernel<KTM, MODE><<<(unsigned)blocks, VL_THREADS, smem, stream>>>(probs, htiles, n_ht, ztiles, n_zt, chunk_base,
                                                                             hticket, done_count, pstat);
   return cudaGetLastError();
 }
 
 }  // namespace
 
-int vl_class_of_tiles(int kt) { return kt <= 4 ? 0 : (kt <= 8 ? 1 : 2); }
-int vl_class_capacity(int cls) { return cls == 0 ? 4 : (cls == 1 ? 8 : 16); }
+int vl_class_of_tiles(int kt) { return kt <= 2 ? 0 : (kt <= 4 ? 1 : (kt <= 8 ? 2 : 3)); }
+int vl_class_capacity(int cls) { return 2 << cls; }
 
 #define VL_DISPATCH(FN, ...)                                                             \
   switch (cls * 2 + (mode == VL_MODE_LEP ? 1 : 0)) {                                     \
-    case 0: return FN<1, VL_MODE_UQS>(__VA_ARGS__);                                      \
-    case 1: return FN<1, VL_MODE_LEP>(__VA_ARGS__);                                      \
-    case 2: return FN<2, VL_MODE_UQS>(__VA_ARGS__);                                      \
-    case 3: return FN<2, VL_MODE_LEP>(__VA_ARGS__);                                      \
-    case 4: return FN<4, VL_MODE_UQS>(__VA_ARGS__);                                      \
-    case 5: return FN<4, VL_MODE_LEP>(__VA_ARGS__);                                      \
+    case 0: return FN<2, VL_MODE_UQS>(__VA_ARGS__);                                      \
+    case 1: return FN<2, VL_MODE_LEP>(__VA_ARGS__);                                      \
+    case 2: return FN<4, VL_MODE_UQS>(__VA_ARGS__);                                      \
+    case 3: return FN<4, VL_MODE_LEP>(__VA_ARGS__);                                      \
+    case 4: return FN<8, VL_MODE_UQS>(__VA_ARGS__);                                      \
+    case 5: return FN<8, VL_MODE_LEP>(__VA_ARGS__);                                      \
+    case 6: return FN<16, VL_MODE_UQS>(__VA_ARGS__);                                     \
+    case 7: return FN<16, VL_MODE_LEP>(__VA_ARGS__);                                     \
     default: return cudaErrorInvalidValue;                                               \
   }
 

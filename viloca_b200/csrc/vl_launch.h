@@ -3,8 +3,9 @@
 #include <cuda_runtime.h>
 #include "vl_device.cuh"
 
-// Kernel classes by layout width: class 0 = up to 4 slot tiles, 1 = up to 8, 2 = up to 16.
-#define VL_N_CLASSES 3
+// Kernel classes by layout width: class c handles up to 2 << c slot tiles (2, 4, 8, 16); the
+// narrowest one is compiled for 8 CTAs per SM.
+#define VL_N_CLASSES 4
 int vl_class_of_tiles(int kt);
 int vl_class_capacity(int cls);
 

@@ -254,7 +254,7 @@ def run_reference_arm(args):
     table = load_iteration_table(args.workload)
     mean_updates = float(np.mean(table["n_updates"])) if table else 300.0
     mean_reads = float(np.mean(table["n_reads"])) if table else None
-    per_step = []
+    per_step, step_s = [], []
     ctx = mp.get_context("fork")
     with ctx.Pool(processes=procs) as pool:
         for step in range(args.warmup + args.steps):
@@ -263,6 +263,7 @@ def run_reference_arm(args):
             out = pool.map(_pool_worker, jobs)
             dt = time.perf_counter() - t0
             if step >= args.warmup:
+                step_s.append(dt)
                 # windows/s = (window-iterations done / iterations a window needs) / time, corrected
                 # for the sampled windows' size relative to the workload mean
                 scale = 1.0
@@ -272,10 +273,13 @@ def run_reference_arm(args):
     value = float(np.mean(per_step))
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": None, "higher_is_better": True,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * float(np.mean(step_s)), "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": args.workload, "n_windows": spec.n_windows, "coverage": spec.coverage,
-                   "window_length": spec.window_length, "n_clusters": spec.n_clusters, "mode": spec.mode},
+        "config": {"workload": args.workload, "mode": spec.mode, "genome_length": spec.genome_length,
+                   "window_length": spec.window_length, "windows_per_gpu": spec.n_windows, "coverage": spec.coverage,
+                   "n_clusters": spec.n_clusters, "n_starts": spec.n_starts, "haplotypes": spec.n_haplotypes,
+                   "parallelism": f"multiprocessing.Pool({procs}) over windows, one single-threaded process per window "
+                                  "(viloca/shotgun.py:527-538)"},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": procs, "kind": "port",
                          "sample": f"Pool({procs}) x {n_iter} iterations per window per step; converted with "
                                    f"mean iterations/window = {mean_updates:.1f} "
@@ -317,6 +321,7 @@ def run_b200_arm(args):
     h2d = batch.input_bytes()
     d2h = 0
     launches = 0
+    launches_run = 0
     outcomes = None
     for _ in range(args.warmup):
         batch.upload(); batch.run(); outcomes = batch.fetch()
@@ -329,7 +334,9 @@ def run_b200_arm(args):
     for _ in range(args.steps):
         batch.upload()
         launches += 2 * len(windows) + 1                # operand preparation (2 kernels per window) + init
-        launches += batch.run()
+        n_run = batch.run()
+        launches += n_run
+        launches_run += n_run
         run_ms += batch.last_device_ms()
         outcomes = batch.fetch()
         launches += 2 * len(windows)                    # mean_haplo / mean_cluster export per window
@@ -370,51 +377,65 @@ def run_b200_arm(args):
 
     if rank == 0:
         kern_ms = {k: v["ms"] for k, v in prof_tot.items()}
-        dom = max(("haplo", "cluster"), key=lambda k: kern_ms[k])
         try:
             fp64_peak = max(r["tflops"] for r in json.load(open(FP64_PEAK_FILE))["results"] if r["kind"] == "dmma884")
             fp64_src = "DMMA m8n8k4 register loop measured on this pool, profiles/r01_fp64_peak.json"
         except (OSError, ValueError, KeyError):
             fp64_peak, fp64_src = 37.0, "fallback: nominal B200 FP64 tensor peak"
         try:
-            hbm_peak = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
-            hbm_src = "MEASURED_PEAKS.json hbm_gbs (burst copy)"
+            hbm_peak = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs_sustained"])
+            hbm_src = "MEASURED_PEAKS.json hbm_gbs_sustained"
         except (OSError, ValueError, KeyError):
-            hbm_peak, hbm_src = 6550.0, "fallback of B200_PROFILING.md"
+            try:
+                hbm_peak = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
+                hbm_src = "MEASURED_PEAKS.json hbm_gbs (copy bandwidth; no sustained figure in the file)"
+            except (OSError, ValueError, KeyError):
+                hbm_peak, hbm_src = 6550.0, "fallback of B200_PROFILING.md"
         traffic = None
         try:
-            traffic = json.load(open(TRAFFIC_FILE)).get(args.workload, {}).get(dom)
+            traffic = json.load(open(TRAFFIC_FILE)).get(args.workload, {}).get("chunk")
         except (OSError, ValueError):
             pass
 
-        def rates(t):
-            sec = max(t["ms"], 1e-9) * 1e-3
-            return {"ms_per_launch": t["ms"] / max(t["launches"], 1), "launches": t["launches"],
+        def rates(t, ms=None):
+            sec = max(t["ms"] if ms is None else ms, 1e-9) * 1e-3
+            return {"ms": t["ms"] if ms is None else ms, "launches": t["launches"],
                     "gbytes_per_s": t["bytes"] / sec * 1e-9, "executed_tflops": t["executed"] / sec * 1e-12,
                     "algorithmic_tflops": t["algorithmic"] / sec * 1e-12,
                     "dense_equivalent_tflops": t["dense_equivalent"] / sec * 1e-12}
 
-        whole, start = rates(prof_tot[dom]), rates(prof_first[dom])
-        frac_hbm, frac_fp = whole["gbytes_per_s"] / hbm_peak, whole["executed_tflops"] / fp64_peak
+        # The timed runs execute both contractions of every update inside vl_chunk_kernel (one
+        # launch per chunk of updates and kernel class): its work is the sum of the two phases,
+        # its duration the device time of the timed loop (launch gaps between chunks included).
+        both = {k: prof_tot["haplo"][k] + prof_tot["cluster"][k] for k in ("bytes", "executed", "algorithmic", "dense_equivalent")}
+        both["ms"], both["launches"] = run_ms / args.steps, launches_run / args.steps
+        fused = rates(both)
+        frac_hbm, frac_fp = fused["gbytes_per_s"] / hbm_peak, fused["executed_tflops"] / fp64_peak
         bound = "hbm" if frac_hbm >= frac_fp else "tensor"
+        per_phase = {k: rates(prof_tot[k]) for k in ("haplo", "cluster")}
+        start = {k: rates(prof_first[k]) for k in ("haplo", "cluster")}
         roofline = {
-            "bound": bound, "kernel": f"vl_{dom}_kernel",
-            "achieved": whole["gbytes_per_s"] if bound == "hbm" else whole["executed_tflops"],
+            "bound": bound, "kernel": "vl_chunk_kernel (haplotype-update + responsibility-update tiles of a chunk of updates)",
+            "achieved": fused["gbytes_per_s"] if bound == "hbm" else fused["executed_tflops"],
             "peak": hbm_peak if bound == "hbm" else fp64_peak, "unit": "GB/s" if bound == "hbm" else "TFLOP/s",
             "frac": max(frac_hbm, frac_fp), "traffic": traffic,
             "peak_source": hbm_src if bound == "hbm" else fp64_src,
-            "whole_run": {**whole, "frac_hbm": frac_hbm, "frac_fp64_executed": frac_fp,
-                          "share_of_kernel_time": kern_ms[dom] / max(sum(kern_ms.values()), 1e-9)},
-            "all_clusters_live_start": {**start, "frac_fp64_executed": start["executed_tflops"] / fp64_peak,
-                                        "frac_hbm": start["gbytes_per_s"] / hbm_peak,
-                                        "note": "first 4 updates, every one of the K clusters still in the layout: tensor bound"},
+            "timed_run": {**fused, "frac_hbm": frac_hbm, "frac_fp64_executed": frac_fp},
+            "per_phase_separate_launches": {k: {**v, "frac_hbm": v["gbytes_per_s"] / hbm_peak,
+                                                "frac_fp64_executed": v["executed_tflops"] / fp64_peak}
+                                            for k, v in per_phase.items()},
+            "all_clusters_live_start": {k: {**v, "frac_fp64_executed": v["executed_tflops"] / fp64_peak}
+                                        for k, v in start.items()},
             "fp64_peak_tflops": fp64_peak, "fp64_peak_source": fp64_src, "hbm_peak_gbs": hbm_peak,
-            "kernel_ms_whole_run": kern_ms,
-            "convention": "every launch of a separate whole-run pass timed with CUDA events on the launching stream; "
-                          "bytes = compulsory HBM bytes per launch (dense operand N x columns x 8 streamed once, "
-                          "responsibilities / haplotype tables once); executed flops = DMMA work incl. padding; "
-                          "algorithmic flops = 2 N columns clusters-in-layout; dense-equivalent = SURVEY 8(d)'s "
-                          "2 N K L B (B = 5) of the reference's einsum, which this formulation does not execute",
+            "convention": "work per launch = sum over the restarts still running (separate whole-run pass over the same "
+                          "workload, vl_batch_profile_step, every launch bracketed by CUDA events, state sampled every "
+                          "4-32 updates); bytes = compulsory HBM bytes (dense operand N x columns x 8 streamed once per "
+                          "contraction, responsibilities / haplotype tables once); executed flops = DMMA work incl. "
+                          "padding; algorithmic flops = 2 N columns clusters-in-layout; dense-equivalent = SURVEY 8(d)'s "
+                          "2 N K L B (B = 5) of the reference's einsum, which this formulation does not execute. timed_run "
+                          "divides the whole-run work by the device time of the timed loop; per_phase_separate_launches "
+                          "are the two phases launched separately (two launches per update, the profiling path); "
+                          "all_clusters_live_start = first 4 updates, all K clusters in the layout (tensor bound)",
         }
         line = {
             "metric": METRIC, "value": total_problems * args.steps / (run_ms_max * 1e-3), "unit": UNIT,

@@ -36,7 +36,7 @@
 #define VL_ZSTAGES 3     // the same for the responsibility-update kernel
 #endif
 #ifndef VL_MAX_STAGES
-#define VL_MAX_STAGES 8  // stages a narrower layout may use in the same shared memory
+#define VL_MAX_STAGES 24 // most stages in flight (narrow layouts, or few restarts left: see vl_launch_chunk)
 #endif
 #define VL_THREADS 128
 #define VL_MAX_KT 16     // 8-slot tiles of a layout (VL_MAX_CLUSTERS / 8)

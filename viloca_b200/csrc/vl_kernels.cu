@@ -61,7 +61,7 @@ namespace {
 // order.
 // =========================================================================================
 template <int KTM, int MODE>
-__device__ __forceinline__ bool vl_haplo_body(const VlProblem* __restrict__ probs, const int2 tm) {
+__device__ __forceinline__ bool vl_haplo_body(const VlProblem* __restrict__ probs, const int2 tm, const int stage_doubles) {
   constexpr int NB = (8 * KTM + 31) / 32;        // 32-slot groups (lanes = slots in the sparse part)
   constexpr int KSM = vl_ks(KTM);
   constexpr int DM_STAGE = VL_H_NC * VL_PT;            // doubles
@@ -90,7 +90,7 @@ __device__ __forceinline__ bool vl_haplo_body(const VlProblem* __restrict__ prob
   if (S->active == 0 || ktl > KTM || ktz > KTM) return false;
   // a narrow layout has small stages: use the same shared memory for a deeper pipeline
   const int st_stride = DM_STAGE + VL_H_NC * vl_ks(ktz);
-  const int nstg = min(VL_MAX_STAGES, (VL_STAGES * ST_STRIDE) / st_stride);
+  const int nstg = min(VL_MAX_STAGES, max(stage_doubles, VL_STAGES * ST_STRIDE) / st_stride);
 
   const int Npad = P.Npad;
   const int KSz = vl_ks(ktz), KSn = vl_ks(ktl), K8 = 8 * ktl;
@@ -308,7 +308,7 @@ __device__ __forceinline__ bool vl_haplo_body(const VlProblem* __restrict__ prob
 template <int KTM, int MODE>
 __global__ void __launch_bounds__(VL_THREADS, vl_min_ctas(KTM))
 vl_haplo_kernel(const VlProblem* __restrict__ probs, const int2* __restrict__ tiles) {
-  vl_haplo_body<KTM, MODE>(probs, tiles[blockIdx.x]);
+  vl_haplo_body<KTM, MODE>(probs, tiles[blockIdx.x], 0);
 }
 
 // =========================================================================================
@@ -318,13 +318,14 @@ vl_haplo_kernel(const VlProblem* __restrict__ probs, const int2* __restrict__ ti
 // =========================================================================================
 template <int KTM, int MODE>
 __device__ __forceinline__ void vl_cluster_body(const VlProblem* __restrict__ probs, const int2 tm,
-                                                int* __restrict__ done_count, int4* __restrict__ pstat) {
+                                                int* __restrict__ done_count, int4* __restrict__ pstat,
+                                                const int stage_doubles) {
   constexpr int KSM = vl_ks(KTM), K8M = 8 * KTM;
   constexpr int DM_STAGE = VL_ZT_READS * VL_PT;        // doubles
   constexpr int ST_STRIDE = DM_STAGE + VL_PT * KSM;    // dm | gm
   extern __shared__ __align__(128) unsigned char vl_smem[];
   double* stg = reinterpret_cast<double*>(vl_smem);
-  double* red_cs = stg + VL_ZSTAGES * ST_STRIDE;       // [4][K8M]
+  double* red_cs = stg + max(stage_doubles, VL_ZSTAGES * ST_STRIDE);   // [4][K8M], after the stages
   __shared__ uint64_t bars[VL_MAX_STAGES];
   __shared__ double red_sc[VL_THREADS / 32][4];
 
@@ -351,7 +352,7 @@ __device__ __forceinline__ void vl_cluster_body(const VlProblem* __restrict__ pr
   const uint32_t stage_bytes = (uint32_t)(DM_STAGE * sizeof(double)) + gm_bytes;
   // narrow layouts: deeper pipeline in the same shared memory (see vl_haplo_kernel)
   const int st_stride = DM_STAGE + VL_PT * KS;
-  const int nstg = min(VL_MAX_STAGES, (VL_ZSTAGES * ST_STRIDE) / st_stride);
+  const int nstg = min(VL_MAX_STAGES, max(stage_doubles, VL_ZSTAGES * ST_STRIDE) / st_stride);
 
   if (tid == 0) {
     for (int s = 0; s < nstg; ++s) vl_mbar_init(&bars[s], 1);
@@ -587,7 +588,7 @@ template <int KTM, int MODE>
 __global__ void __launch_bounds__(VL_THREADS, vl_min_ctas(KTM))
 vl_cluster_kernel(const VlProblem* __restrict__ probs, const int2* __restrict__ tiles,
                   int* __restrict__ done_count, int4* __restrict__ pstat) {
-  vl_cluster_body<KTM, MODE>(probs, tiles[blockIdx.x], done_count, pstat);
+  vl_cluster_body<KTM, MODE>(probs, tiles[blockIdx.x], done_count, pstat, 0);
 }
 
 // =========================================================================================
@@ -625,7 +626,7 @@ template <int KTM, int MODE>
 __global__ void __launch_bounds__(VL_THREADS, vl_min_ctas(KTM))
 vl_chunk_kernel(const VlProblem* __restrict__ probs, const int2* __restrict__ htiles, int n_ht,
                 const int2* __restrict__ ztiles, int n_zt, const int* __restrict__ chunk_base,
-                int* hticket, int* __restrict__ done_count, int4* __restrict__ pstat) {
+                int* hticket, int* __restrict__ done_count, int4* __restrict__ pstat, const int stage_doubles) {
   const int per_update = n_ht + n_zt;
   const int it = blockIdx.x / per_update, r = blockIdx.x - it * per_update;
   const bool is_h = r < n_ht;
@@ -637,7 +638,7 @@ vl_chunk_kernel(const VlProblem* __restrict__ probs, const int2* __restrict__ ht
   GK_TICK(is_h ? 6 : 14);
   if (is_h) {
     asm volatile("fence.proxy.async;\n" ::: "memory");   // bulk copies below read what other CTAs wrote
-    if (!vl_haplo_body<KTM, MODE>(probs, tm)) return;
+    if (!vl_haplo_body<KTM, MODE>(probs, tm, stage_doubles)) return;
 #ifdef VL_RS_PROFILE
     gk_t_ = clock64();
 #endif
@@ -665,7 +666,7 @@ vl_chunk_kernel(const VlProblem* __restrict__ probs, const int2* __restrict__ ht
     __syncthreads();
     GK_TICK(15);
     asm volatile("fence.proxy.async;\n" ::: "memory");
-    vl_cluster_body<KTM, MODE>(probs, tm, done_count, pstat);
+    vl_cluster_body<KTM, MODE>(probs, tm, done_count, pstat, stage_doubles);
   }
 }
 
@@ -861,13 +862,21 @@ template <int KTM, int MODE>
 cudaError_t launch_chunk(const VlProblem* probs, const int2* htiles, int n_ht, const int2* ztiles, int n_zt,
                          int n_updates, const int* chunk_base, int* hticket, int* done_count, int4* pstat,
                          cudaStream_t stream) {
-  const size_t smem = std::max(smem_haplo<KTM>(), smem_cluster<KTM>());
-  cudaError_t e = cudaFuncSetAttribute(vl_chunk_kernel<KTM, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  // With few tiles per update the SMs are mostly idle and one restart's update is a chain of
+  // latencies: give every CTA enough shared memory to have (nearly) all its operand stages in
+  // flight at once.  Otherwise size it for residency.  Same arithmetic either way.
+  size_t smem = std::max(smem_haplo<KTM>(), smem_cluster<KTM>());
+  int stage_doubles = 0;
+  if (std::max(n_ht, n_zt) <= 148 * 2) {
+    const size_t deep = (size_t)104 * 1024;      // two CTAs per SM
+    if (deep > smem) { stage_doubles = (int)((deep - (VL_THREADS / 32) * 8 * KTM * sizeof(double)) / sizeof(double)); smem = deep; }
+  }
+  cudaError_t e = cudaFuncSetAttribute(vl_chunk_kernel<KTM, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(160 * 1024));
   if (e != cudaSuccess) return e;
   const long long blocks = (long long)n_updates * (n_ht + n_zt);
   if (blocks > 0x7fffffffLL) return cudaErrorInvalidValue;
   vl_chunk_kernel<KTM, MODE><<<(unsigned)blocks, VL_THREADS, smem, stream>>>(probs, htiles, n_ht, ztiles, n_zt, chunk_base,
-                                                                            hticket, done_count, pstat);
+                                                                            hticket, done_count, pstat, stage_doubles);
   return cudaGetLastError();
 }
 

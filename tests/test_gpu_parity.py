@@ -273,6 +273,28 @@ def test_dead_cluster_skipping_is_exact():
         assert (a.state["mean_cluster"].sum(axis=0) > 0).sum() < a.state["mean_cluster"].shape[1]   # some cluster died
 
 
+@pytest.mark.parametrize("name,n_raw,L,K,updates", [("sars_ont", 3000, 300, 100, 14), ("sars_amplicon", 6000, 410, 60, 12)])
+def test_long_noisy_windows_against_oracle(name, n_raw, L, K, updates):
+    """ONT-like reads (Q ~ 18, 5 % deletions: nearly every (position, base) pair becomes a dense
+    column, thousands of sparse entries, no dedup effect) and deep amplicon windows: many read and
+    column tiles per restart.  The first updates against the oracle, trajectory and state."""
+    from viloca_b200 import synthetic
+    engine = _engine()
+    spec = dataclasses.replace(synthetic.WORKLOADS[name], n_clusters=K, n_starts=1, length_jitter=0)
+    win = synthetic.make_window(spec, 2, n_reads=n_raw, length=L, max_iter=updates)
+    assert win.n_reads > 700
+    traj = br.oracle_run(win, max_iterations=updates)
+    for opts in ({}, {"fused_chunks": False}):
+        out = engine.run_windows([win], **opts)[0]
+        r = out.restarts[0]
+        assert r.n_updates == traj.n_updates == updates and r.status == 4
+        assert br.rel_err(r.history_elbo, np.array(traj.history_elbo)) < ENG_TOL
+        assert np.array_equal(out.state["mean_cluster"] == 0, traj.state["mean_cluster"] == 0)
+        assert br.rel_err(out.state["mean_cluster"], traj.state["mean_cluster"]) < SPEC_TOL
+        assert br.rel_err(out.state["mean_haplo"], traj.state["mean_haplo"]) < SPEC_TOL
+        assert br.rel_err(out.state["alpha"], traj.state["alpha"]) < ENG_TOL
+
+
 def test_ragged_mixed_batch_equals_single_window_runs():
     """Windows of different N, L, K and mode in one batch give bit-identical results to
     running each alone (problems are independent; the reductions are order-fixed)."""

@@ -324,7 +324,7 @@ def run_b200_arm(args):
     launches_run = 0
     outcomes = None
     for _ in range(args.warmup):
-        batch.upload(); batch.run(); outcomes = batch.fetch()
+        batch.upload(); batch.run(); outcomes = batch.fetch(pinned=True)
     sampler = ClockSampler(device)
     sampler.start()
     barrier()
@@ -338,7 +338,7 @@ def run_b200_arm(args):
         launches += n_run
         launches_run += n_run
         run_ms += batch.last_device_ms()
-        outcomes = batch.fetch()
+        outcomes = batch.fetch(pinned=True)            # results land in page-locked buffers owned by the batch
         launches += 2 * len(windows)                    # mean_haplo / mean_cluster export per window
     ev1.record()
     barrier()

@@ -252,6 +252,23 @@ def test_fused_chunks_equal_per_update_launches():
         assert np.array_equal(a.state["alpha"], b.state["alpha"])
 
 
+def test_pinned_fetch_equals_pageable_fetch():
+    from viloca_b200 import synthetic
+    engine = _engine()
+    wins = [synthetic.make_window(_spec("uqs", 30, 40), 40 + i, n_reads=150 + 50 * i, length=60) for i in range(3)]
+    with engine.CaviBatch(wins) as b:
+        b.upload()
+        b.run()
+        plain = b.fetch()
+        pinned = b.fetch(pinned=True)
+        again = b.fetch(pinned=True)
+        for p, q, r in zip(plain, pinned, again):
+            assert q.state["mean_cluster"] is r.state["mean_cluster"] or np.shares_memory(q.state["mean_cluster"], r.state["mean_cluster"])
+            for key in ("mean_cluster", "mean_haplo", "alpha"):
+                assert np.array_equal(p.state[key], q.state[key])
+            assert np.array_equal(p.restarts[0].history_elbo, q.restarts[0].history_elbo)
+
+
 def test_dead_cluster_skipping_is_exact():
     """Taking the clusters whose responsibilities are exactly 0 out of the contractions
     (VL_OPT_SKIP_DEAD, the default) changes nothing but the summation order: same iteration

@@ -19,6 +19,6 @@ with engine.CaviBatch(wins, resident=resident, fused_chunks=fused) as b:
     for _ in range(rep):
         t0 = time.perf_counter(); b.upload(); t1 = time.perf_counter()
         n = b.run(); t2 = time.perf_counter()
-        out = b.fetch(); t3 = time.perf_counter()
+        out = b.fetch(pinned=True); t3 = time.perf_counter()
         print(f"upload {1e3*(t1-t0):.1f} ms  run {1e3*(t2-t1):.1f} ms (device {b.last_device_ms():.1f} ms, {n} launches)"
               f"  fetch {1e3*(t3-t2):.1f} ms  windows {len(wins)}", flush=True)

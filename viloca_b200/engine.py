@@ -245,10 +245,28 @@ class CaviBatch:
                                                  int(n_groups), capi.f64_ptr(zc), capi.f64_ptr(hm)))
         return zc, hm
 
+    def _buffer(self, key, shape, dtype, pinned: bool, zero: bool = False) -> np.ndarray:
+        """Result buffer: a fresh pageable array, or (``pinned``) a page-locked one owned by the
+        batch and REUSED by the next pinned fetch, so that the device -> host copies are plain
+        DMA transfers."""
+        if not pinned:
+            return np.zeros(shape, dtype) if zero else np.empty(shape, dtype)
+        cache = self.__dict__.setdefault("_pinned_results", {})
+        arr = cache.get(key)
+        if arr is None or arr.shape != tuple(np.atleast_1d(shape)) or arr.dtype != np.dtype(dtype):
+            t = torch.empty(tuple(np.atleast_1d(shape)), dtype=getattr(torch, np.dtype(dtype).name), pin_memory=True)
+            arr = t.numpy()
+            cache[key] = arr
+            cache[("tensor",) + key] = t
+            if zero:
+                arr[...] = 0
+        return arr
+
     def fetch(self, state: str | int = "best", want_cluster: bool = True, want_haplo: bool = True,
-              want_history: bool = True) -> list:
+              want_history: bool = True, pinned: bool = False) -> list:
         """Copy results to the host.  ``state`` = "best" (max-ELBO restart), "none", a restart
-        index, or a per-window list of those."""
+        index, or a per-window list of those.  ``pinned=True`` returns views of page-locked
+        buffers owned by the batch (valid until the next pinned fetch)."""
         nw = len(self.windows)
         states = list(state) if isinstance(state, (list, tuple)) else [state] * nw
         res = (capi.WindowResult * nw)()
@@ -265,7 +283,7 @@ class CaviBatch:
             for key in ("n_iterations", "n_updates", "status", "converged", "history_len"):
                 setattr(res[i], key, capi.i32_ptr(bufs[key]))
             if want_history:
-                bufs["history"] = np.zeros((r_, w.max_iter), np.float64)
+                bufs["history"] = self._buffer((i, "history"), (r_, w.max_iter), np.float64, pinned, zero=True)
                 res[i].history = capi.f64_ptr(bufs["history"])
                 res[i].history_stride = w.max_iter
             if state == "none":
@@ -274,10 +292,10 @@ class CaviBatch:
                 res[i].state_restart = -1 if state == "best" else int(state)
                 k, l, n = w.n_clusters, w.length, w.n_reads
                 if want_haplo:
-                    bufs["mean_haplo"] = np.empty((k, l, capi.N_BASES), np.float64)
+                    bufs["mean_haplo"] = self._buffer((i, "mean_haplo"), (k, l, capi.N_BASES), np.float64, pinned)
                     res[i].mean_haplo = capi.f64_ptr(bufs["mean_haplo"])
                 if want_cluster:
-                    bufs["mean_cluster"] = np.empty((n, k), np.float64)
+                    bufs["mean_cluster"] = self._buffer((i, "mean_cluster"), (n, k), np.float64, pinned)
                     res[i].mean_cluster = capi.f64_ptr(bufs["mean_cluster"])
                 bufs["alpha"] = np.empty(k, np.float64)
                 bufs["mean_log_pi"] = np.empty(k, np.float64)
@@ -294,7 +312,7 @@ class CaviBatch:
             restarts = []
             for r in range(w.n_starts):
                 hl = int(b["history_len"][r])
-                hist = b["history"][r, :hl].copy() if want_history else np.empty(0)
+                hist = b["history"][r, :hl].copy() if want_history else np.empty(0)   # (a copy: safe with pinned buffers)
                 restarts.append(RestartOutcome(
                     elbo=float(b["elbo"][r]), n_iterations=int(b["n_iterations"][r]),
                     n_updates=int(b["n_updates"][r]), status=int(b["status"][r]),

@@ -58,7 +58,7 @@ struct Layout {
   int n_problems = 0;
   size_t data_begin = 0, data_end = 0;   // zero-filled on upload
   size_t probs = 0, states = 0, done = 0, pstat = 0;
-  size_t htiles = 0, ztiles = 0, rlist = 0, cbase = 0, hticket = 0;
+  size_t htiles = 0, ztiles = 0, rlist = 0, cbase = 0, hticket = 0, zticket = 0;
   size_t raw_codes = 0, raw_lt = 0, raw_lo = 0;      // staging of one window's raw arrays
   size_t export_h = 0, export_z = 0;
   size_t tmp_z = 0, tmp_wz = 0, tmp_h = 0, tmp_g = 0, tmp_gm = 0, tmp_hpart = 0, tmp_group = 0, tmp_prob = 0,
@@ -250,6 +250,7 @@ int build_layout(const vl_window_desc* w, int n, Layout& lay, std::string& err) 
   lay.rlist = take((size_t)lay.n_problems * sizeof(int));
   lay.cbase = take((size_t)lay.n_problems * sizeof(int));
   lay.hticket = take((size_t)lay.n_problems * sizeof(int));
+  lay.zticket = take((size_t)lay.n_problems * sizeof(int));
   lay.raw_codes = take(max_nl);
   lay.raw_lt = take(max_nl * 8);
   lay.raw_lo = take(max_nl * 8);
@@ -392,13 +393,14 @@ int run_chunk_fused(vl_batch* b, int n_iter, int64_t* launches) {
   for (int p = 0; p < np; ++p) b->h_cbase[p] = b->pstat[p].w;
   VL_CUDA(cudaMemcpyAsync(b->dev<int>(L.cbase), b->h_cbase, (size_t)np * sizeof(int), cudaMemcpyHostToDevice, b->stream));
   VL_CUDA(cudaMemsetAsync(b->dev<int>(L.hticket), 0, (size_t)np * sizeof(int), b->stream));
+  VL_CUDA(cudaMemsetAsync(b->dev<int>(L.zticket), 0, (size_t)np * sizeof(int), b->stream));
   if (launch_resident(b, n_iter, launches)) return 1;
   for (int c = 0; c < VL_N_CLASSES; ++c)
     for (int m = 0; m < 2; ++m)
       if (b->n_ht[c][m] > 0) {
         VL_CUDA(vl_launch_chunk(c, m ? VL_MODE_LEP : VL_MODE_UQS, b->d_probs(), b->dev<int2>(L.htiles) + b->off_ht[c][m],
                                 b->n_ht[c][m], b->dev<int2>(L.ztiles) + b->off_zt[c][m], b->n_zt[c][m], n_iter,
-                                b->dev<int>(L.cbase), b->dev<int>(L.hticket), b->d_done(), b->d_pstat(), b->stream));
+                                b->dev<int>(L.cbase), b->dev<int>(L.hticket), b->dev<int>(L.zticket), b->d_done(), b->d_pstat(), b->stream));
         *launches += 1;
       }
   return 0;
@@ -879,6 +881,7 @@ int vl_batch_set_state(vl_batch* b, int32_t window, int32_t restart, const doubl
   S.n_hist = 0; S.n_updates = 0; S.h_last = 0.0; S.h_prev = 0.0;
   S.ktl = W.KT; S.ktl_z = W.KT; S.nlay = W.K; S.ghost = -1; S.nlay_z = W.K; S.ghost_z = -1;
   S.ghost_mult = 0.0; S.stalled = 0; S.skip = b->skip_dead;
+  S.ticket = 0; S.pub = 0; S.ktring[0] = W.KT; S.ktring[1] = W.KT;
   VL_CUDA(cudaMemcpyAsync(b->d_states() + p, &S, sizeof S, cudaMemcpyHostToDevice, s));
   const int4 st = make_int4(1, W.KT, W.K, 0);
   VL_CUDA(cudaMemcpyAsync(b->d_pstat() + p, &st, sizeof st, cudaMemcpyHostToDevice, s));
@@ -921,6 +924,7 @@ int vl_batch_merge_haplo(vl_batch* b, int32_t window, int32_t restart, const int
   VL_CUDA(cudaStreamSynchronize(s));
   S.active = 1;
   S.ktl = KTg; S.ktl_z = KTg; S.nlay = G; S.ghost = -1; S.nlay_z = G; S.ghost_z = -1; S.ghost_mult = 0.0;
+  S.ktring[0] = KTg; S.ktring[1] = KTg;
   std::vector<int> lay, gat;
   identity_layout(G, 8 * KTg, lay, gat);
   std::vector<int2> tiles(W.n_htiles);

@@ -285,6 +285,7 @@ __device__ __forceinline__ int vl_scalar_update(const VlProblem& P, const VlStat
       S->ghost_mult = (double)n_dead;
       S->nlay = nl; S->ghost = (n_dead > 0) ? n_live : -1;
       S->ktl = kt_new;
+      S->ktring[n_updates & 1] = kt_new;      // update number n_updates (the next one) stores z in this layout
     } else {
       S->active = 0;
       atomicAdd(done_count, 1);

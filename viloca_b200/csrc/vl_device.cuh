@@ -77,6 +77,8 @@ struct VlState {
   int stalled;    // layout grew past the kernel class this restart is scheduled in
   int ticket;     // read tiles of the current responsibility update that have finished
   int pub;        // updates completed AND visible: written last by the scalar update (fused chunks poll it)
+  int ktring[2];  // ktring[u & 1] = tiles of the layout update u stores z / w z in (set by the update before it)
+  int pad_;
 };
 
 // Read-only description of one (window, restart) problem.

@@ -51,6 +51,29 @@ constexpr int vl_min_ctas(int ktm) { return ktm <= 2 ? 6 : (ktm <= 4 ? 5 : (ktm 
 
 namespace {
 
+// Poll (thread 0, bounded) until the restart has published `target` completed updates; false if
+// it left its loop instead.
+__device__ __forceinline__ bool vl_wait_published(const VlState* S, int target) {
+  __shared__ int ok;
+  if (threadIdx.x == 0) {
+    const volatile int* pub = &S->pub;
+    const volatile int* act = &S->active;
+    int r = 1;
+    for (unsigned spin = 0; *pub < target; ++spin) {
+      if (*act == 0) { r = 0; break; }
+      __nanosleep(40);
+      if (spin > (1u << 26)) __trap();       // bounded: a lost dependency is an error, not a hang
+    }
+    if (*act == 0) r = 0;
+    ok = r;
+    __threadfence();
+  }
+  __syncthreads();
+  const int r = ok;
+  __syncthreads();
+  return r != 0;
+}
+
 // =========================================================================================
 // update_mean_haplo.  Per (position l, base b, slot s) the logit is
 //   (l, b) a dense column j:  T[j,s]    = sum_n w_n z[n,s] Dm[n,j]              (DMMA, M = column)
@@ -61,7 +84,8 @@ namespace {
 // order.
 // =========================================================================================
 template <int KTM, int MODE>
-__device__ __forceinline__ bool vl_haplo_body(const VlProblem* __restrict__ probs, const int2 tm, const int stage_doubles) {
+__device__ __forceinline__ bool vl_haplo_body(const VlProblem* __restrict__ probs, const int2 tm, const int stage_doubles,
+                                              const int* zticket, const int z_want, const int pub_want) {
   constexpr int NB = (8 * KTM + 31) / 32;        // 32-slot groups (lanes = slots in the sparse part)
   constexpr int KSM = vl_ks(KTM);
   constexpr int DM_STAGE = VL_H_NC * VL_PT;            // doubles
@@ -74,27 +98,48 @@ __device__ __forceinline__ bool vl_haplo_body(const VlProblem* __restrict__ prob
   GK_DECL(tm.x == 0 && tm.y == 0);
   const VlProblem& P = probs[tm.x];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, q = lane & 3;
-  // the restart's state and this tile's static maps go to shared memory up front: one memory
-  // latency each, overlapped with the first bulk copies, instead of dependent loads later
+  // Inside a chunk launch (zticket != nullptr) the operand loop starts as soon as the read tiles
+  // of the previous update have written w z -- it needs that update's layout width only
+  // (ktring) -- and overlaps the scalar update; the state is read after it has been published.
+  // This tile's static maps go to shared memory up front (one memory latency, overlapped).
   __shared__ VlState sS;
   __shared__ int s_tpos[VL_PT], s_collb[VL_PT], s_poscol[VL_PT][VL_B], s_ep[VL_PT][VL_B + 1];
   __shared__ unsigned s_refb[VL_PT];
-  vl_load_state(&sS, P.st, tid);
+  __shared__ int s_kt_old;
+  const bool early = zticket != nullptr;
   if (tid < VL_PT) {
     s_tpos[tid] = P.tile_pos[(size_t)tm.y * VL_PT + tid];
     s_collb[tid] = P.col_lb[(size_t)tm.y * VL_PT + tid];
   }
+  if (early) {
+    if (tid == 0) {
+      int kt = -1;
+      const volatile int* t = zticket;
+      const volatile int* act = &P.st->active;
+      for (unsigned spin = 0; *t < z_want; ++spin) {
+        if (*act == 0) break;
+        __nanosleep(40);
+        if (spin > (1u << 26)) __trap();
+      }
+      if (*t >= z_want) kt = *reinterpret_cast<const volatile int*>(&P.st->ktring[(pub_want + 1) & 1]);
+      __threadfence();
+      s_kt_old = kt;
+    }
+  } else {
+    vl_load_state(&sS, P.st, tid);
+  }
   __syncthreads();
-  const VlState* S = &sS;
-  const int ktl = S->ktl, ktz = S->ktl_z;
-  if (S->active == 0 || ktl > KTM || ktz > KTM) return false;
+  if (!early && tid == 0) s_kt_old = (sS.active != 0) ? sS.ktl_z : -1;
+  if (!early) __syncthreads();
+  const int ktz = s_kt_old;                // tiles of the layout w z is stored in
+  if (ktz < 0 || ktz > KTM) return false;
+  if (early) asm volatile("fence.proxy.async;\n" ::: "memory");   // bulk copies below read what other CTAs wrote
   // a narrow layout has small stages: use the same shared memory for a deeper pipeline
   const int st_stride = DM_STAGE + VL_H_NC * vl_ks(ktz);
   const int nstg = min(VL_MAX_STAGES, max(stage_doubles, VL_STAGES * ST_STRIDE) / st_stride);
 
   const int Npad = P.Npad;
-  const int KSz = vl_ks(ktz), KSn = vl_ks(ktl), K8 = 8 * ktl;
-  const int nlay = S->nlay;
+  const int KSz = vl_ks(ktz), K8z = 8 * ktz;
   const int nchunks = Npad / VL_H_NC;
   const double* __restrict__ dmg = P.dm + (size_t)tm.y * Npad * VL_PT;
   const double* wzg = P.wz;     // (mutable state: no __restrict__, these must stay coherent loads)
@@ -124,13 +169,6 @@ __device__ __forceinline__ bool vl_haplo_body(const VlProblem* __restrict__ prob
   if (tid == 0)
     for (int c = 0; c < nstg - 1 && c < nchunks; ++c) issue(c);
 
-  // column of the stored w z each of this thread's B-fragment columns comes from
-  int co[KTM];
-#pragma unroll
-  for (int i = 0; i < KTM; ++i) {
-    const int s = 8 * i + g;
-    co[i] = (i < ktl && s < nlay) ? gat[s] : 0;
-  }
   // warp = all 16 columns (two m-tiles) x 8 of the 32 reads of every stage: one w z fragment
   // feeds two DMMAs
   double acc[2][KTM][2];
@@ -141,7 +179,7 @@ __device__ __forceinline__ bool vl_haplo_body(const VlProblem* __restrict__ prob
 
   const int acol0 = (g + 4 * q) & 15, acol1 = (8 + g + 4 * q) & 15;   // vl_dm_col(row, g / 8 + g), row % 4 == q
   GK_TICK(0);
-  vl_dispatch_tiles<KTM>(ktl, [&](auto ktc) {
+  vl_dispatch_tiles<KTM>(ktz, [&](auto ktc) {
     constexpr int KT = decltype(ktc)::value;
     for (int c = 0; c < nchunks; ++c) {
       const int st = c % nstg;
@@ -154,10 +192,10 @@ __device__ __forceinline__ bool vl_haplo_body(const VlProblem* __restrict__ prob
         const int row = warp * (VL_H_NC / 4) + 4 * s + q;
         const double a0 = dt[row * VL_PT + acol0];
         const double a1 = dt[row * VL_PT + acol1];
-        const double* zr = zt + row * KSz;
+        const double* zr = zt + row * KSz + g;
 #pragma unroll
         for (int i = 0; i < KT; ++i) {
-          const double bf = zr[co[i]];
+          const double bf = zr[8 * i];
           vl_dmma(acc[0][i], a0, bf);
           vl_dmma(acc[1][i], a1, bf);
         }
@@ -169,16 +207,28 @@ __device__ __forceinline__ bool vl_haplo_body(const VlProblem* __restrict__ prob
   // ---- the stage buffers are free now: T [16][K8] and Cm [16][5][K8] live in them; the four
   // warps add their partial sums over the reads into T one after the other (fixed order) ----
   GK_TICK(1);
+  // the state of this update: published by the scalar update of the previous one
+  if (early) {
+    if (!vl_wait_published(P.st, pub_want)) return false;
+    vl_load_state(&sS, P.st, tid);
+    __syncthreads();
+  }
+  const VlState* S = &sS;
+  const int ktl = S->ktl;
+  if (S->active == 0 || ktl > KTM || S->ktl_z != ktz) return false;
+  const int KSn = vl_ks(ktl), K8 = 8 * ktl;
+  const int nlay = S->nlay;
+  // T [16][8 ktz] in the slot order of the stored w z, Cm [16][5][K8] in the current one
   double* T = stg;
-  double* Cm = stg + VL_PT * K8;
+  double* Cm = stg + VL_PT * K8z;
   for (int turn = 0; turn < VL_THREADS / 32; ++turn) {
     if (warp == turn) {
 #pragma unroll
       for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
         for (int i = 0; i < KTM; ++i)
-          if (i < ktl) {
-            double2* tp = reinterpret_cast<double2*>(T + (mt * 8 + g) * K8 + 8 * i + 2 * q);
+          if (i < ktz) {
+            double2* tp = reinterpret_cast<double2*>(T + (mt * 8 + g) * K8z + 8 * i + 2 * q);
             double2 o = make_double2(0.0, 0.0);
             if (turn > 0) o = *tp;
             *tp = make_double2(o.x + acc[mt][i][0], o.y + acc[mt][i][1]);
@@ -247,10 +297,11 @@ __device__ __forceinline__ bool vl_haplo_body(const VlProblem* __restrict__ prob
       lc[b] = (j < 0) ? -1 : j - tm.y * VL_PT;
     }
     if (slot < nlay) {
+      const int zslot = gat[slot];                         // column of the stored w z this slot continues
       double lgt[VL_B];
 #pragma unroll
       for (int b = 0; b < VL_B; ++b) {
-        const double cb = (lc[b] >= 0) ? T[lc[b] * K8 + slot] : Cm[(pos * VL_B + b) * K8 + slot];
+        const double cb = (lc[b] >= 0) ? T[lc[b] * K8z + zslot] : Cm[(pos * VL_B + b) * K8 + slot];
         lgt[b] = ((MODE == VL_MODE_LEP) ? cscale * cb : cb) + ((rc == (unsigned)b) ? mlg0 : refoff);
       }
       double m = lgt[0];
@@ -308,7 +359,7 @@ __device__ __forceinline__ bool vl_haplo_body(const VlProblem* __restrict__ prob
 template <int KTM, int MODE>
 __global__ void __launch_bounds__(VL_THREADS, vl_min_ctas(KTM))
 vl_haplo_kernel(const VlProblem* __restrict__ probs, const int2* __restrict__ tiles) {
-  vl_haplo_body<KTM, MODE>(probs, tiles[blockIdx.x], 0);
+  vl_haplo_body<KTM, MODE>(probs, tiles[blockIdx.x], 0, nullptr, 0, 0);
 }
 
 // =========================================================================================
@@ -319,7 +370,7 @@ vl_haplo_kernel(const VlProblem* __restrict__ probs, const int2* __restrict__ ti
 template <int KTM, int MODE>
 __device__ __forceinline__ void vl_cluster_body(const VlProblem* __restrict__ probs, const int2 tm,
                                                 int* __restrict__ done_count, int4* __restrict__ pstat,
-                                                const int stage_doubles) {
+                                                const int stage_doubles, int* zticket) {
   constexpr int KSM = vl_ks(KTM), K8M = 8 * KTM;
   constexpr int DM_STAGE = VL_ZT_READS * VL_PT;        // doubles
   constexpr int ST_STRIDE = DM_STAGE + VL_PT * KSM;    // dm | gm
@@ -562,7 +613,10 @@ __device__ __forceinline__ void vl_cluster_body(const VlProblem* __restrict__ pr
   VlState* Sw = P.st;
   __threadfence();
   __syncthreads();
-  if (tid == 0) s_last = (atomicAdd(&Sw->ticket, 1) == P.n_ztiles - 1);
+  if (tid == 0) {
+    if (zticket != nullptr) atomicAdd(zticket, 1);       // w z of this tile is visible: the next haplotype tiles may start
+    s_last = (atomicAdd(&Sw->ticket, 1) == P.n_ztiles - 1);
+  }
   __syncthreads();
   GK_TICK(12);
 #ifdef VL_RS_PROFILE
@@ -588,45 +642,26 @@ template <int KTM, int MODE>
 __global__ void __launch_bounds__(VL_THREADS, vl_min_ctas(KTM))
 vl_cluster_kernel(const VlProblem* __restrict__ probs, const int2* __restrict__ tiles,
                   int* __restrict__ done_count, int4* __restrict__ pstat) {
-  vl_cluster_body<KTM, MODE>(probs, tiles[blockIdx.x], done_count, pstat, 0);
+  vl_cluster_body<KTM, MODE>(probs, tiles[blockIdx.x], done_count, pstat, 0, nullptr);
 }
 
 // =========================================================================================
 // A whole chunk of updates of one kernel class in ONE launch.  Block b works on update
 // b / (n_ht + n_zt) of the chunk: first the haplotype tiles of every scheduled restart, then
 // their read tiles.  Dependencies are per restart and point to lower block indices only (blocks
-// are dispatched in index order): a haplotype tile of update u waits until the restart has
-// published u completed updates (VlState::pub, written last by the scalar update), a read tile
-// additionally until all haplotype tiles of its update have signalled (hticket).  No launch
-// latency and no kernel boundary between the steps, and restarts advance independently of each
-// other inside the chunk.
+// are dispatched in index order): a haplotype tile of update u starts its operand loop when all
+// read tiles of update u - 1 have signalled (zticket: their w z is visible; the loop overlaps the
+// scalar update of u - 1) and reads the state once the restart has published u completed updates
+// (VlState::pub, written last by the scalar update); a read tile waits for the published state and
+// for all haplotype tiles of its update (hticket).  No launch latency and no kernel boundary
+// between the steps, and restarts advance independently of each other inside the chunk.
 // =========================================================================================
-__device__ __forceinline__ bool vl_wait_published(const VlState* S, int target) {
-  __shared__ int ok;
-  if (threadIdx.x == 0) {
-    const volatile int* pub = &S->pub;
-    const volatile int* act = &S->active;
-    int r = 1;
-    for (unsigned spin = 0; *pub < target; ++spin) {
-      if (*act == 0) { r = 0; break; }
-      __nanosleep(40);
-      if (spin > (1u << 26)) __trap();       // bounded: a lost dependency is an error, not a hang
-    }
-    if (*act == 0) r = 0;
-    ok = r;
-    __threadfence();
-  }
-  __syncthreads();
-  const int r = ok;
-  __syncthreads();
-  return r != 0;
-}
-
 template <int KTM, int MODE>
 __global__ void __launch_bounds__(VL_THREADS, vl_min_ctas(KTM))
 vl_chunk_kernel(const VlProblem* __restrict__ probs, const int2* __restrict__ htiles, int n_ht,
                 const int2* __restrict__ ztiles, int n_zt, const int* __restrict__ chunk_base,
-                int* hticket, int* __restrict__ done_count, int4* __restrict__ pstat, const int stage_doubles) {
+                int* hticket, int* zticket, int* __restrict__ done_count, int4* __restrict__ pstat,
+                const int stage_doubles) {
   const int per_update = n_ht + n_zt;
   const int it = blockIdx.x / per_update, r = blockIdx.x - it * per_update;
   const bool is_h = r < n_ht;
@@ -634,11 +669,9 @@ vl_chunk_kernel(const VlProblem* __restrict__ probs, const int2* __restrict__ ht
   const VlProblem& P = probs[tm.x];
   const VlState* S = P.st;
   GK_DECL(tm.x == 0 && tm.y == 0);
-  if (!vl_wait_published(S, chunk_base[tm.x] + it)) return;        // the restart left its loop
-  GK_TICK(is_h ? 6 : 14);
+  const int pub_want = chunk_base[tm.x] + it;
   if (is_h) {
-    asm volatile("fence.proxy.async;\n" ::: "memory");   // bulk copies below read what other CTAs wrote
-    if (!vl_haplo_body<KTM, MODE>(probs, tm, stage_doubles)) return;
+    if (!vl_haplo_body<KTM, MODE>(probs, tm, stage_doubles, zticket + tm.x, it * P.n_ztiles, pub_want)) return;
 #ifdef VL_RS_PROFILE
     gk_t_ = clock64();
 #endif
@@ -646,28 +679,28 @@ vl_chunk_kernel(const VlProblem* __restrict__ probs, const int2* __restrict__ ht
     __syncthreads();
     if (threadIdx.x == 0) atomicAdd(&hticket[tm.x], 1);
     GK_TICK(7);
-  } else {
-    {
-      const volatile int* kt = &S->ktl;
-      const volatile int* ktz = &S->ktl_z;
-      if (*kt > KTM || *ktz > KTM) return;       // layout outgrew this class: its haplotype tiles bail out too
-    }
-    __shared__ int go;
-    if (threadIdx.x == 0) {
-      const volatile int* t = &hticket[tm.x];
-      const int want = (it + 1) * P.n_htiles;
-      for (unsigned spin = 0; *t < want; ++spin) {
-        __nanosleep(40);
-        if (spin > (1u << 26)) __trap();
-      }
-      __threadfence();
-      go = 1;
-    }
-    __syncthreads();
-    GK_TICK(15);
-    asm volatile("fence.proxy.async;\n" ::: "memory");
-    vl_cluster_body<KTM, MODE>(probs, tm, done_count, pstat, stage_doubles);
+    return;
   }
+  if (!vl_wait_published(S, pub_want)) return;        // the restart left its loop
+  GK_TICK(14);
+  {
+    const volatile int* kt = &S->ktl;
+    const volatile int* ktz = &S->ktl_z;
+    if (*kt > KTM || *ktz > KTM) return;         // layout outgrew this class: its haplotype tiles bail out too
+  }
+  if (threadIdx.x == 0) {
+    const volatile int* t = &hticket[tm.x];
+    const int want = (it + 1) * P.n_htiles;
+    for (unsigned spin = 0; *t < want; ++spin) {
+      __nanosleep(40);
+      if (spin > (1u << 26)) __trap();
+    }
+    __threadfence();
+  }
+  __syncthreads();
+  GK_TICK(15);
+  asm volatile("fence.proxy.async;\n" ::: "memory");
+  vl_cluster_body<KTM, MODE>(probs, tm, done_count, pstat, stage_doubles, zticket + tm.x);
 }
 
 // One thread per problem: state_init_dict of draw_init_state (initialization.py:6-43), the
@@ -707,6 +740,7 @@ __global__ void vl_init_kernel(const VlProblem* __restrict__ probs, int n_probs,
   S->status = VL_STATUS_RUNNING; S->active = 1;
   S->ktl = P.KT; S->ktl_z = P.KT; S->nlay = K; S->ghost = -1; S->ghost_mult = 0.0; S->stalled = 0;
   S->nlay_z = K; S->ghost_z = -1; S->ticket = 0; S->pub = 0;
+  S->ktring[0] = P.KT; S->ktring[1] = P.KT;
   pstat[p] = make_int4(1, P.KT, K, 0);
 }
 
@@ -860,7 +894,7 @@ cudaError_t launch_cluster(const VlProblem* probs, const int2* tiles, int n, int
 
 template <int KTM, int MODE>
 cudaError_t launch_chunk(const VlProblem* probs, const int2* htiles, int n_ht, const int2* ztiles, int n_zt,
-                         int n_updates, const int* chunk_base, int* hticket, int* done_count, int4* pstat,
+                         int n_updates, const int* chunk_base, int* hticket, int* zticket, int* done_count, int4* pstat,
                          cudaStream_t stream) {
   // With few tiles per update the SMs are mostly idle and one restart's update is a chain of
   // latencies: give every CTA enough shared memory to have (nearly) all its operand stages in
@@ -876,7 +910,7 @@ cudaError_t launch_chunk(const VlProblem* probs, const int2* htiles, int n_ht, c
   const long long blocks = (long long)n_updates * (n_ht + n_zt);
   if (blocks > 0x7fffffffLL) return cudaErrorInvalidValue;
   vl_chunk_kernel<KTM, MODE><<<(unsigned)blocks, VL_THREADS, smem, stream>>>(probs, htiles, n_ht, ztiles, n_zt, chunk_base,
-                                                                            hticket, done_count, pstat, stage_doubles);
+                                                                            hticket, zticket, done_count, pstat, stage_doubles);
   return cudaGetLastError();
 }
 
@@ -912,9 +946,9 @@ cudaError_t vl_launch_cluster(int cls, int mode, const VlProblem* probs, const i
 
 cudaError_t vl_launch_chunk(int cls, int mode, const VlProblem* probs, const int2* htiles, int n_ht,
                             const int2* ztiles, int n_zt, int n_updates, const int* chunk_base, int* hticket,
-                            int* done_count, int4* pstat, cudaStream_t stream) {
+                            int* zticket, int* done_count, int4* pstat, cudaStream_t stream) {
   if (n_ht <= 0 || n_zt <= 0 || n_updates <= 0) return cudaSuccess;
-  VL_DISPATCH(launch_chunk, probs, htiles, n_ht, ztiles, n_zt, n_updates, chunk_base, hticket, done_count, pstat, stream)
+  VL_DISPATCH(launch_chunk, probs, htiles, n_ht, ztiles, n_zt, n_updates, chunk_base, hticket, zticket, done_count, pstat, stream)
 }
 
 cudaError_t vl_launch_init(const VlProblem* probs, int n_probs, int4* pstat, cudaStream_t stream) {

@@ -26,10 +26,10 @@ cudaError_t vl_launch_haplo(int cls, int mode, const VlProblem* probs, const int
 cudaError_t vl_launch_cluster(int cls, int mode, const VlProblem* probs, const int2* tiles, int n_tiles,
                               int* done_count, int4* pstat, cudaStream_t stream);
 // n_updates updates of one kernel class in one launch (vl_chunk_kernel): chunk_base[p] = updates
-// restart p had completed when the chunk was scheduled, hticket[p] zeroed by the caller
+// restart p had completed when the chunk was scheduled, hticket[p] and zticket[p] zeroed by the caller
 cudaError_t vl_launch_chunk(int cls, int mode, const VlProblem* probs, const int2* htiles, int n_ht,
                             const int2* ztiles, int n_zt, int n_updates, const int* chunk_base, int* hticket,
-                            int* done_count, int4* pstat, cudaStream_t stream);
+                            int* zticket, int* done_count, int4* pstat, cudaStream_t stream);
 cudaError_t vl_launch_init(const VlProblem* probs, int n_probs, int4* pstat, cudaStream_t stream);
 cudaError_t vl_launch_prepare(const uint8_t* codes, const double* lt, const double* lo, const int* col_lb,
                               double* dm, double* mcount, double* ltsum, int N, int L, int Npad, int NCs,

@@ -124,8 +124,8 @@ int vl_batch_workspace_bytes(const vl_window_desc* windows, int32_t n_windows, s
  * Host-only (no CUDA call): how the engine will lay out the reads of one window.  The
  * one-hot-expanded read matrix has a column per (position, base); the most frequent base of
  * every position and every other pair that at least max(2, min(64, N/128)) reads carry become
- * dense operand columns (all columns of a position inside one 16-column tile), the remaining
- * entries go to sparse lists.  n_cols_out: dense columns including tile padding; n_sparse_out:
+ * dense operand columns (all columns of a position inside one 16-column tile; positions are
+ * placed first-fit in ascending order), the remaining entries go to sparse lists.  n_cols_out: dense columns including tile padding; n_sparse_out:
  * sparse entries; col_lb (optional, capacity 5 * length + 16 rounded up to 16): l * 5 + b per
  * dense column, -1 for padding.  Only mode, n_reads, length and codes of the desc are read.
  */

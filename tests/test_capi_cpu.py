@@ -91,16 +91,19 @@ def _plan_numpy(codes):
     n, length = codes.shape
     cnt = np.stack([(codes == b).sum(axis=0) for b in range(5)], axis=1)
     thr = min(max(n // 128, 2), 64)
-    cols, in_tile = [], 0
+    tiles = []
     for l in range(length):
         best = int(np.argmax(cnt[l]))
         bases = [b for b in range(5) if b == best or cnt[l, b] >= thr]
-        if len(cols) % 16 + len(bases) > 16 or (len(cols) % 16 == 0 and in_tile):
-            cols += [-1] * (-len(cols) % 16)
-            in_tile = 0
-        cols += [l * 5 + b for b in bases]
-        in_tile += 1
-    cols += [-1] * (-len(cols) % 16)
+        for t in tiles:                           # first fit in position order
+            if len(t) + len(bases) <= 16:
+                t.extend(l * 5 + b for b in bases)
+                break
+        else:
+            tiles.append([l * 5 + b for b in bases])
+    cols = []
+    for t in tiles:
+        cols += t + [-1] * (16 - len(t))
     dense = set(c for c in cols if c >= 0)
     sparse = sum(int(cnt[l, b]) for l in range(length) for b in range(5) if l * 5 + b not in dense)
     return cols, sparse

@@ -82,7 +82,8 @@ struct WindowAnalysis {
 // Dense columns: the most frequent called base of every position (first on ties; base 0 if no
 // read covers the position) and every other pair carried by at least `thr` reads, where thr
 // grows with N: a dense column costs O(N) per contraction, a sparse entry one gathered row.
-// The columns of a position are consecutive and never straddle a 16-column tile.
+// The columns of a position are consecutive and never straddle a 16-column tile; tiles are filled
+// first-fit in position order.
 void plan_columns(const vl_window_desc& d, int Ls, WindowAnalysis& A) {
   const int N = d.n_reads, L = d.length;
   std::vector<int> cnt((size_t)L * VL_N_BASES, 0);
@@ -92,16 +93,11 @@ void plan_columns(const vl_window_desc& d, int Ls, WindowAnalysis& A) {
       if (row[l] < VL_N_BASES) ++cnt[(size_t)l * VL_N_BASES + row[l]];
   }
   const int thr = std::min(std::max(N / 128, 2), 64);
-  A.col_lb.clear(); A.tile_pos.clear();
   A.poscol.assign((size_t)Ls * VL_N_BASES, -1);
-  std::vector<int> tile_positions;
-  auto close_tile = [&]() {
-    while (A.col_lb.size() % VL_PT) A.col_lb.push_back(-1);
-    tile_positions.resize(VL_PT, -1);
-    A.tile_pos.insert(A.tile_pos.end(), tile_positions.begin(), tile_positions.end());
-    tile_positions.clear();
-  };
-  size_t sparse = 0;
+  // first fit: a position goes to the first tile that still has room for all its columns, so
+  // the single-column positions fill the gaps the multi-column ones leave
+  std::vector<std::vector<int>> tile_cols, tile_positions;
+  size_t first_open = 0, sparse = 0;
   for (int l = 0; l < L; ++l) {
     const int* c = &cnt[(size_t)l * VL_N_BASES];
     int best = 0;
@@ -111,15 +107,23 @@ void plan_columns(const vl_window_desc& d, int Ls, WindowAnalysis& A) {
       if (b == best || c[b] >= thr) bases[nb++] = b;
       else sparse += c[b];
     }
-    const size_t used = A.col_lb.size() % VL_PT;
-    if ((used == 0 && !tile_positions.empty()) || used + nb > VL_PT) close_tile();
-    for (int i = 0; i < nb; ++i) {
-      A.poscol[(size_t)l * VL_N_BASES + bases[i]] = (int)A.col_lb.size();
-      A.col_lb.push_back(l * VL_N_BASES + bases[i]);
-    }
-    tile_positions.push_back(l);
+    while (first_open < tile_cols.size() && tile_cols[first_open].size() == VL_PT) ++first_open;
+    size_t t = first_open;
+    while (t < tile_cols.size() && tile_cols[t].size() + nb > VL_PT) ++t;
+    if (t == tile_cols.size()) { tile_cols.emplace_back(); tile_positions.emplace_back(); }
+    for (int i = 0; i < nb; ++i) tile_cols[t].push_back(l * VL_N_BASES + bases[i]);
+    tile_positions[t].push_back(l);
   }
-  if (!tile_positions.empty()) close_tile();
+  A.col_lb.clear(); A.tile_pos.clear();
+  for (size_t t = 0; t < tile_cols.size(); ++t) {
+    for (int lb : tile_cols[t]) {
+      A.poscol[lb] = (int)A.col_lb.size();
+      A.col_lb.push_back(lb);
+    }
+    A.col_lb.resize((t + 1) * VL_PT, -1);
+    A.tile_pos.insert(A.tile_pos.end(), tile_positions[t].begin(), tile_positions[t].end());
+    A.tile_pos.resize((t + 1) * VL_PT, -1);
+  }
   A.NCs = (int)A.col_lb.size();
   A.nnz = sparse;
 }

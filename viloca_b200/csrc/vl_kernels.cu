@@ -61,8 +61,8 @@ __device__ __forceinline__ bool vl_wait_published(const VlState* S, int target) 
     int r = 1;
     for (unsigned spin = 0; *pub < target; ++spin) {
       if (*act == 0) { r = 0; break; }
-      __nanosleep(40);
-      if (spin > (1u << 26)) __trap();       // bounded: a lost dependency is an error, not a hang
+      __nanosleep(spin < 4096 ? 40 : 1000);
+      if (spin > (1u << 27)) __trap();       // bounded (~2 min): a lost dependency is an error, not a hang
     }
     if (*act == 0) r = 0;
     ok = r;
@@ -118,8 +118,8 @@ __device__ __forceinline__ bool vl_haplo_body(const VlProblem* __restrict__ prob
       const volatile int* act = &P.st->active;
       for (unsigned spin = 0; *t < z_want; ++spin) {
         if (*act == 0) break;
-        __nanosleep(40);
-        if (spin > (1u << 26)) __trap();
+        __nanosleep(spin < 4096 ? 40 : 1000);
+        if (spin > (1u << 27)) __trap();
       }
       if (*t >= z_want) kt = *reinterpret_cast<const volatile int*>(&P.st->ktring[(pub_want + 1) & 1]);
       __threadfence();
@@ -692,8 +692,8 @@ vl_chunk_kernel(const VlProblem* __restrict__ probs, const int2* __restrict__ ht
     const volatile int* t = &hticket[tm.x];
     const int want = (it + 1) * P.n_htiles;
     for (unsigned spin = 0; *t < want; ++spin) {
-      __nanosleep(40);
-      if (spin > (1u << 26)) __trap();
+      __nanosleep(spin < 4096 ? 40 : 1000);
+      if (spin > (1u << 27)) __trap();
     }
     __threadfence();
   }

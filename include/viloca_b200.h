@@ -152,9 +152,10 @@ void vl_batch_destroy(vl_batch* batch);
 /*
  * VL_OPT_RESIDENT (default 0): 1 lets restarts whose live clusters fit 4 tiles and whose operand
  * fits one SM's shared memory iterate inside a persistent one-CTA-per-restart kernel (one pass
- * over the operand per update, no launches); 0 keeps every restart on the three per-iteration
- * kernels.  Same results to rounding; pays off when the batch holds many more restarts than the
- * GPU has SMs.  May be changed between runs.
+ * over the operand per update, no launches); 0 keeps every restart on the general-path
+ * kernels (haplotype tiles + read tiles of every update).  Same results to rounding; pays off
+ * when the batch holds many more restarts than the GPU has SMs.  May be
+ * changed between runs.
  */
 #define VL_OPT_RESIDENT 2
 /*

@@ -1,19 +1,20 @@
-// CAVI kernels for sm_100a.  One iteration of a (window, restart) problem = two launches
-// over the whole batch:
-//   vl_haplo_kernel    update_mean_haplo   (uqs update_eqs.py:73-101, lep update_eqs.py:115-159)
+// CAVI kernels for sm_100a.  One iteration (update) of a (window, restart) problem = its
+// haplotype tiles, then its read tiles; vl_chunk_kernel runs a whole chunk of updates of all
+// scheduled restarts in one launch (blocks wait on per-restart counters), vl_haplo_kernel and
+// vl_cluster_kernel run the two phases of one update as separate launches (same device code):
+//   vl_haplo_body      update_mean_haplo   (uqs update_eqs.py:73-101, lep update_eqs.py:115-159)
 //                      + the sums update_a_and_b / elbo_haplo need (update_eqs.py:103-112,
 //                      elbo_eqs.py:65-78)
-//   vl_cluster_kernel  update_mean_cluster (uqs update_eqs.py:55-71, lep update_eqs.py:90-112)
+//   vl_cluster_body    update_mean_cluster (uqs update_eqs.py:55-71, lep update_eqs.py:90-112)
 //                      + the sums update_alpha / elbo_data / elbo_cluster / update_c_and_d need;
 //                      the CTA of a restart that finishes last then does the scalar update
 //                      (vl_cavi.cuh): alpha, mean_log_pi, a, b, (c, d), the ELBO, the loop state
 //                      machine of run_cavi (cavi.py:120-169) and the next live-cluster layout
 //
-// Both contractions run on the FP64 tensor pipe (DMMA m8n8k4) over the dense majority operand
-// Dm (vl_device.cuh), whose tiles and the other operand (responsibilities or the haplotype
-// complement table) are staged in shared memory by TMA bulk copies behind mbarriers; the
-// minority entries are added from the sparse lists; softmax / ELBO reductions are fused into
-// the epilogues.
+// Both contractions run on the FP64 tensor pipe (DMMA m8n8k4) over the dense-column operand
+// Dm (vl_device.cuh), whose tiles and the other operand (w z or the haplotype complement
+// table) are staged in shared memory by TMA bulk copies behind mbarriers; the remaining
+// entries are added from the sparse lists; softmax / ELBO reductions are fused into the epilogues.
 #ifdef VL_RS_PROFILE
 #define VL_SU_PROFILE
 __device__ unsigned long long vl_su_cycles[8];     // vl_scalar_update phases of restart 0 (vl_cavi.cuh)

@@ -5,7 +5,7 @@
 // Eligible restarts: layout of at most 4 cluster tiles (32 live clusters + ghost), at most 16
 // column tiles, operand ring + tables within the 227 KB of shared memory (vl_resident_smem_bytes).
 // Everything else, and the first iterations of every restart while most of the K clusters are
-// still alive, runs on the three general-path kernels (vl_kernels.cu); the two paths share the
+// still alive, runs on the general-path kernels (vl_kernels.cu); the two paths share the
 // state in global memory and can alternate at chunk boundaries.
 //
 // One iteration = ONE pass over the dense operand Dm (vl_device.cuh), streamed through a

@@ -44,7 +44,7 @@ def build(force: bool = False, verbose: bool = False, profile: bool = False) -> 
     """``profile=True`` compiles the resident kernel's cycle counters in (vl_debug_counters)."""
     os.makedirs(LIB_DIR, exist_ok=True)
     headers = [os.path.normpath(os.path.join(CSRC, h)) for h in HEADERS]
-    objs = []
+    objs, jobs = [], []
     for src in SOURCES:
         src_path = os.path.join(CSRC, src)
         obj = os.path.join(LIB_DIR, src.replace(".cu", ".o"))
@@ -55,7 +55,10 @@ def build(force: bool = False, verbose: bool = False, profile: bool = False) -> 
             if verbose:
                 cmd.insert(1, "-Xptxas=-v")
                 print(" ".join(cmd), file=sys.stderr)
-            subprocess.run(cmd, check=True)
+            jobs.append((cmd, subprocess.Popen(cmd)))          # the translation units compile side by side
+    for cmd, proc in jobs:
+        if proc.wait() != 0:
+            raise subprocess.CalledProcessError(proc.returncode, cmd)
     if force or _stale(LIB_PATH, objs):
         cmd = [_nvcc(), "-shared", "-o", LIB_PATH] + objs + ["-lcudart_static", "-lrt", "-lpthread", "-ldl"]
         if verbose:

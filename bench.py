@@ -25,7 +25,8 @@ multiprocessing Pool over windows with cpu_count()-1 single-threaded workers
 (viloca/shotgun.py:527-538).
 
 Multi-GPU: one process per GPU (torchrun), windows sharded by the host-side longest-first
-scheduler, no data-path collective; weak scaling (one synthetic genome per GPU).
+scheduler, no data-path collective; weak scaling with fixed per-GPU work (one copy of the same
+synthetic genome per GPU; the shards mix windows of the copies).
 """
 from __future__ import annotations
 
@@ -68,8 +69,9 @@ def dist_env():
 
 
 def shard_items(spec, n_windows, world):
-    """Global work list of a weak-scaling job: one synthetic genome per GPU, every window an
-    independent item; longest-first partition over the ranks (no collective)."""
+    """Global work list of a weak-scaling job: one copy of the synthetic genome per GPU, every
+    window an independent item; longest-first partition over the ranks (no collective).  The
+    copies are identical (seed 0), so per-GPU work does not depend on the number of GPUs."""
     from viloca_b200 import scheduler
     items = [(sample, w) for sample in range(world) for w in range(n_windows)]
     costs = [float(spec.coverage) * spec.window_length * spec.n_clusters * spec.n_starts] * len(items)
@@ -308,7 +310,9 @@ def run_b200_arm(args):
     n_windows = args.windows or spec.n_windows
     items, parts = shard_items(spec, n_windows, world)
     mine = [items[i] for i in parts[rank]]
-    windows = [synthetic.make_window(spec, w, master_seed=sample).pin() for sample, w in mine]
+    # weak scaling with FIXED per-GPU work: every sample is the same synthetic genome (seed 0), so each
+    # rank runs every window index exactly once whatever the number of GPUs
+    windows = [synthetic.make_window(spec, w, master_seed=0).pin() for sample, w in mine]
     n_problems = sum(w.n_starts for w in windows)
 
     def barrier():
@@ -444,7 +448,7 @@ def run_b200_arm(args):
             "config": {"workload": args.workload, "mode": spec.mode, "genome_length": spec.genome_length,
                        "window_length": spec.window_length, "windows_per_gpu": len(windows), "coverage": spec.coverage,
                        "n_unique_mean": float(np.mean([w.n_reads for w in windows])), "n_clusters": spec.n_clusters,
-                       "n_starts": spec.n_starts, "haplotypes": spec.n_haplotypes, "parallelism": f"windows x{world}",
+                       "n_starts": spec.n_starts, "haplotypes": spec.n_haplotypes, "parallelism": f"windows x{world}", "per_gpu_work": "the same 145-window genome on every GPU (seed 0)",
                        "dense_columns_mean": float(np.mean([o["NC"] for o in ops])),
                        "sparse_entries_mean": float(np.mean([o["nnz"] for o in ops])),
                        "l2": "inputs larger than L2 (working set %.0f MB per GPU, re-uploaded every step)" % (batch.workspace_bytes / 1e6)},

@@ -18,6 +18,9 @@ Fixtures:
                                   compute_reads_log_error_proba / load_reference_seq outputs
   data4/                          the reference's own fixture window tests/data_4 run through
                                   run_dpm_mfa.main (support.fas, cor.fas, ELBO history)
+  bam_windows/                    windows with real bases and qualities cut from the reference's
+                                  BAM fixtures tests/data_2,3,6,7 (oracle/bam_windows.py) and the
+                                  files run_dpm_mfa.main writes for them
 """
 from __future__ import annotations
 
@@ -40,6 +43,7 @@ GOLD = os.path.join(ROOT, "tests", "golden")
 sys.path.insert(0, os.path.join(HERE, "_bioshim"))
 sys.path.insert(0, REF)
 sys.path.insert(0, ROOT)
+sys.path.insert(0, HERE)
 
 from numpy.random import default_rng  # noqa: E402
 from scipy.special import betaln, digamma  # noqa: E402
@@ -344,6 +348,63 @@ def golden_data4():
         json.dump(meta, fh, indent=1)
 
 
+BAM_WINDOWS = [
+    # name, BAM, reference FASTA, start (0-based), length, max reads, n_starts, K, seed
+    ("hiv_3120", "data_2/REF_aln.bam", "data_2/cohort_consensus.fasta", 3120, 201, 300, 1, 100, 42),
+    ("hiv_2500_3starts", "data_2/REF_aln.bam", "data_2/cohort_consensus.fasta", 2500, 201, 300, 3, 100, 7),
+    ("sars_24520", "data_3/REF_aln.bam", "data_3/NC_045512.2.fasta", 24520, 201, 300, 1, 100, 42),
+    ("amplicon_90", "data_6/reads.shotgun.bam", "data_6/reference.fasta", 0, 90, None, 1, 100, 42),
+    ("longreads_2900", "data_7/reads.shotgun.bam", "data_7/reference.fasta", 2900, 1000, None, 1, 100, 42),
+]
+
+
+def golden_bam_windows():
+    """Windows of real reads (real Phred qualities, deletions, N padding) from the reference's
+    BAM fixtures through the unmodified run_dpm_mfa.main (use_quality_scores)."""
+    import time
+    import bam_windows as bw
+    from viloca.local_haplotype_inference.use_quality_scores import run_dpm_mfa, cavi, preparation
+    top = os.path.join(GOLD, "bam_windows")
+    os.makedirs(top, exist_ok=True)
+    meta = {}
+    for name, bam, fasta, start, length, max_reads, n_starts, K, seed in BAM_WINDOWS:
+        refs, alns = bw.read_bam(os.path.join(REF, "tests", bam))
+        ref_name, ref_seq = bw.read_fasta(os.path.join(REF, "tests", fasta))[0]
+        assert refs[0][0] == ref_name
+        ids, rows, quals = bw.cut_window(alns, 0, start, length, max_reads=max_reads)
+        d = os.path.join(top, name)
+        os.makedirs(d, exist_ok=True)
+        bw.save_fixture(os.path.join(d, "window.npz"), ref_name, start, ref_seq[start:start + length].upper(), ids, rows, quals)
+        t0 = time.time()
+        with tempfile.TemporaryDirectory() as tmp:
+            stem, f_reads, f_ref, f_q = bw.materialize(os.path.join(d, "window.npz"), tmp)
+            out = os.path.join(tmp, "out") + "/"
+            os.makedirs(out)
+            with contextlib.redirect_stdout(io.StringIO()):
+                run_dpm_mfa.main(f_reads, f_ref, f_q, out, n_starts, K, 0.0001, seed=seed)
+            for suffix in ("support.fas", "cor.fas"):
+                shutil.copy(os.path.join(out, f"{stem}.reads-{suffix}"), os.path.join(d, f"expected.reads-{suffix}"))
+            ref_bin, _ = preparation.load_reference_seq(f_ref, "ACGT-")
+            rb, w, q, _ = preparation.load_and_process_reads(f_reads, f_q, "ACGT-", True)
+        entry = {"stem": stem, "n_raw": len(rows), "n_unique": int(rb.shape[0]), "length": length, "n_starts": n_starts,
+                 "K": K, "seed": seed, "mean_quality": float(quals[quals > 2].mean()),
+                 "frac_gap": float(np.mean([r.count("-") for r in rows]) / length),
+                 "frac_N": float(np.mean([r.count("N") for r in rows]) / length)}
+        if n_starts == 1:
+            E = preparation.compute_reads_log_error_proba(q, rb, 5)
+            with contextlib.redirect_stdout(io.StringIO()):
+                _, res = cavi.run_cavi(K, 0.0001, "ACGT-", ref_bin, rb, w, E, 0, "./", 1e-3, False,
+                                       default_rng(seed=seed), seed)
+            entry.update(n_iterations=int(res["n_iterations"]), exit_message=res["exit_message"],
+                         elbo=float(res["elbo"]), history_elbo=[float(x) for x in res["history_elbo"]])
+        meta[name] = entry
+        print("bam window", name, {k: v for k, v in entry.items() if k != "history_elbo"}, f"{time.time() - t0:.1f}s")
+    import numpy, scipy
+    meta["versions"] = {"numpy": numpy.__version__, "scipy": scipy.__version__}
+    with open(os.path.join(top, "expected.json"), "w") as fh:
+        json.dump(meta, fh, indent=1)
+
+
 if __name__ == "__main__":
     if not os.path.isdir(REF):
         sys.exit(f"{REF} not found: goldens can only be regenerated where the reference is mounted")
@@ -355,4 +416,5 @@ if __name__ == "__main__":
     golden_init()
     golden_prep()
     golden_data4()
+    golden_bam_windows()
     print("wrote", GOLD)

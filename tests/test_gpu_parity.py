@@ -187,6 +187,52 @@ def test_data4_window_files_end_to_end(golden_dir, tmp_path):
         open(os.path.join(d, "expected_seed42.reads-cor.fas")).read()
 
 
+BAM_WINDOWS = ["hiv_3120", "hiv_2500_3starts", "sars_24520", "amplicon_90", "longreads_2900"]
+
+
+@pytest.mark.parametrize("name", BAM_WINDOWS)
+def test_bam_fixture_windows_end_to_end(golden_dir, tmp_path, name):
+    """Windows of real reads with real Phred qualities, deletions and N padding, cut from the
+    reference's BAM fixtures tests/data_2,3,6,7 (oracle/bam_windows.py), through the drop-in
+    entry point: the files the unmodified reference wrote for the same inputs are reproduced —
+    identical haplotype sequences, ids, ave_reads and corrected reads, posteriors to 1e-9."""
+    from oracle import bam_windows
+    from viloca_b200.local_haplotype_inference.use_quality_scores import run_dpm_mfa
+    d = os.path.join(golden_dir, "bam_windows", name)
+    meta = json.load(open(os.path.join(golden_dir, "bam_windows", "expected.json")))[name]
+    stem, f_reads, f_ref, f_q = bam_windows.materialize(os.path.join(d, "window.npz"), str(tmp_path))
+    assert stem == meta["stem"]
+    out_dir = os.path.join(str(tmp_path), "out") + "/"
+    os.makedirs(out_dir)
+    run_dpm_mfa.main(f_reads, f_ref, f_q, out_dir, meta["n_starts"], meta["K"], 0.0001, seed=meta["seed"])
+    got = _parse_support(out_dir + stem + ".reads-support.fas")
+    exp = _parse_support(os.path.join(d, "expected.reads-support.fas"))
+    assert [(i, s, w) for i, s, _, w in got] == [(i, s, w) for i, s, _, w in exp]
+    for (_, _, pg, _), (_, _, pe, _) in zip(got, exp):
+        assert abs(pg - pe) <= ENG_TOL * abs(pe) + 1e-300
+        assert (pg >= 0.9) == (pe >= 0.9)
+    assert open(out_dir + stem + ".reads-cor.fas").read() == open(os.path.join(d, "expected.reads-cor.fas")).read()
+
+
+@pytest.mark.parametrize("name", [n for n in BAM_WINDOWS if "starts" not in n])
+def test_bam_fixture_windows_trajectory(golden_dir, tmp_path, name):
+    """Same windows at the numeric seam: iteration count, exit message and the whole ELBO
+    history of the reference's cavi.run_cavi."""
+    from oracle import bam_windows
+    from viloca_b200.local_haplotype_inference import _common
+    d = os.path.join(golden_dir, "bam_windows", name)
+    meta = json.load(open(os.path.join(golden_dir, "bam_windows", "expected.json")))[name]
+    _, f_reads, f_ref, f_q = bam_windows.materialize(os.path.join(d, "window.npz"), str(tmp_path))
+    job = _common.WindowJob(mode="uqs", freads_in=f_reads, fref_in=f_ref, fname_qualities=f_q, output_dir="./",
+                            n_starts=1, K=meta["K"], alpha0=1e-4, seed=meta["seed"])
+    job.load()
+    assert job.window.n_reads == meta["n_unique"]
+    out = _engine().run_windows([job.window])[0]
+    r = out.restarts[0]
+    assert (r.n_iterations, r.exit_message) == (meta["n_iterations"], meta["exit_message"])
+    assert br.rel_err(r.history_elbo, np.array(meta["history_elbo"])) < ENG_TOL
+
+
 def _spec(mode, K, called):
     from viloca_b200 import synthetic
     base = synthetic.WORKLOADS["hiv5k_uqs"]

@@ -142,6 +142,28 @@ def test_data4_known_answer(golden_dir):
     assert len(groups) == 26
 
 
+@pytest.mark.parametrize("name", ["amplicon_90", "sars_24520", "longreads_2900"])
+def test_bam_fixture_windows(golden_dir, tmp_path, name):
+    """Windows of real reads cut from the reference's BAM fixtures (oracle/bam_windows.py): the
+    oracle follows the reference's cavi.run_cavi trajectory — same iteration count and exit, ELBO
+    history to 1e-12 (real Phred qualities, deletions, N padding, Q~10 long reads)."""
+    from oracle import bam_windows
+    from viloca_b200.local_haplotype_inference import _common
+    meta = json.load(open(os.path.join(golden_dir, "bam_windows", "expected.json")))[name]
+    _, f_reads, f_ref, f_q = bam_windows.materialize(os.path.join(golden_dir, "bam_windows", name, "window.npz"), str(tmp_path))
+    ids, seqs = _common.read_window_fasta(f_reads)
+    p = _common.prepare_reads(ids, seqs, np.load(f_q, allow_pickle=True), "ACGT-", True)
+    assert p.codes.shape == (meta["n_unique"], meta["length"]) and int(p.weights.sum()) == meta["n_raw"]
+    ref_codes, _, _ = _common.load_reference(f_ref, "ACGT-", upper=True)
+    reads = orc.onehot_from_codes(p.codes, dtype=np.int8)
+    ref = orc.onehot_from_codes(ref_codes, dtype=np.int8)
+    E = orc.reads_log_error_tensor(p.qualities, reads)
+    init = orc.draw_init_state("uqs", meta["K"], 1e-4, meta["length"], meta["n_unique"], ref, np.random.default_rng(meta["seed"]))
+    traj = orc.run("uqs", p.weights, ref, E, init)
+    assert (traj.n_iterations, traj.exit_message) == (meta["n_iterations"], meta["exit_message"])
+    np.testing.assert_allclose(np.array(traj.history_elbo), np.array(meta["history_elbo"]), rtol=1e-12)
+
+
 def test_init_draw_order(golden_dir):
     g = _load(golden_dir, "init.npz")
     from viloca_b200 import init_state

@@ -1,6 +1,9 @@
 """One upload + run + fetch of a synthetic workload (profiling target for ncu).
 
     python tools/run_workload.py [workload] [n_windows] [repeats]
+
+Environment: VL_N_READS / VL_MAX_ITER override the raw reads per window and the iteration cap
+(bounded samples of the large workloads), VL_RESIDENT / VL_FUSED select engine options.
 """
 import os
 import sys
@@ -12,7 +15,14 @@ from viloca_b200 import engine, synthetic  # noqa: E402
 name = sys.argv[1] if len(sys.argv) > 1 else "hiv5k_uqs"
 nw = int(sys.argv[2]) if len(sys.argv) > 2 and int(sys.argv[2]) > 0 else None
 rep = int(sys.argv[3]) if len(sys.argv) > 3 else 1
-wins = [w.pin() for w in synthetic.make_workload(name, nw)]
+kw = {}
+if os.environ.get("VL_N_READS"):
+    kw["n_reads"] = int(os.environ["VL_N_READS"])
+if os.environ.get("VL_MAX_ITER"):
+    kw["max_iter"] = int(os.environ["VL_MAX_ITER"])
+wins = [w.pin() for w in synthetic.make_workload(name, nw, **kw)]
+print(f"{name}: {len(wins)} windows, N_unique {[w.n_reads for w in wins[:4]]}, L {wins[0].length}, restarts {wins[0].n_starts}",
+      flush=True)
 resident = os.environ.get("VL_RESIDENT", "0") != "0"
 fused = os.environ.get("VL_FUSED", "1") != "0"
 with engine.CaviBatch(wins, resident=resident, fused_chunks=fused) as b:

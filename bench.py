@@ -87,7 +87,7 @@ def operand_stats(windows):
     for w in windows:
         d = w.desc()
         ncols, nsp = C.c_int32(0), C.c_int64(0)
-        col_lb = np.full((5 * w.length + 31) // 16 * 16, -1, dtype=np.int32)
+        col_lb = np.full(capi.lib.vl_window_plan_capacity(w.length), -1, dtype=np.int32)
         capi.check(capi.lib.vl_window_plan(C.byref(d), C.byref(ncols), C.byref(nsp), capi.i32_ptr(col_lb)))
         out.append({"N": w.n_reads, "Npad": -(-w.n_reads // 64) * 64, "L": w.length, "K": w.n_clusters,
                     "NCs": int(ncols.value), "NC": int((col_lb[:ncols.value] >= 0).sum()), "nnz": int(nsp.value)})
@@ -103,6 +103,7 @@ def launch_work(ops, stats):
     bytes: compulsory HBM traffic of the launch (operand streamed once, responsibilities and
     haplotype tables read / written once)."""
     ex = alg = dense = bytes_h = bytes_z = 0.0
+    assert len(ops) == len(stats)
     for o, (running, kt, nlay, _) in zip(ops, stats):
         if not running:
             continue
@@ -354,7 +355,8 @@ def run_b200_arm(args):
 
     # per-kernel roofline numbers: a separate pass with every launch bracketed by CUDA events
     ops = operand_stats(windows)
-    prof_tot, prof_first = profiled_run(batch, ops)
+    ops_per_problem = [o for o, w in zip(ops, windows) for _ in range(w.n_starts)]     # problem = (window, restart)
+    prof_tot, prof_first = profiled_run(batch, ops_per_problem)
     n_updates = [o.restarts[o.best_restart].n_updates for o in outcomes]
     all_updates = [r.n_updates for o in outcomes for r in o.restarts]
     read_iters = sum(r.n_updates * w.n_reads for o, w in zip(outcomes, windows) for r in o.restarts)
@@ -448,7 +450,7 @@ def run_b200_arm(args):
             "config": {"workload": args.workload, "mode": spec.mode, "genome_length": spec.genome_length,
                        "window_length": spec.window_length, "windows_per_gpu": len(windows), "coverage": spec.coverage,
                        "n_unique_mean": float(np.mean([w.n_reads for w in windows])), "n_clusters": spec.n_clusters,
-                       "n_starts": spec.n_starts, "haplotypes": spec.n_haplotypes, "parallelism": f"windows x{world}", "per_gpu_work": "the same 145-window genome on every GPU (seed 0)",
+                       "n_starts": spec.n_starts, "haplotypes": spec.n_haplotypes, "parallelism": f"windows x{world}", "per_gpu_work": f"the same {n_windows}-window genome on every GPU (seed 0)",
                        "dense_columns_mean": float(np.mean([o["NC"] for o in ops])),
                        "sparse_entries_mean": float(np.mean([o["nnz"] for o in ops])),
                        "l2": "inputs larger than L2 (working set %.0f MB per GPU, re-uploaded every step)" % (batch.workspace_bytes / 1e6)},

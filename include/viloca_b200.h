@@ -126,9 +126,12 @@ int vl_batch_workspace_bytes(const vl_window_desc* windows, int32_t n_windows, s
  * every position and every other pair that at least max(2, min(64, N/128)) reads carry become
  * dense operand columns (all columns of a position inside one 16-column tile; positions are
  * placed first-fit in ascending order), the remaining entries go to sparse lists.  n_cols_out: dense columns including tile padding; n_sparse_out:
- * sparse entries; col_lb (optional, capacity 5 * length + 16 rounded up to 16): l * 5 + b per
+ * sparse entries; col_lb (optional, capacity vl_window_plan_capacity(length)): l * 5 + b per
  * dense column, -1 for padding.  Only mode, n_reads, length and codes of the desc are read.
  */
+/* Upper bound of n_cols_out for a window of `length` positions: every tile but the last keeps at
+ * least 12 of its 16 columns in use (a position has at most 5), so 16 * (ceil(5 * length / 12) + 1). */
+int32_t vl_window_plan_capacity(int32_t length);
 int vl_window_plan(const vl_window_desc* window, int32_t* n_cols_out, int64_t* n_sparse_out,
                    int32_t* col_lb);
 

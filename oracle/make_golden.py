@@ -18,6 +18,11 @@ Fixtures:
                                   compute_reads_log_error_proba / load_reference_seq outputs
   data4/                          the reference's own fixture window tests/data_4 run through
                                   run_dpm_mfa.main (support.fas, cor.fas, ELBO history)
+  snv_windows.json                window-level SNV tables and co-occurring-mutation rows of the
+                                  reference's shorah_snv.parseWindow / get_cooccuring_muts_haplo_df
+                                  on the expected support files above, plus random reference /
+                                  haplotype pairs (deletions, inserted 'X' columns) through
+                                  _compare_ref_to_read and __mutations_in_haplotype
   bam_windows/                    windows with real bases and qualities cut from the reference's
                                   BAM fixtures tests/data_2,3,6,7 (oracle/bam_windows.py) and the
                                   files run_dpm_mfa.main writes for them
@@ -405,6 +410,83 @@ def golden_bam_windows():
         json.dump(meta, fh, indent=1)
 
 
+def _snv_rows(snp):
+    return [[k.pos, k.var, v.chrom, v.haplotype_id, v.pos, v.ref, v.var, v.freq, v.support] for k, v in sorted(snp.items())]
+
+
+def _cooc_rows(df):
+    rows = []
+    for rec in df.to_dict("records"):
+        rows.append({k: (None if (isinstance(v, float) and v != v) else (v.item() if hasattr(v, "item") else v))
+                     for k, v in rec.items()})
+    return rows
+
+
+def golden_snv():
+    """Post-inference window parsing of the unmodified reference (viloca/shorah_snv.py); libshorah (the
+    C++ strand-bias filter, not used by these functions) is stubbed so that the module imports."""
+    import types
+    sys.modules.setdefault("libshorah", types.ModuleType("libshorah"))
+    from viloca import shorah_snv as ss
+    mutations_in_haplotype = ss.__dict__["__mutations_in_haplotype"]
+    out = {"windows": {}, "pairs": []}
+    fixtures = [("data4", os.path.join(GOLD, "data4", "expected_seed42.reads-support.fas"),
+                 os.path.join(GOLD, "data4", "w-HXB2-2335-2535.ref.fas"), "HXB2", "2335", "2535")]
+    meta = json.load(open(os.path.join(GOLD, "bam_windows", "expected.json")))
+    import bam_windows as bw
+    for name, entry in meta.items():
+        if name == "versions":
+            continue
+        _, chrom, beg, end = entry["stem"].rsplit("-", 3)[0:1] + entry["stem"].split("-", 1)[1].rsplit("-", 2)
+        fixtures.append((name, os.path.join(GOLD, "bam_windows", name, "expected.reads-support.fas"), None, chrom, beg, end))
+    for name, support, ref_file, chrom, beg, end in fixtures:
+        with tempfile.TemporaryDirectory() as tmp:
+            cwd = os.getcwd()
+            os.chdir(tmp)
+            try:
+                os.makedirs("haplotypes"); os.makedirs("raw_reads")
+                stem = f"w-{chrom}-{beg}-{end}"
+                shutil.copy(support, os.path.join("haplotypes", stem + ".reads-support.fas"))
+                if ref_file is None:
+                    _, _, ref_file, _ = bw.materialize(os.path.join(GOLD, "bam_windows", name, "window.npz"), tmp)
+                shutil.copy(ref_file, os.path.join("raw_reads", stem + ".ref.fas"))
+                line = f"{stem}.reads.fas\t{chrom}\t{beg}\t{end}\t100\n"
+                per = {}
+                for thr in (0.9, 0.0):
+                    per[str(thr)] = _snv_rows(ss.parseWindow(line, False, 0, tmp, thr))
+                cooc = ss.get_cooccuring_muts_haplo_df(os.path.join("haplotypes", stem + ".reads-support.fas"),
+                                                       os.path.join("raw_reads", stem + ".ref.fas"), beg, end, chrom)
+                out["windows"][name] = {"chrom": chrom, "beg": beg, "end": end, "snvs": per, "cooccurring": _cooc_rows(cooc)}
+                print("snv golden", name, {k: len(v) for k, v in per.items()}, "cooccurring rows", len(cooc))
+            finally:
+                os.chdir(cwd)
+    rng = default_rng(5)
+    while len(out["pairs"]) < 300:
+        n = int(rng.integers(4, 24))
+        ref = "".join(rng.choice(list("ACGT-X"), size=n, p=[0.22, 0.22, 0.22, 0.22, 0.04, 0.08]))
+        seq = []
+        for r in ref:
+            u = rng.random()
+            if r == "X":
+                seq.append(str(rng.choice(list("ACGTX-"), p=[0.1, 0.1, 0.1, 0.1, 0.5, 0.1])))
+            else:
+                seq.append(r if u < 0.7 else str(rng.choice(list("ACGT-"), p=[0.2, 0.2, 0.2, 0.2, 0.2])))
+        seq = "".join(seq)
+        start = int(rng.integers(1, 500))
+        try:
+            snp = {}
+            pre = ss._preprocess_seq_with_X(ref, seq)
+            tot = ss._compare_ref_to_read(ref, pre, start, snp, 3.0, 0.95, "chr", "hid")
+            tot2 = ss._compare_ref_to_read(ref, pre, start, snp, 2.0, 0.5, "chr", "other")     # aggregation path
+            cooc = mutations_in_haplotype(ref, seq, start, 3.0, 0.95, "chr", "hid")
+        except (IndexError, AssertionError):
+            continue
+        out["pairs"].append({"ref": ref, "seq": seq, "preprocessed": pre, "start": start, "tot": [tot, tot2],
+                             "snvs": _snv_rows(snp), "cooccurring": cooc})
+    with open(os.path.join(GOLD, "snv_windows.json"), "w") as fh:
+        json.dump(out, fh, separators=(",", ":"))
+
+
 if __name__ == "__main__":
     if not os.path.isdir(REF):
         sys.exit(f"{REF} not found: goldens can only be regenerated where the reference is mounted")
@@ -417,4 +499,5 @@ if __name__ == "__main__":
     golden_prep()
     golden_data4()
     golden_bam_windows()
+    golden_snv()
     print("wrote", GOLD)

@@ -110,7 +110,7 @@ def _plan_numpy(codes):
 
 
 @pytest.mark.parametrize("n,length,p_err", [(300, 201, 0.01), (40, 16, 0.2), (1000, 57, 0.05), (5, 1, 0.5),
-                                            (700, 33, 0.6)])
+                                            (700, 33, 0.6), (600, 100, 0.8)])
 def test_window_plan_matches_documented_rule(n, length, p_err):
     rng = np.random.default_rng(n + length)
     codes = np.tile(rng.integers(0, 4, size=length).astype(np.uint8), (n, 1))
@@ -121,7 +121,8 @@ def test_window_plan_matches_documented_rule(n, length, p_err):
         codes[:, 2] = 255                         # a position no read covers still gets its column
     d = _desc(n=n, l=length, codes=np.ascontiguousarray(codes))
     ncols, nsp = C.c_int32(0), C.c_int64(0)
-    cap = (5 * length + 31) // 16 * 16
+    cap = capi.lib.vl_window_plan_capacity(length)
+    assert cap == 16 * (-(-5 * length // 12) + 1)
     col_lb = np.full(cap, -7, dtype=np.int32)
     assert capi.lib.vl_window_plan(C.byref(d), C.byref(ncols), C.byref(nsp), capi.i32_ptr(col_lb)) == 0
     exp_cols, exp_sparse = _plan_numpy(codes)

@@ -214,6 +214,37 @@ def test_bam_fixture_windows_end_to_end(golden_dir, tmp_path, name):
     assert open(out_dir + stem + ".reads-cor.fas").read() == open(os.path.join(d, "expected.reads-cor.fas")).read()
 
 
+def test_batched_hook_snv_tables_match_reference(golden_dir, tmp_path, monkeypatch):
+    """All fixture windows as one batch through the shotgun hook (shotgun.py:524-538 replacement); the
+    SNV tables and co-occurring-mutation rows built from the in-memory results equal what the
+    reference's shorah_snv.parseWindow / get_cooccuring_muts_haplo_df give on the reference's files."""
+    from oracle import bam_windows
+    from viloca_b200 import shotgun_hook
+    meta = json.load(open(os.path.join(golden_dir, "bam_windows", "expected.json")))
+    gold = json.load(open(os.path.join(golden_dir, "snv_windows.json")))["windows"]
+    monkeypatch.chdir(tmp_path)
+    runlist = []
+    for name in BAM_WINDOWS:
+        m = meta[name]
+        stem, f_reads, _, _ = bam_windows.materialize(os.path.join(golden_dir, "bam_windows", name, "window.npz"), str(tmp_path))
+        runlist.append((f_reads, 0, 0.0001, np.array([m["seed"]]), "use_quality_scores", m["K"], m["n_starts"], True, 1e-3, False))
+    jobs, finished = shotgun_hook.run_dpm_batch(runlist, devices=[0], collect=True)
+    tables = shotgun_hook.snv_tables(jobs, finished, threshold=0.9)
+    for name, tab in zip(BAM_WINDOWS, tables):
+        g = gold[name]
+        assert tab["window"] == (g["chrom"], g["beg"], g["end"])
+        got = [[k.pos, k.var, v.chrom, v.haplotype_id, v.pos, v.ref, v.var, v.freq, v.support] for k, v in sorted(tab["snvs"].items())]
+        assert [r[:8] for r in got] == [r[:8] for r in g["snvs"]["0.9"]]          # identical SNV calls and frequencies
+        for a, e in zip(got, g["snvs"]["0.9"]):
+            assert abs(a[8] - e[8]) <= ENG_TOL * abs(e[8])
+        exp = [{k: v for k, v in r.items() if v is not None} for r in g["cooccurring"]]
+        assert len(tab["cooccurring"]) == len(exp)
+        for a, e in zip(tab["cooccurring"], exp):
+            assert {k: v for k, v in a.items() if k != "support"} == {k: v for k, v in e.items() if k != "support"}
+            assert abs(a["support"] - e["support"]) <= ENG_TOL * abs(e["support"]) + 1e-300
+        assert os.path.exists(meta[name]["stem"] + ".reads-support.fas")
+
+
 @pytest.mark.parametrize("name", [n for n in BAM_WINDOWS if "starts" not in n])
 def test_bam_fixture_windows_trajectory(golden_dir, tmp_path, name):
     """Same windows at the numeric seam: iteration count, exit message and the whole ELBO

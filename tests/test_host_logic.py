@@ -1,5 +1,6 @@
 """Host-side logic that needs no GPU: preparation (against vectors from the reference's
 preparation.py), FASTA conventions, the longest-first scheduler, synthetic generators."""
+import json
 import os
 
 import numpy as np
@@ -142,3 +143,71 @@ def test_runlist_unpacking_matches_shotgun_run_dpm():
     assert jobs[1].mode == "lep" and jobs[1].fname_qualities is None and jobs[1].K == 50 and not jobs[1].unique_modus
     with pytest.raises(ValueError):
         shotgun_hook.jobs_from_runlist([("x.reads.fas", 1, 0.1, 1, "shorah", 10, 1, True, 1e-3, False)])
+
+
+# ---------------------------------------------------------------------------------------
+# window-level SNV extraction
+# ---------------------------------------------------------------------------------------
+
+# the reference's own vectors, tests/test_shorah_snv.py:5-38 (start = 1, ave_reads 1, posterior 0.1)
+REFERENCE_SNV_VECTORS = [
+    ("AACTTA", "AGA--A", {(2, "G"): (2, "A", "G"), (3, "A"): (3, "C", "A"), (4, "--"): (3, "CTT", "A")}),
+    ("AA--G", "A---T", {(2, "---"): (1, "AA--", "A"), (5, "T"): (5, "G", "T")}),
+    ("AA--X-GC", "AA--X-TC", {(7, "T"): (6, "G", "T")}),
+    ("AA-X-GCXGG", "AA-G-TCX-G", {(4, "G"): (3, "-", "-G"), (6, "T"): (5, "G", "T"), (9, "-"): (6, "CG", "C")}),
+    ("AXXG", "AGGG", {(2, "GG"): (1, "A", "AGG")}),
+    ("ACXXXXGT", "ACXGGCCT", {(4, "GGC"): (2, "C", "CGGC"), (7, "C"): (3, "G", "C")}),
+    ("ACXGT", "ACCGT", {(3, "C"): (2, "C", "CC")}),
+]
+
+
+@pytest.mark.parametrize("ref,seq,spec", REFERENCE_SNV_VECTORS)
+def test_compare_ref_to_read_reference_vectors(ref, seq, spec):
+    from viloca_b200 import snv_windows as sw
+    snp = {}
+    tot = sw.compare_ref_to_read(ref, seq, 1, snp, 1, 0.1, "HXB2", "some-id")
+    expected = {sw.SNP_id(pos=k[0], var=k[1]): sw.SNV("HXB2", "some-id", v[0], v[1], v[2], 1, 0.1) for k, v in spec.items()}
+    assert snp == expected and tot == len(snp)
+
+
+def _snv_rows(snp):
+    return [[k.pos, k.var, v.chrom, v.haplotype_id, v.pos, v.ref, v.var, v.freq, v.support] for k, v in sorted(snp.items())]
+
+
+def test_snv_random_pairs_match_reference_functions(golden_dir):
+    """300 random reference / haplotype pairs with deletions and inserted 'X' columns, expected tables
+    from the unmodified _compare_ref_to_read / __mutations_in_haplotype (oracle/make_golden.py)."""
+    from viloca_b200 import snv_windows as sw
+    pairs = json.load(open(os.path.join(golden_dir, "snv_windows.json")))["pairs"]
+    assert len(pairs) == 300
+    for c in pairs:
+        pre = sw.mark_inserted_gaps(c["ref"], c["seq"])
+        assert pre == c["preprocessed"]
+        snp = {}
+        tot = [sw.compare_ref_to_read(c["ref"], pre, c["start"], snp, 3.0, 0.95, "chr", "hid"),
+               sw.compare_ref_to_read(c["ref"], pre, c["start"], snp, 2.0, 0.5, "chr", "other")]
+        assert tot == c["tot"] and _snv_rows(snp) == c["snvs"]
+        rows = sw.cooccurring_mutations([sw.Haplotype("hid", c["seq"], 0.95, 3.0)], c["ref"], "chr", c["start"], 0)
+        got = [{k: v for k, v in r.items() if k != "coverage"} for r in rows if "position" in r]
+        exp = [dict(r, haplotype_id="hid-%d-0" % c["start"]) for r in c["cooccurring"]]
+        assert got == exp
+
+
+@pytest.mark.parametrize("name", ["data4", "hiv_3120", "hiv_2500_3starts", "sars_24520", "amplicon_90", "longreads_2900"])
+def test_window_snvs_match_reference_on_fixture_windows(golden_dir, name):
+    """parseWindow / get_cooccuring_muts_haplo_df of the reference on the expected support files of the
+    fixture windows, against the in-memory functions fed with the same haplotypes."""
+    from viloca_b200 import fasta, snv_windows as sw
+    g = json.load(open(os.path.join(golden_dir, "snv_windows.json")))["windows"][name]
+    if name == "data4":
+        support = os.path.join(golden_dir, "data4", "expected_seed42.reads-support.fas")
+        ref_seq = next(iter(fasta.parse(os.path.join(golden_dir, "data4", "w-HXB2-2335-2535.ref.fas")))).seq
+    else:
+        support = os.path.join(golden_dir, "bam_windows", name, "expected.reads-support.fas")
+        ref_seq = str(np.load(os.path.join(golden_dir, "bam_windows", name, "window.npz"))["ref_seq"])
+    haps = sw.read_support_file(support)
+    for thr, rows in g["snvs"].items():
+        assert _snv_rows(sw.window_snvs(haps, ref_seq, g["chrom"], g["beg"], g["end"], float(thr))) == rows
+    got = sw.cooccurring_mutations(haps, ref_seq, g["chrom"], g["beg"], g["end"])
+    exp = [{k: v for k, v in r.items() if v is not None} for r in g["cooccurring"]]
+    assert got == exp

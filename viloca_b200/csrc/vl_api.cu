@@ -464,6 +464,10 @@ int vl_batch_workspace_bytes(const vl_window_desc* windows, int32_t n_windows, s
   return 0;
 }
 
+int32_t vl_window_plan_capacity(int32_t length) {
+  return length <= 0 ? 0 : VL_PT * ((5 * length + 11) / 12 + 1);
+}
+
 int vl_window_plan(const vl_window_desc* w, int32_t* n_cols_out, int64_t* n_sparse_out, int32_t* col_lb) {
   if (!w || !w->codes) return fail("window or its codes is NULL");
   if (w->n_reads <= 0 || w->length <= 0) return fail("n_reads and length must be positive");
@@ -705,8 +709,11 @@ int vl_batch_run(vl_batch* b, int64_t* n_launches_out) {
     done_iters += chunk;
     if (trace) {
       const double us = std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t0).count();
-      fprintf(stderr, "chunk %3d: %3d updates, running %d -> %d, %.0f us (%.1f us/update)\n", n_chunks, chunk, before, running,
-              us, us / chunk);
+      int kt_min = 1 << 30, kt_max = 0;
+      for (const int4& st : b->pstat)
+        if (st.x) { kt_min = std::min(kt_min, st.y); kt_max = std::max(kt_max, st.y); }
+      fprintf(stderr, "chunk %3d: %3d updates, running %d -> %d, %.0f us (%.1f us/update), cluster tiles of the running %d..%d\n",
+              n_chunks, chunk, before, running, us, us / chunk, running ? kt_min : 0, kt_max);
     }
   }
   VL_CUDA(cudaEventRecord(b->ev1, b->stream));

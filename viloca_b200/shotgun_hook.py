@@ -5,6 +5,11 @@
 conv_thres, record_history)``.  All windows are loaded, sharded over the visible GPUs by the
 longest-first scheduler and run as one engine batch per GPU (one host thread per GPU; the C ABI
 releases the GIL).  Outputs are the per-window files the serial path writes into the CWD.
+
+``run_dpm_batch(..., collect=True)`` also returns the finished state dicts, and ``snv_tables`` turns
+them into the per-window SNV tables and co-occurring-mutation rows that ``shorah_snv.getSNV`` /
+``get_cooccuring_muts_haplo_df`` (viloca/shorah_snv.py:190-256, 486-526) would otherwise re-parse
+from the support files.
 """
 from __future__ import annotations
 
@@ -37,22 +42,45 @@ def jobs_from_runlist(runlist) -> list:
     return jobs
 
 
-def run_dpm_batch(runlist, devices: Optional[Sequence[int]] = None) -> None:
+def window_coordinates(job) -> tuple:
+    """(chrom, beg, end) from the window file name ``w-<chrom>-<beg>-<end>.reads.fas`` (b2w.py:604-616)."""
+    stem = job.freads_in.split("/")[-1].split(".reads.")[0]
+    chrom, beg, end = stem[2:].rsplit("-", 2)
+    return chrom, beg, end
+
+
+def snv_tables(jobs, finished, threshold: float = 0.9) -> list:
+    """Per window: {"window": (chrom, beg, end), "snvs": {SNP_id: SNV}, "cooccurring": [rows]} from the
+    in-memory results of :func:`run_dpm_batch` (``collect=True``)."""
+    from . import snv_windows as sw
+    out = []
+    for job, (state, _result) in zip(jobs, finished):
+        chrom, beg, end = window_coordinates(job)
+        haps = sw.haplotypes_from_state(state)
+        out.append({"window": (chrom, beg, end),
+                    "snvs": sw.window_snvs(haps, job.ref_seq, chrom, beg, end, threshold),
+                    "cooccurring": sw.cooccurring_mutations(haps, job.ref_seq, chrom, beg, end)})
+    return out
+
+
+def run_dpm_batch(runlist, devices: Optional[Sequence[int]] = None, collect: bool = False):
     import torch
     jobs = [j.load() for j in jobs_from_runlist(runlist)]
     if not jobs:
-        return
+        return ([], []) if collect else None
     if devices is None:
         devices = list(range(torch.cuda.device_count()))
     if not devices:
         raise RuntimeError("no CUDA device: the CAVI engine has no CPU fallback")
     parts = scheduler.lpt_partition([j.window.cost() for j in jobs], len(devices))
     errors = []
+    finished = [None] * len(jobs)
 
     def work(dev, idx):
         try:
             if idx:
-                _common.run_jobs([jobs[i] for i in idx], device=dev)
+                for i, fin in zip(idx, _common.run_jobs([jobs[i] for i in idx], device=dev)):
+                    finished[i] = fin
         except Exception as exc:                                 # shotgun.py:137-143: log and re-raise
             logging.error(f"Error in process for device {dev}: {exc}")
             errors.append(exc)
@@ -64,3 +92,4 @@ def run_dpm_batch(runlist, devices: Optional[Sequence[int]] = None) -> None:
         t.join()
     if errors:
         raise errors[0]
+    return (jobs, finished) if collect else None

@@ -231,6 +231,15 @@ int vl_batch_problem_stats(vl_batch* batch, int32_t* out, int32_t n_problems);
 int vl_debug_exp(int32_t device, const double* x, double* out, int32_t n);
 
 /*
+ * Development aid: residency of the fused chunk kernel on `device` as the CUDA occupancy calculator
+ * reports it: CTAs per SM, shared memory per CTA (static + dynamic) and registers per thread, for
+ * kernel class 0..3 (layouts of <= 2 / 4 / 8 / 16 cluster tiles), mode VL_MODE_*, and the deep
+ * pipeline (deep != 0) the launcher uses when a chunk has few tiles per update.
+ */
+int vl_debug_occupancy(int32_t device, int32_t kernel_class, int32_t mode, int32_t deep, int32_t* ctas_per_sm,
+                       int32_t* smem_bytes, int32_t* registers);
+
+/*
  * Development aid: per-phase cycle counters, 36 values: [0..15] one CTA of the resident kernel,
  * [16..35] tile 0 of restart 0 in the general-path kernels (slot meanings in vl_resident.cu /
  * vl_kernels.cu).  Fails unless the library was built with -DVL_RS_PROFILE

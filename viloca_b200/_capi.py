@@ -63,7 +63,7 @@ EXPORTS = (
     "vl_batch_create", "vl_batch_destroy", "vl_batch_upload", "vl_batch_run", "vl_batch_step",
     "vl_batch_fetch", "vl_batch_set_state", "vl_batch_merge_haplo", "vl_batch_profile_step",
     "vl_batch_last_device_ms", "vl_batch_set_option", "vl_batch_problem_stats",
-    "vl_window_plan", "vl_window_plan_capacity", "vl_debug_counters", "vl_debug_exp",
+    "vl_window_plan", "vl_window_plan_capacity", "vl_debug_counters", "vl_debug_exp", "vl_debug_occupancy",
 )
 
 
@@ -100,6 +100,7 @@ def _load():
     lib.vl_window_plan_capacity.argtypes = [C.c_int32]
     lib.vl_window_plan_capacity.restype = C.c_int32
     lib.vl_window_plan.argtypes = [C.POINTER(WindowDesc), _i32p, C.POINTER(C.c_int64), _i32p]
+    lib.vl_debug_occupancy.argtypes = [C.c_int32] * 4 + [_i32p] * 3
     lib.vl_debug_exp.argtypes = [C.c_int32, _f64p, _f64p, C.c_int32]
     lib.vl_debug_counters.argtypes = [C.POINTER(C.c_uint64), C.c_int32]
     lib.vl_batch_set_option.argtypes = [C.c_void_p, C.c_int32, C.c_int32]

@@ -959,6 +959,17 @@ int vl_batch_merge_haplo(vl_batch* b, int32_t window, int32_t restart, const int
   return 0;
 }
 
+int vl_debug_occupancy(int32_t device, int32_t kernel_class, int32_t mode, int32_t deep, int32_t* ctas_per_sm,
+                       int32_t* smem_bytes, int32_t* registers) {
+  if (!ctas_per_sm || !smem_bytes || !registers) return fail("NULL output");
+  if (kernel_class < 0 || kernel_class >= VL_N_CLASSES) return fail("kernel_class out of range");
+  VL_CUDA(cudaSetDevice(device));
+  int c = 0, sm = 0, r = 0;
+  VL_CUDA(vl_chunk_occupancy(kernel_class, mode, deep, &c, &sm, &r));
+  *ctas_per_sm = c; *smem_bytes = sm; *registers = r;
+  return 0;
+}
+
 int vl_debug_exp(int32_t device, const double* x, double* out, int32_t n) {
   if (!x || !out || n <= 0) return fail("bad argument");
   VL_CUDA(cudaSetDevice(device));

@@ -49,6 +49,15 @@ __device__ unsigned long long vl_gk_cycles[20];
 // CTAs per SM each kernel class is compiled for (bounds the registers per thread): the work of a
 // narrow layout is latency bound, so residency matters more than registers there
 constexpr int vl_min_ctas(int ktm) { return ktm <= 2 ? 6 : (ktm <= 4 ? 5 : (ktm <= 8 ? 3 : 2)); }
+// operand stages of the haplotype tile: the widest class double-buffers so that two CTAs fit one SM
+// (three stages of 32 reads x 132 doubles would leave room for one: tools/occupancy.py)
+__host__ __device__ constexpr int vl_hstages(int ktm) { return ktm > 8 ? 2 : VL_STAGES; }
+// doubles of dynamic shared memory a haplotype tile needs: its operand stages, or the post-loop tables
+// T [16][K8] + Cm [16][5][K8] that reuse them, whichever is larger
+__host__ __device__ constexpr int vl_haplo_doubles(int ktm) {
+  const int stages = vl_hstages(ktm) * (VL_H_NC * VL_PT + VL_H_NC * vl_ks(ktm)), tables = VL_PT * 6 * 8 * ktm;
+  return stages > tables ? stages : tables;
+}
 
 namespace {
 
@@ -137,7 +146,8 @@ __device__ __forceinline__ bool vl_haplo_body(const VlProblem* __restrict__ prob
   if (early) asm volatile("fence.proxy.async;\n" ::: "memory");   // bulk copies below read what other CTAs wrote
   // a narrow layout has small stages: use the same shared memory for a deeper pipeline
   const int st_stride = DM_STAGE + VL_H_NC * vl_ks(ktz);
-  const int nstg = min(VL_MAX_STAGES, max(stage_doubles, VL_STAGES * ST_STRIDE) / st_stride);
+  constexpr int OWN_DOUBLES = vl_haplo_doubles(KTM);
+  const int nstg = min(VL_MAX_STAGES, max(stage_doubles, OWN_DOUBLES) / st_stride);
 
   const int Npad = P.Npad;
   const int KSz = vl_ks(ktz), K8z = 8 * ktz;
@@ -866,7 +876,7 @@ __global__ void vl_exp_test_kernel(const double* __restrict__ x, double* __restr
 
 template <int KTM>
 constexpr size_t smem_haplo() {
-  return (size_t)VL_STAGES * (VL_H_NC * VL_PT + VL_H_NC * vl_ks(KTM)) * sizeof(double);
+  return (size_t)vl_haplo_doubles(KTM) * sizeof(double);
 }
 template <int KTM>
 constexpr size_t smem_cluster() {
@@ -915,6 +925,20 @@ cudaError_t launch_chunk(const VlProblem* probs, const int2* htiles, int n_ht, c
   return cudaGetLastError();
 }
 
+template <int KTM, int MODE>
+cudaError_t chunk_occupancy(int deep, int* ctas_per_sm, int* smem_bytes, int* regs) {
+  size_t smem = std::max(smem_haplo<KTM>(), smem_cluster<KTM>());
+  if (deep) smem = std::max(smem, (size_t)104 * 1024);
+  cudaError_t e = cudaFuncSetAttribute(vl_chunk_kernel<KTM, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(160 * 1024));
+  if (e != cudaSuccess) return e;
+  cudaFuncAttributes at;
+  e = cudaFuncGetAttributes(&at, vl_chunk_kernel<KTM, MODE>);
+  if (e != cudaSuccess) return e;
+  *regs = at.numRegs;
+  *smem_bytes = (int)(smem + at.sharedSizeBytes);
+  return cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas_per_sm, vl_chunk_kernel<KTM, MODE>, VL_THREADS, smem);
+}
+
 }  // namespace
 
 int vl_class_of_tiles(int kt) { return kt <= 2 ? 0 : (kt <= 4 ? 1 : (kt <= 8 ? 2 : 3)); }
@@ -932,6 +956,10 @@ int vl_class_capacity(int cls) { return 2 << cls; }
     case 7: return FN<16, VL_MODE_LEP>(__VA_ARGS__);                                     \
     default: return cudaErrorInvalidValue;                                               \
   }
+
+cudaError_t vl_chunk_occupancy(int cls, int mode, int deep, int* ctas_per_sm, int* smem_bytes, int* regs) {
+  VL_DISPATCH(chunk_occupancy, deep, ctas_per_sm, smem_bytes, regs)
+}
 
 cudaError_t vl_launch_haplo(int cls, int mode, const VlProblem* probs, const int2* tiles, int n_tiles,
                             cudaStream_t stream) {

@@ -42,3 +42,4 @@ cudaError_t vl_launch_scale_rows(const double* z, const double* w, double* wz, i
 cudaError_t vl_launch_exp_test(const double* x, double* out, int n, cudaStream_t stream);
 // per-phase cycle counters of restart 0 in the general-path kernels (see vl_kernels.cu); 2 unless -DVL_RS_PROFILE
 int vl_debug_general_cycles(unsigned long long* out20, int reset);
+cudaError_t vl_chunk_occupancy(int cls, int mode, int deep, int* ctas_per_sm, int* smem_bytes, int* regs);

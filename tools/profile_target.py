@@ -11,11 +11,17 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--workload", default="hiv5k_uqs")
 ap.add_argument("--windows", type=int, default=145)
 ap.add_argument("--updates", type=int, default=6)
+ap.add_argument("--reads", type=int, default=None, help="raw reads per window (default: the workload's coverage)")
+ap.add_argument("--run", action="store_true", help="vl_batch_run (fused chunk kernel) capped at --updates iterations")
 args = ap.parse_args()
 spec = synthetic.WORKLOADS[args.workload]
-wins = [synthetic.make_window(spec, i) for i in range(args.windows)]
+wins = [synthetic.make_window(spec, i, n_reads=args.reads, max_iter=args.updates if args.run else 50000)
+        for i in range(args.windows)]
 with engine.CaviBatch(wins) as b:
     b.upload()
-    b.step(args.updates)
+    if args.run:
+        b.run()
+    else:
+        b.step(args.updates)
     out = b.fetch(state="none")
 print("ok", len(wins), "windows", sum(o.restarts[0].n_updates for o in out), "updates")

@@ -48,10 +48,17 @@ __device__ unsigned long long vl_gk_cycles[20];
 
 // CTAs per SM each kernel class is compiled for (bounds the registers per thread): the work of a
 // narrow layout is latency bound, so residency matters more than registers there
-constexpr int vl_min_ctas(int ktm) { return ktm <= 2 ? 6 : (ktm <= 4 ? 5 : (ktm <= 8 ? 3 : 2)); }
+#ifndef VL_C0_CTAS
+#define VL_C0_CTAS 6       // resident CTAs per SM the narrowest class is compiled for
+#endif
+#ifndef VL_C0_STAGES
+#define VL_C0_STAGES 3     // its operand stages
+#endif
+constexpr int vl_min_ctas(int ktm) { return ktm <= 2 ? VL_C0_CTAS : (ktm <= 4 ? 5 : (ktm <= 8 ? 3 : 2)); }
+__host__ __device__ constexpr int vl_zstages(int ktm) { return ktm <= 2 ? VL_C0_STAGES : VL_ZSTAGES; }
 // operand stages of the haplotype tile: the widest class double-buffers so that two CTAs fit one SM
 // (three stages of 32 reads x 132 doubles would leave room for one: tools/occupancy.py)
-__host__ __device__ constexpr int vl_hstages(int ktm) { return ktm > 8 ? 2 : VL_STAGES; }
+__host__ __device__ constexpr int vl_hstages(int ktm) { return ktm > 8 ? 2 : (ktm <= 2 ? VL_C0_STAGES : VL_STAGES); }
 // doubles of dynamic shared memory a haplotype tile needs: its operand stages, or the post-loop tables
 // T [16][K8] + Cm [16][5][K8] that reuse them, whichever is larger
 __host__ __device__ constexpr int vl_haplo_doubles(int ktm) {
@@ -387,7 +394,7 @@ __device__ __forceinline__ void vl_cluster_body(const VlProblem* __restrict__ pr
   constexpr int ST_STRIDE = DM_STAGE + VL_PT * KSM;    // dm | gm
   extern __shared__ __align__(128) unsigned char vl_smem[];
   double* stg = reinterpret_cast<double*>(vl_smem);
-  double* red_cs = stg + max(stage_doubles, VL_ZSTAGES * ST_STRIDE);   // [4][K8M], after the stages
+  double* red_cs = stg + max(stage_doubles, vl_zstages(KTM) * ST_STRIDE);   // [4][K8M], after the stages
   __shared__ uint64_t bars[VL_MAX_STAGES];
   __shared__ double red_sc[VL_THREADS / 32][4];
 
@@ -414,7 +421,7 @@ __device__ __forceinline__ void vl_cluster_body(const VlProblem* __restrict__ pr
   const uint32_t stage_bytes = (uint32_t)(DM_STAGE * sizeof(double)) + gm_bytes;
   // narrow layouts: deeper pipeline in the same shared memory (see vl_haplo_kernel)
   const int st_stride = DM_STAGE + VL_PT * KS;
-  const int nstg = min(VL_MAX_STAGES, max(stage_doubles, VL_ZSTAGES * ST_STRIDE) / st_stride);
+  const int nstg = min(VL_MAX_STAGES, max(stage_doubles, vl_zstages(KTM) * ST_STRIDE) / st_stride);
 
   if (tid == 0) {
     for (int s = 0; s < nstg; ++s) vl_mbar_init(&bars[s], 1);
@@ -880,7 +887,7 @@ constexpr size_t smem_haplo() {
 }
 template <int KTM>
 constexpr size_t smem_cluster() {
-  return ((size_t)VL_ZSTAGES * (VL_ZT_READS * VL_PT + VL_PT * vl_ks(KTM)) + (VL_THREADS / 32) * 8 * KTM) * sizeof(double);
+  return ((size_t)vl_zstages(KTM) * (VL_ZT_READS * VL_PT + VL_PT * vl_ks(KTM)) + (VL_THREADS / 32) * 8 * KTM) * sizeof(double);
 }
 
 template <int KTM, int MODE>

@@ -594,7 +594,16 @@ int vl_batch_upload(vl_batch* b, const vl_window_desc* windows, int32_t n_window
   if (n_windows != (int)L.wins.size()) return fail("n_windows differs from the batch");
   VL_CUDA(cudaSetDevice(b->device));
   cudaStream_t s = b->stream;
+  static const bool trace = std::getenv("VL_TRACE") != nullptr;
+  const auto t_begin = std::chrono::steady_clock::now();
+  auto lap = [&](const char* what) {
+    if (!trace) return;
+    cudaStreamSynchronize(s);
+    fprintf(stderr, "upload: %-28s at %.2f ms\n", what,
+            std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_begin).count());
+  };
   VL_CUDA(cudaMemsetAsync(b->ws + L.data_begin, 0, L.data_end - L.data_begin, s));
+  lap("workspace cleared");
   for (int i = 0; i < n_windows; ++i) {
     const vl_window_desc& d = windows[i];
     const WindowLayout& W = L.wins[i];
@@ -639,6 +648,7 @@ int vl_batch_upload(vl_batch* b, const vl_window_desc* windows, int32_t n_window
     work(0);
     for (auto& th : pool) th.join();
   }
+  lap("host analysis");
   for (int i = 0; i < n_windows; ++i)
     if (bad[i]) {
       char buf[200];
@@ -676,6 +686,7 @@ int vl_batch_upload(vl_batch* b, const vl_window_desc* windows, int32_t n_window
       S.skip = b->skip_dead;
     }
   }
+  lap("copies + operand kernels");
   VL_CUDA(cudaMemcpyAsync(b->d_states(), b->states.data(), b->states.size() * sizeof(VlState), cudaMemcpyHostToDevice, s));
   VL_CUDA(cudaMemsetAsync(b->d_done(), 0, 64, s));
   VL_CUDA(vl_launch_init(b->d_probs(), L.n_problems, b->d_pstat(), s));

@@ -673,9 +673,12 @@ int vl_batch_upload(vl_batch* b, const vl_window_desc* windows, int32_t n_window
                               b->dev<int>(W.col_lb), b->dev<double>(W.dm), b->dev<double>(W.mcount),
                               b->dev<double>(W.ltsum), W.N, W.L, W.Npad, W.NCs, W.mode, s));
     for (int r = 0; r < W.R; ++r) {
-      VL_CUDA(cudaMemcpy2DAsync(b->ws + W.rs[r].z, (size_t)W.KS * 8, d.init_cluster + (size_t)r * W.N * W.K,
-                                (size_t)W.K * 8, (size_t)W.K * 8, W.N, cudaMemcpyHostToDevice, s));
-      VL_CUDA(vl_launch_scale_rows(b->dev<double>(W.rs[r].z), b->dev<double>(W.w), b->dev<double>(W.rs[r].wz), W.Npad, W.KS, s));
+      // one contiguous copy into the staging area (the export buffer, idle during uploads; reuse is
+      // stream-ordered), the row pitch is applied on the device
+      VL_CUDA(cudaMemcpyAsync(b->ws + L.export_z, d.init_cluster + (size_t)r * W.N * W.K, (size_t)W.N * W.K * 8,
+                              cudaMemcpyHostToDevice, s));
+      VL_CUDA(vl_launch_init_rows(b->dev<double>(L.export_z), b->dev<double>(W.w), b->dev<double>(W.rs[r].z),
+                                  b->dev<double>(W.rs[r].wz), W.N, W.K, W.Npad, W.KS, s));
       VlState& S = b->states[W.first_problem + r];
       std::memset(&S, 0, sizeof S);
       const double* in = d.init_scalars + (size_t)r * VL_INIT_STRIDE;

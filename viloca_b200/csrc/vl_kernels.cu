@@ -870,6 +870,17 @@ __global__ void vl_scale_rows_kernel(const double* __restrict__ z, const double*
   wz[i] = w[i / KS] * z[i];
 }
 
+// initial responsibilities as the host holds them ([N][K], contiguous) -> z [Npad][KS] and w z
+__global__ void vl_init_rows_kernel(const double* __restrict__ raw, const double* __restrict__ w, double* __restrict__ z,
+                                    double* __restrict__ wz, int N, int K, int Npad, int KS) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (size_t)Npad * KS) return;
+  const int n = (int)(i / KS), k = (int)(i - (size_t)n * KS);
+  const double v = (n < N && k < K) ? raw[(size_t)n * K + k] : 0.0;
+  z[i] = v;
+  wz[i] = w[n] * v;
+}
+
 // test hook: the softmax exponential on arbitrary non-positive inputs
 __global__ void vl_exp_test_kernel(const double* __restrict__ x, double* __restrict__ out, int n) {
   const int i = 2 * (blockIdx.x * blockDim.x + threadIdx.x);
@@ -1025,6 +1036,13 @@ int vl_debug_general_cycles(unsigned long long* out20, int reset) {
 cudaError_t vl_launch_scale_rows(const double* z, const double* w, double* wz, int Npad, int KS, cudaStream_t stream) {
   const size_t total = (size_t)Npad * KS;
   vl_scale_rows_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(z, w, wz, Npad, KS);
+  return cudaGetLastError();
+}
+
+cudaError_t vl_launch_init_rows(const double* raw, const double* w, double* z, double* wz, int N, int K, int Npad, int KS,
+                                cudaStream_t stream) {
+  const size_t total = (size_t)Npad * KS;
+  vl_init_rows_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(raw, w, z, wz, N, K, Npad, KS);
   return cudaGetLastError();
 }
 

@@ -39,6 +39,8 @@ cudaError_t vl_launch_export_cluster(const VlProblem* prob, double* out, size_t 
 cudaError_t vl_launch_merge(const VlProblem* prob, double* zm, double* wzm, const int* group_of, int G, int KSg,
                             size_t total, cudaStream_t stream);
 cudaError_t vl_launch_scale_rows(const double* z, const double* w, double* wz, int Npad, int KS, cudaStream_t stream);
+cudaError_t vl_launch_init_rows(const double* raw, const double* w, double* z, double* wz, int N, int K, int Npad, int KS,
+                                cudaStream_t stream);
 cudaError_t vl_launch_exp_test(const double* x, double* out, int n, cudaStream_t stream);
 // per-phase cycle counters of restart 0 in the general-path kernels (see vl_kernels.cu); 2 unless -DVL_RS_PROFILE
 int vl_debug_general_cycles(unsigned long long* out20, int reset);

@@ -819,8 +819,15 @@ int vl_batch_fetch(vl_batch* b, vl_window_result* results, int32_t n_windows) {
   if (n_windows != (int)L.wins.size()) return fail("n_windows differs from the batch");
   VL_CUDA(cudaSetDevice(b->device));
   cudaStream_t s = b->stream;
+  static const bool trace = std::getenv("VL_TRACE") != nullptr;
+  const auto t_begin = std::chrono::steady_clock::now();
+  auto lap = [&](const char* what) {
+    if (trace) fprintf(stderr, "fetch: %-28s at %.2f ms\n", what,
+                       std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_begin).count());
+  };
   VL_CUDA(cudaMemcpyAsync(b->states.data(), b->d_states(), b->states.size() * sizeof(VlState), cudaMemcpyDeviceToHost, s));
   VL_CUDA(cudaStreamSynchronize(s));
+  lap("states on the host");
   for (int i = 0; i < n_windows; ++i) {
     const WindowLayout& W = L.wins[i];
     vl_window_result& R = results[i];
@@ -866,7 +873,9 @@ int vl_batch_fetch(vl_batch* b, vl_window_result* results, int32_t n_windows) {
     // the export buffers are reused by the next window: the next export kernel is ordered after
     // these copies on the same stream
   }
+  lap("exports and copies enqueued");
   VL_CUDA(cudaStreamSynchronize(s));
+  lap("copies done");
   return 0;
 }
 

@@ -409,6 +409,30 @@ def test_long_noisy_windows_against_oracle(name, n_raw, L, K, updates):
         assert br.rel_err(out.state["alpha"], traj.state["alpha"]) < ENG_TOL
 
 
+@pytest.mark.parametrize("n_raw,L,K", [(1400, 100, 24), (4200, 64, 12)])
+def test_split_haplotype_tiles_run_to_convergence(n_raw, L, K):
+    """Windows of >= 1024 padded reads share the reads of every haplotype tile among 2..8 CTAs (partial
+    sums added in split order by the last CTA to arrive).  Whole runs against the oracle, alone and in
+    a batch with a small window (bit-identical either way: the split is a property of the window)."""
+    from viloca_b200 import synthetic
+    engine = _engine()
+    spec = dataclasses.replace(synthetic.WORKLOADS["sars_ont"], n_clusters=K, n_starts=1, length_jitter=0)
+    win = synthetic.make_window(spec, 5, n_reads=n_raw, length=L)
+    assert win.n_reads >= 1024
+    small = synthetic.make_window(_spec("uqs", 20, 48), 1, n_reads=200, length=64)
+    traj = br.oracle_run(win)
+    alone = engine.run_windows([win])[0]
+    batch = engine.run_windows([small, win])[1]
+    r = alone.restarts[0]
+    assert (r.n_iterations, r.n_updates, r.exit_message) == (traj.n_iterations, traj.n_updates, traj.exit_message)
+    assert br.rel_err(r.history_elbo, np.array(traj.history_elbo)) < ENG_TOL
+    assert orc.haplotype_strings(alone.state["mean_haplo"]) == orc.haplotype_strings(traj.state["mean_haplo"])
+    assert br.rel_err(alone.state["mean_cluster"], traj.state["mean_cluster"]) < SPEC_TOL
+    assert np.array_equal(alone.restarts[0].history_elbo, batch.restarts[0].history_elbo)
+    assert np.array_equal(alone.state["mean_cluster"], batch.state["mean_cluster"])
+    assert np.array_equal(alone.state["mean_haplo"], batch.state["mean_haplo"])
+
+
 def test_ragged_mixed_batch_equals_single_window_runs():
     """Windows of different N, L, K and mode in one batch give bit-identical results to
     running each alone (problems are independent; the reductions are order-fixed)."""

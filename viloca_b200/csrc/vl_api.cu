@@ -37,12 +37,12 @@ inline size_t align_up(size_t x, size_t a = kAlign) { return (x + a - 1) / a * a
 inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
 
 struct RestartLayout {
-  size_t z, wz, h, g, gm, zpart, hpart, alpha, mlp, mlp_lay, lay, gat, lay_z, hist;
+  size_t z, wz, h, g, gm, zpart, hpart, tsplit, hsplit_count, alpha, mlp, mlp_lay, lay, gat, lay_z, hist;
 };
 
 struct WindowLayout {
   int mode, N, L, K, R, max_iter;
-  int Npad, Ls, KT, KS, K8, n_ztiles, n_htiles;
+  int Npad, Ls, KT, KS, K8, n_ztiles, n_htiles, n_hsplit;
   double alpha0, conv_thres;
   size_t nnz_cap;
   int NCs;
@@ -194,6 +194,9 @@ int build_layout(const vl_window_desc* w, int n, Layout& lay, std::string& err) 
     plan_columns(d, W.Ls, plan);
     W.NCs = plan.NCs;
     W.n_htiles = W.NCs / VL_PT;
+    // Large windows: the reads of a haplotype tile are shared by several CTAs (a property of the
+    // window alone, so the sums a restart computes never depend on the rest of the batch)
+    W.n_hsplit = std::max(1, std::min(VL_MAX_HSPLIT, W.Npad / VL_HSPLIT_READS));
     W.nnz_cap = std::max<size_t>(plan.nnz, 1);
     W.dm = take((size_t)W.Npad * W.NCs * 8);
     W.w = take((size_t)W.Npad * 8);
@@ -223,6 +226,11 @@ int build_layout(const vl_window_desc* w, int n, Layout& lay, std::string& err) 
       RL.gm = take((size_t)W.NCs * W.KS * 8);
       RL.zpart = take((size_t)W.n_ztiles * (W.K8 + VL_ZP_EXTRA) * 8);
       RL.hpart = take((size_t)W.n_htiles * VL_HP_STRIDE * 8);
+      RL.tsplit = RL.hsplit_count = 0;
+      if (W.n_hsplit > 1) {
+        RL.tsplit = take((size_t)W.n_htiles * W.n_hsplit * VL_PT * W.K8 * 8);
+        RL.hsplit_count = take((size_t)W.n_htiles * 4);
+      }
       RL.alpha = take((size_t)W.K8 * 8);
       RL.mlp = take((size_t)W.K8 * 8);
       RL.mlp_lay = take((size_t)W.K8 * 8);
@@ -240,8 +248,8 @@ int build_layout(const vl_window_desc* w, int n, Layout& lay, std::string& err) 
     max_z = std::max(max_z, (size_t)W.Npad * W.KS * 8);
     max_h = std::max(max_h, (size_t)W.Ls * VL_N_BASES * W.KS * 8);
     max_gm = std::max(max_gm, (size_t)W.NCs * W.KS * 8);
-    max_htiles = std::max(max_htiles, W.n_htiles);
-    lay.n_htiles_total += (size_t)W.n_htiles * W.R;
+    max_htiles = std::max(max_htiles, W.n_htiles * W.n_hsplit);
+    lay.n_htiles_total += (size_t)W.n_htiles * W.n_hsplit * W.R;
     lay.n_ztiles_total += (size_t)W.n_ztiles * W.R;
   }
   lay.data_end = off;
@@ -334,7 +342,7 @@ int schedule(vl_batch* b) {
       b->smem_res[m] = std::max(b->smem_res[m], vl_resident_smem_bytes(nct, st.y));
       continue;
     }
-    for (int t = 0; t < P.n_htiles; ++t) ht[cls][m].push_back(make_int2(p, t));
+    for (int t = 0; t < P.n_htiles * P.n_hsplit; ++t) ht[cls][m].push_back(make_int2(p, t));   // split * n_htiles + tile
     for (int t = 0; t < P.n_ztiles; ++t) zt[cls][m].push_back(make_int2(p, t));
     ++b->n_sched;
   }
@@ -519,6 +527,7 @@ int vl_batch_create(vl_batch** out, int32_t device, const vl_window_desc* window
       P.mode = W.mode; P.N = W.N; P.L = W.L; P.K = W.K;
       P.Npad = W.Npad; P.Ls = W.Ls; P.KT = W.KT; P.NCs = W.NCs;
       P.n_ztiles = W.n_ztiles; P.n_htiles = W.n_htiles; P.window = (int)i; P.restart = r;
+      P.n_hsplit = W.n_hsplit; P.pad0_ = 0;
       P.dm = b->dev<double>(W.dm);
       P.w = b->dev<double>(W.w);
       P.ltsum = b->dev<double>(W.ltsum);
@@ -531,6 +540,8 @@ int vl_batch_create(vl_batch** out, int32_t device, const vl_window_desc* window
       P.z = b->dev<double>(RL.z); P.wz = b->dev<double>(RL.wz); P.h = b->dev<double>(RL.h);
       P.g = b->dev<double>(RL.g); P.gm = b->dev<double>(RL.gm);
       P.zpart = b->dev<double>(RL.zpart); P.hpart = b->dev<double>(RL.hpart);
+      P.tsplit = W.n_hsplit > 1 ? b->dev<double>(RL.tsplit) : nullptr;
+      P.hsplit_count = W.n_hsplit > 1 ? b->dev<int>(RL.hsplit_count) : nullptr;
       P.alpha = b->dev<double>(RL.alpha); P.mlp = b->dev<double>(RL.mlp);
       P.mlp_lay = b->dev<double>(RL.mlp_lay);
       P.lay = b->dev<int>(RL.lay); P.gat = b->dev<int>(RL.gat); P.lay_z = b->dev<int>(RL.lay_z);
@@ -947,6 +958,7 @@ int vl_batch_merge_haplo(vl_batch* b, int32_t window, int32_t restart, const int
   // over the G groups, scratch outputs
   VlProblem T = b->probs[p];
   T.K = G; T.KT = KTg;
+  T.n_hsplit = 1; T.tsplit = nullptr; T.hsplit_count = nullptr;      // one CTA per column tile here
   T.z = b->dev<double>(L.tmp_z); T.wz = b->dev<double>(L.tmp_wz);
   T.h = b->dev<double>(L.tmp_h); T.g = b->dev<double>(L.tmp_g); T.gm = b->dev<double>(L.tmp_gm);
   T.hpart = b->dev<double>(L.tmp_hpart);

@@ -115,6 +115,10 @@ __device__ __forceinline__ bool vl_haplo_body(const VlProblem* __restrict__ prob
   GK_DECL(tm.x == 0 && tm.y == 0);
   const VlProblem& P = probs[tm.x];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, q = lane & 3;
+  // Large windows: n_hsplit CTAs share the reads of a column tile (tile id = split * n_htiles + tile);
+  // the last one to arrive adds the partial sums in split order and finishes the tile.
+  const int n_split = P.n_hsplit;
+  const int ty = (n_split > 1) ? tm.y % P.n_htiles : tm.y, split = (n_split > 1) ? tm.y / P.n_htiles : 0;
   // Inside a chunk launch (zticket != nullptr) the operand loop starts as soon as the read tiles
   // of the previous update have written w z -- it needs that update's layout width only
   // (ktring) -- and overlaps the scalar update; the state is read after it has been published.
@@ -125,8 +129,8 @@ __device__ __forceinline__ bool vl_haplo_body(const VlProblem* __restrict__ prob
   __shared__ int s_kt_old;
   const bool early = zticket != nullptr;
   if (tid < VL_PT) {
-    s_tpos[tid] = P.tile_pos[(size_t)tm.y * VL_PT + tid];
-    s_collb[tid] = P.col_lb[(size_t)tm.y * VL_PT + tid];
+    s_tpos[tid] = P.tile_pos[(size_t)ty * VL_PT + tid];
+    s_collb[tid] = P.col_lb[(size_t)ty * VL_PT + tid];
   }
   if (early) {
     if (tid == 0) {
@@ -158,9 +162,13 @@ __device__ __forceinline__ bool vl_haplo_body(const VlProblem* __restrict__ prob
 
   const int Npad = P.Npad;
   const int KSz = vl_ks(ktz), K8z = 8 * ktz;
-  const int nchunks = Npad / VL_H_NC;
-  const double* __restrict__ dmg = P.dm + (size_t)tm.y * Npad * VL_PT;
+  const int nchunks_all = Npad / VL_H_NC;
+  const int per_split = (nchunks_all + n_split - 1) / n_split;
+  const int c_first = min(nchunks_all, split * per_split);            // this CTA's stages of 32 reads
+  const int nchunks = min(nchunks_all, c_first + per_split) - c_first;
+  const double* __restrict__ dmg = P.dm + (size_t)ty * Npad * VL_PT + (size_t)c_first * VL_H_NC * VL_PT;
   const double* wzg = P.wz;     // (mutable state: no __restrict__, these must stay coherent loads)
+  const double* wzs = wzg + (size_t)c_first * VL_H_NC * vl_ks(ktz);   // first read of this CTA's range
   const int* gat = P.gat;
   const uint32_t z_bytes = (uint32_t)(VL_H_NC * KSz * sizeof(double));
   const uint32_t stage_bytes = (uint32_t)(DM_STAGE * sizeof(double)) + z_bytes;
@@ -182,7 +190,7 @@ __device__ __forceinline__ bool vl_haplo_body(const VlProblem* __restrict__ prob
     double* dst = stg + (size_t)sn * st_stride;
     vl_mbar_expect_tx(&bars[sn], stage_bytes);
     vl_tma_load_1d(dst, dmg + (size_t)c * DM_STAGE, DM_STAGE * sizeof(double), &bars[sn]);
-    vl_tma_load_1d(dst + DM_STAGE, wzg + (size_t)c * VL_H_NC * KSz, z_bytes, &bars[sn]);
+    vl_tma_load_1d(dst + DM_STAGE, wzs + (size_t)c * VL_H_NC * KSz, z_bytes, &bars[sn]);
   };
   if (tid == 0)
     for (int c = 0; c < nstg - 1 && c < nchunks; ++c) issue(c);
@@ -225,20 +233,8 @@ __device__ __forceinline__ bool vl_haplo_body(const VlProblem* __restrict__ prob
   // ---- the stage buffers are free now: T [16][K8] and Cm [16][5][K8] live in them; the four
   // warps add their partial sums over the reads into T one after the other (fixed order) ----
   GK_TICK(1);
-  // the state of this update: published by the scalar update of the previous one
-  if (early) {
-    if (!vl_wait_published(P.st, pub_want)) return false;
-    vl_load_state(&sS, P.st, tid);
-    __syncthreads();
-  }
-  const VlState* S = &sS;
-  const int ktl = S->ktl;
-  if (S->active == 0 || ktl > KTM || S->ktl_z != ktz) return false;
-  const int KSn = vl_ks(ktl), K8 = 8 * ktl;
-  const int nlay = S->nlay;
-  // T [16][8 ktz] in the slot order of the stored w z, Cm [16][5][K8] in the current one
+  // T [16][8 ktz] in the slot order of the stored w z
   double* T = stg;
-  double* Cm = stg + VL_PT * K8z;
   for (int turn = 0; turn < VL_THREADS / 32; ++turn) {
     if (warp == turn) {
 #pragma unroll
@@ -254,6 +250,40 @@ __device__ __forceinline__ bool vl_haplo_body(const VlProblem* __restrict__ prob
     }
     if (turn + 1 < VL_THREADS / 32) __syncthreads();
   }
+  if (n_split > 1) {
+    // this CTA's reads are a part of the tile's: park the partial sums; the CTA that arrives last
+    // adds all parts in split order (a fixed order, whoever arrives last) and carries on
+    __shared__ int s_last;
+    const size_t part_stride = (size_t)VL_PT * 8 * P.KT;
+    double* parts = P.tsplit + (size_t)ty * n_split * part_stride;
+    __syncthreads();
+    for (int idx = tid; idx < VL_PT * K8z; idx += VL_THREADS) parts[split * part_stride + idx] = T[idx];
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) s_last = (atomicAdd(&P.hsplit_count[ty], 1) == n_split - 1) ? 1 : 0;
+    __syncthreads();
+    if (!s_last) return false;
+    __threadfence();
+    for (int idx = tid; idx < VL_PT * K8z; idx += VL_THREADS) {
+      double v = parts[idx];
+      for (int s2 = 1; s2 < n_split; ++s2) v += parts[s2 * part_stride + idx];
+      T[idx] = v;
+    }
+    if (tid == 0) P.hsplit_count[ty] = 0;          // the next update's CTAs of this tile come after our signal
+  }
+  // the state of this update: published by the scalar update of the previous one
+  if (early) {
+    if (!vl_wait_published(P.st, pub_want)) return false;
+    vl_load_state(&sS, P.st, tid);
+    __syncthreads();
+  }
+  const VlState* S = &sS;
+  const int ktl = S->ktl;
+  if (S->active == 0 || ktl > KTM || S->ktl_z != ktz) return false;
+  const int KSn = vl_ks(ktl), K8 = 8 * ktl;
+  const int nlay = S->nlay;
+  // Cm [16][5][K8] in the current slot order, behind T
+  double* Cm = stg + VL_PT * K8z;
   GK_TICK(2);
   // sparse entries of the positions whose columns lie in this tile: warp = 4 of them,
   // lanes = slots
@@ -298,7 +328,7 @@ __device__ __forceinline__ bool vl_haplo_body(const VlProblem* __restrict__ prob
   if (MODE == VL_MODE_LEP) cscale = S->mlt0 - (S->mlt1 - VL_LOG4);
   const int ghost = S->ghost;
   const double gmult = S->ghost_mult;
-  double* __restrict__ gmt = P.gm + (size_t)tm.y * VL_PT * KSn;
+  double* __restrict__ gmt = P.gm + (size_t)ty * VL_PT * KSn;
   double s_ref = 0.0, s_nref = 0.0, s_ent = 0.0;
   for (int idx = tid; idx < VL_PT * K8; idx += VL_THREADS) {
     const int pos = idx / K8, slot = idx - pos * K8;
@@ -312,7 +342,7 @@ __device__ __forceinline__ bool vl_haplo_body(const VlProblem* __restrict__ prob
 #pragma unroll
     for (int b = 0; b < VL_B; ++b) {
       const int j = s_poscol[pos][b];
-      lc[b] = (j < 0) ? -1 : j - tm.y * VL_PT;
+      lc[b] = (j < 0) ? -1 : j - ty * VL_PT;
     }
     if (slot < nlay) {
       const int zslot = gat[slot];                         // column of the stored w z this slot continues
@@ -365,7 +395,7 @@ __device__ __forceinline__ bool vl_haplo_body(const VlProblem* __restrict__ prob
     double v = 0.0;
 #pragma unroll
     for (int wI = 0; wI < VL_THREADS / 32; ++wI) v += red[wI][tid];
-    P.hpart[(size_t)tm.y * VL_HP_STRIDE + tid] = v;
+    P.hpart[(size_t)ty * VL_HP_STRIDE + tid] = v;
   }
   GK_TICK(5);
 #ifdef VL_RS_PROFILE

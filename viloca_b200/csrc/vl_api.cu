@@ -304,8 +304,9 @@ struct vl_batch {
   unsigned char* h_arena = nullptr;    // pinned image of every window's small arrays (maps, sparse lists)
   int n_res[2] = {};                   // restarts scheduled on the resident kernel, per mode
   size_t off_res[2] = {}, smem_res[2] = {};
-  int n_ht[VL_N_CLASSES][2] = {}, n_zt[VL_N_CLASSES][2] = {};
-  size_t off_ht[VL_N_CLASSES][2] = {}, off_zt[VL_N_CLASSES][2] = {};
+  // general path: tile lists per kernel class and variant v = mode (bit 0: lep) + 2 * (window with split haplotype tiles)
+  int n_ht[VL_N_CLASSES][4] = {}, n_zt[VL_N_CLASSES][4] = {};
+  size_t off_ht[VL_N_CLASSES][4] = {}, off_zt[VL_N_CLASSES][4] = {};
   int n_sched = 0;
   bool sched_dirty = true;
   int skip_dead = 1, resident = 0, fused = 1;
@@ -326,7 +327,7 @@ namespace {
 // SM's shared memory) or the general path, there grouped by kernel class (layout width) and mode.
 int schedule(vl_batch* b) {
   const Layout& L = b->lay;
-  std::vector<int2> ht[VL_N_CLASSES][2], zt[VL_N_CLASSES][2];
+  std::vector<int2> ht[VL_N_CLASSES][4], zt[VL_N_CLASSES][4];
   std::vector<int> res[2];
   const size_t smem_limit = vl_resident_smem_limit();
   b->n_sched = 0;
@@ -342,13 +343,15 @@ int schedule(vl_batch* b) {
       b->smem_res[m] = std::max(b->smem_res[m], vl_resident_smem_bytes(nct, st.y));
       continue;
     }
-    for (int t = 0; t < P.n_htiles * P.n_hsplit; ++t) ht[cls][m].push_back(make_int2(p, t));   // split * n_htiles + tile
-    for (int t = 0; t < P.n_ztiles; ++t) zt[cls][m].push_back(make_int2(p, t));
+    const int v = m + (P.n_hsplit > 1 ? 2 : 0);
+    for (int sp = 0; sp < P.n_hsplit; ++sp)
+      for (int t = 0; t < P.n_htiles; ++t) ht[cls][v].push_back(make_int2(p, vl_htile_id(t, sp, P.n_hsplit)));
+    for (int t = 0; t < P.n_ztiles; ++t) zt[cls][v].push_back(make_int2(p, t));
     ++b->n_sched;
   }
   size_t ho = 0, zo = 0, ro = 0;
   for (int c = 0; c < VL_N_CLASSES; ++c)
-    for (int m = 0; m < 2; ++m) {
+    for (int m = 0; m < 4; ++m) {
       b->n_ht[c][m] = (int)ht[c][m].size(); b->off_ht[c][m] = ho;
       b->n_zt[c][m] = (int)zt[c][m].size(); b->off_zt[c][m] = zo;
       std::copy(ht[c][m].begin(), ht[c][m].end(), b->h_htiles + ho);
@@ -383,10 +386,10 @@ int launch_resident(vl_batch* b, int n_iter, int64_t* launches) {
 int launch_phase(vl_batch* b, int phase, int64_t* launches) {
   const Layout& L = b->lay;
   for (int c = 0; c < VL_N_CLASSES; ++c)
-    for (int m = 0; m < 2; ++m) {
-      const int mode = m ? VL_MODE_LEP : VL_MODE_UQS;
+    for (int m = 0; m < 4; ++m) {
+      const int mode = (m & 1) ? VL_MODE_LEP : VL_MODE_UQS;
       if (phase == 0 && b->n_ht[c][m] > 0) {
-        VL_CUDA(vl_launch_haplo(c, mode, b->d_probs(), b->dev<int2>(L.htiles) + b->off_ht[c][m], b->n_ht[c][m], b->stream));
+        VL_CUDA(vl_launch_haplo(c, mode, m >> 1, b->d_probs(), b->dev<int2>(L.htiles) + b->off_ht[c][m], b->n_ht[c][m], b->stream));
         *launches += 1;
       }
       if (phase == 1 && b->n_zt[c][m] > 0) {
@@ -408,9 +411,9 @@ int run_chunk_fused(vl_batch* b, int n_iter, int64_t* launches) {
   VL_CUDA(cudaMemsetAsync(b->dev<int>(L.zticket), 0, (size_t)np * sizeof(int), b->stream));
   if (launch_resident(b, n_iter, launches)) return 1;
   for (int c = 0; c < VL_N_CLASSES; ++c)
-    for (int m = 0; m < 2; ++m)
+    for (int m = 0; m < 4; ++m)
       if (b->n_ht[c][m] > 0) {
-        VL_CUDA(vl_launch_chunk(c, m ? VL_MODE_LEP : VL_MODE_UQS, b->d_probs(), b->dev<int2>(L.htiles) + b->off_ht[c][m],
+        VL_CUDA(vl_launch_chunk(c, (m & 1) ? VL_MODE_LEP : VL_MODE_UQS, m >> 1, b->d_probs(), b->dev<int2>(L.htiles) + b->off_ht[c][m],
                                 b->n_ht[c][m], b->dev<int2>(L.ztiles) + b->off_zt[c][m], b->n_zt[c][m], n_iter,
                                 b->dev<int>(L.cbase), b->dev<int>(L.hticket), b->dev<int>(L.zticket), b->d_done(), b->d_pstat(), b->stream));
         *launches += 1;
@@ -980,7 +983,7 @@ int vl_batch_merge_haplo(vl_batch* b, int32_t window, int32_t restart, const int
   VL_CUDA(cudaMemcpyAsync(b->ws + L.tmp_state, &S, sizeof S, cudaMemcpyHostToDevice, s));
   VL_CUDA(cudaMemcpyAsync(b->ws + L.tmp_prob, &T, sizeof T, cudaMemcpyHostToDevice, s));
   VL_CUDA(cudaMemcpyAsync(b->ws + L.tmp_tiles, tiles.data(), tiles.size() * sizeof(int2), cudaMemcpyHostToDevice, s));
-  VL_CUDA(vl_launch_haplo(vl_class_of_tiles(KTg), W.mode, b->dev<VlProblem>(L.tmp_prob), b->dev<int2>(L.tmp_tiles),
+  VL_CUDA(vl_launch_haplo(vl_class_of_tiles(KTg), W.mode, 0, b->dev<VlProblem>(L.tmp_prob), b->dev<int2>(L.tmp_tiles),
                           W.n_htiles, s));
   if (merged_haplo_out) {
     const size_t total = (size_t)G * W.L * VL_N_BASES;

@@ -39,9 +39,9 @@
 #define VL_MAX_STAGES 24 // most stages in flight (narrow layouts, or few restarts left: see vl_launch_chunk)
 #endif
 #define VL_THREADS 128
-#define VL_MAX_KT 16
+#define VL_MAX_KT 16     // 8-slot tiles of a layout (VL_MAX_CLUSTERS / 8)
 #define VL_HSPLIT_READS 512   // a haplotype tile's reads are shared by Npad / 512 CTAs ...
-#define VL_MAX_HSPLIT 8       // ... at most 8 (windows of fewer than 1024 padded reads: one CTA, as before)     // 8-slot tiles of a layout (VL_MAX_CLUSTERS / 8)
+#define VL_MAX_HSPLIT 8       // ... at most 8 (windows of fewer than 1024 padded reads: one CTA, as before)
 #define VL_ZP_EXTRA 8    // scalars appended to each per-tile column-sum record: data, ent, c, d
 #define VL_HP_STRIDE 4
 
@@ -88,7 +88,6 @@ struct VlProblem {
   int mode, N, L, K;
   int Npad, Ls, KT, NCs;   // NCs: dense columns incl. padding, a multiple of 16
   int n_ztiles, n_htiles, window, restart;
-  int n_hsplit, pad0_;     // CTAs that share the reads of one haplotype tile (1 unless the window is large)
   // window tensors (shared by the restarts of a window)
   const double* dm;        // [NCs/16][Npad][16] dense operand, see vl_dm_col
   const double* w;         // [Npad]  read multiplicity, 0 in the padding
@@ -112,8 +111,6 @@ struct VlProblem {
   double* gm;              // [NCs][vl_ks(ktl)]      g at the (position, base) of each dense column
   double* zpart;           // [n_ztiles][8*KT + VL_ZP_EXTRA]
   double* hpart;           // [n_htiles][VL_HP_STRIDE]
-  double* tsplit;          // [n_htiles][n_hsplit][16 * 8*KT]  partial sums over reads of a split tile (n_hsplit > 1)
-  int* hsplit_count;       // [n_htiles]  arrivals at a split tile in the current update
   double* alpha;           // [8*KT]  per cluster
   double* mlp;             // [8*KT]  mean_log_pi per cluster
   double* mlp_lay;         // [8*KT]  mean_log_pi per slot
@@ -122,6 +119,10 @@ struct VlProblem {
   int* lay_z;              // [8*KT]  slot -> cluster for the layout z is stored in
   double* hist;            // [max_iter] history_elbo
   VlState* st;
+  // large windows only (kept behind the fields every tile reads, whose cache lines stay as they were)
+  double* tsplit;          // [n_htiles][n_hsplit][16 * 8*KT]  partial sums over reads of a split tile (n_hsplit > 1)
+  int* hsplit_count;       // [n_htiles]  arrivals at a split tile in the current update
+  int n_hsplit, pad0_;     // CTAs that share the reads of one haplotype tile (1 unless the window is large)
 };
 
 // ---------------------------------------------------------------------------------------

@@ -91,6 +91,32 @@ __device__ __forceinline__ bool vl_wait_published(const VlState* S, int target) 
   return r != 0;
 }
 
+// A column tile whose reads are shared by n_split CTAs: park this CTA's partial sums T; the CTA that
+// arrives last adds all parts in split order (a fixed order, whoever arrives last) into its T and
+// carries on (returns true), the others are done.  Kept out of line: windows below 1024 padded
+// reads never come here and their code should not pay for it.
+__device__ __noinline__ bool vl_split_combine(const VlProblem& P, double* T, int ty, int split, int n_split, int count) {
+  __shared__ int s_last;
+  const int tid = threadIdx.x;
+  const size_t part_stride = (size_t)VL_PT * 8 * P.KT;
+  double* parts = P.tsplit + (size_t)ty * n_split * part_stride;
+  __syncthreads();
+  for (int idx = tid; idx < count; idx += VL_THREADS) parts[split * part_stride + idx] = T[idx];
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) s_last = (atomicAdd(&P.hsplit_count[ty], 1) == n_split - 1) ? 1 : 0;
+  __syncthreads();
+  if (!s_last) return false;
+  __threadfence();
+  for (int idx = tid; idx < count; idx += VL_THREADS) {
+    double v = parts[idx];
+    for (int s2 = 1; s2 < n_split; ++s2) v += parts[s2 * part_stride + idx];
+    T[idx] = v;
+  }
+  if (tid == 0) P.hsplit_count[ty] = 0;          // the next update's CTAs of this tile come after our signal
+  return true;
+}
+
 // =========================================================================================
 // update_mean_haplo.  Per (position l, base b, slot s) the logit is
 //   (l, b) a dense column j:  T[j,s]    = sum_n w_n z[n,s] Dm[n,j]              (DMMA, M = column)
@@ -100,7 +126,9 @@ __device__ __forceinline__ bool vl_wait_published(const VlState* S, int target) 
 // (lg, rh) = 8 columns x one half of the reads of every stage; the halves are added in fixed
 // order.
 // =========================================================================================
-template <int KTM, int MODE>
+// SPLIT: the variant for large windows whose tiles share their reads among several CTAs; windows below
+// 1024 padded reads run the SPLIT = false instantiation, which is the code they always had.
+template <int KTM, int MODE, bool SPLIT>
 __device__ __forceinline__ bool vl_haplo_body(const VlProblem* __restrict__ probs, const int2 tm, const int stage_doubles,
                                               const int* zticket, const int z_want, const int pub_want) {
   constexpr int NB = (8 * KTM + 31) / 32;        // 32-slot groups (lanes = slots in the sparse part)
@@ -115,10 +143,11 @@ __device__ __forceinline__ bool vl_haplo_body(const VlProblem* __restrict__ prob
   GK_DECL(tm.x == 0 && tm.y == 0);
   const VlProblem& P = probs[tm.x];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, q = lane & 3;
-  // Large windows: n_hsplit CTAs share the reads of a column tile (tile id = split * n_htiles + tile);
+  // Large windows: n_hsplit CTAs share the reads of a column tile;
   // the last one to arrive adds the partial sums in split order and finishes the tile.
-  const int n_split = P.n_hsplit;
-  const int ty = (n_split > 1) ? tm.y % P.n_htiles : tm.y, split = (n_split > 1) ? tm.y / P.n_htiles : 0;
+  // (the split travels in the tile id -- vl_htile_id -- so that no tile waits for a load to learn its tile)
+  const int ty = SPLIT ? (tm.y & 0xFFFFF) : tm.y, split = SPLIT ? ((tm.y >> 20) & 0xF) : 0;
+  const int n_split = SPLIT ? max(1, (tm.y >> 24) & 0xF) : 1;
   // Inside a chunk launch (zticket != nullptr) the operand loop starts as soon as the read tiles
   // of the previous update have written w z -- it needs that update's layout width only
   // (ktring) -- and overlaps the scalar update; the state is read after it has been published.
@@ -235,41 +264,26 @@ __device__ __forceinline__ bool vl_haplo_body(const VlProblem* __restrict__ prob
   GK_TICK(1);
   // T [16][8 ktz] in the slot order of the stored w z
   double* T = stg;
-  for (int turn = 0; turn < VL_THREADS / 32; ++turn) {
-    if (warp == turn) {
+  auto combine_warps = [&]() {
+    for (int turn = 0; turn < VL_THREADS / 32; ++turn) {
+      if (warp == turn) {
 #pragma unroll
-      for (int mt = 0; mt < 2; ++mt)
+        for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
-        for (int i = 0; i < KTM; ++i)
-          if (i < ktz) {
-            double2* tp = reinterpret_cast<double2*>(T + (mt * 8 + g) * K8z + 8 * i + 2 * q);
-            double2 o = make_double2(0.0, 0.0);
-            if (turn > 0) o = *tp;
-            *tp = make_double2(o.x + acc[mt][i][0], o.y + acc[mt][i][1]);
-          }
+          for (int i = 0; i < KTM; ++i)
+            if (i < ktz) {
+              double2* tp = reinterpret_cast<double2*>(T + (mt * 8 + g) * K8z + 8 * i + 2 * q);
+              double2 o = make_double2(0.0, 0.0);
+              if (turn > 0) o = *tp;
+              *tp = make_double2(o.x + acc[mt][i][0], o.y + acc[mt][i][1]);
+            }
+      }
+      if (turn + 1 < VL_THREADS / 32) __syncthreads();
     }
-    if (turn + 1 < VL_THREADS / 32) __syncthreads();
-  }
-  if (n_split > 1) {
-    // this CTA's reads are a part of the tile's: park the partial sums; the CTA that arrives last
-    // adds all parts in split order (a fixed order, whoever arrives last) and carries on
-    __shared__ int s_last;
-    const size_t part_stride = (size_t)VL_PT * 8 * P.KT;
-    double* parts = P.tsplit + (size_t)ty * n_split * part_stride;
-    __syncthreads();
-    for (int idx = tid; idx < VL_PT * K8z; idx += VL_THREADS) parts[split * part_stride + idx] = T[idx];
-    __threadfence();
-    __syncthreads();
-    if (tid == 0) s_last = (atomicAdd(&P.hsplit_count[ty], 1) == n_split - 1) ? 1 : 0;
-    __syncthreads();
-    if (!s_last) return false;
-    __threadfence();
-    for (int idx = tid; idx < VL_PT * K8z; idx += VL_THREADS) {
-      double v = parts[idx];
-      for (int s2 = 1; s2 < n_split; ++s2) v += parts[s2 * part_stride + idx];
-      T[idx] = v;
-    }
-    if (tid == 0) P.hsplit_count[ty] = 0;          // the next update's CTAs of this tile come after our signal
+  };
+  if constexpr (SPLIT) {
+    combine_warps();
+    if (n_split > 1 && !vl_split_combine(P, T, ty, split, n_split, VL_PT * K8z)) return false;
   }
   // the state of this update: published by the scalar update of the previous one
   if (early) {
@@ -284,6 +298,7 @@ __device__ __forceinline__ bool vl_haplo_body(const VlProblem* __restrict__ prob
   const int nlay = S->nlay;
   // Cm [16][5][K8] in the current slot order, behind T
   double* Cm = stg + VL_PT * K8z;
+  if constexpr (!SPLIT) combine_warps();
   GK_TICK(2);
   // sparse entries of the positions whose columns lie in this tile: warp = 4 of them,
   // lanes = slots
@@ -404,10 +419,10 @@ __device__ __forceinline__ bool vl_haplo_body(const VlProblem* __restrict__ prob
   return true;
 }
 
-template <int KTM, int MODE>
+template <int KTM, int MODE, bool SPLIT>
 __global__ void __launch_bounds__(VL_THREADS, vl_min_ctas(KTM))
 vl_haplo_kernel(const VlProblem* __restrict__ probs, const int2* __restrict__ tiles) {
-  vl_haplo_body<KTM, MODE>(probs, tiles[blockIdx.x], 0, nullptr, 0, 0);
+  vl_haplo_body<KTM, MODE, SPLIT>(probs, tiles[blockIdx.x], 0, nullptr, 0, 0);
 }
 
 // =========================================================================================
@@ -704,7 +719,7 @@ vl_cluster_kernel(const VlProblem* __restrict__ probs, const int2* __restrict__ 
 // for all haplotype tiles of its update (hticket).  No launch latency and no kernel boundary
 // between the steps, and restarts advance independently of each other inside the chunk.
 // =========================================================================================
-template <int KTM, int MODE>
+template <int KTM, int MODE, bool SPLIT>
 __global__ void __launch_bounds__(VL_THREADS, vl_min_ctas(KTM))
 vl_chunk_kernel(const VlProblem* __restrict__ probs, const int2* __restrict__ htiles, int n_ht,
                 const int2* __restrict__ ztiles, int n_zt, const int* __restrict__ chunk_base,
@@ -719,7 +734,7 @@ vl_chunk_kernel(const VlProblem* __restrict__ probs, const int2* __restrict__ ht
   GK_DECL(tm.x == 0 && tm.y == 0);
   const int pub_want = chunk_base[tm.x] + it;
   if (is_h) {
-    if (!vl_haplo_body<KTM, MODE>(probs, tm, stage_doubles, zticket + tm.x, it * P.n_ztiles, pub_want)) return;
+    if (!vl_haplo_body<KTM, MODE, SPLIT>(probs, tm, stage_doubles, zticket + tm.x, it * P.n_ztiles, pub_want)) return;
 #ifdef VL_RS_PROFILE
     gk_t_ = clock64();
 #endif
@@ -931,17 +946,17 @@ constexpr size_t smem_cluster() {
   return ((size_t)vl_zstages(KTM) * (VL_ZT_READS * VL_PT + VL_PT * vl_ks(KTM)) + (VL_THREADS / 32) * 8 * KTM) * sizeof(double);
 }
 
-template <int KTM, int MODE>
+template <int KTM, int MODE, bool SPLIT>
 cudaError_t launch_haplo(const VlProblem* probs, const int2* tiles, int n, cudaStream_t stream) {
   // the post-loop tables T [16][K8] + Cm [16][5][K8] reuse the stage buffers
   static_assert(smem_haplo<KTM>() >= (size_t)VL_PT * 6 * 8 * KTM * sizeof(double), "haplo smem union");
-  cudaError_t e = cudaFuncSetAttribute(vl_haplo_kernel<KTM, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+  cudaError_t e = cudaFuncSetAttribute(vl_haplo_kernel<KTM, MODE, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)smem_haplo<KTM>());
   if (e != cudaSuccess) return e;
-  vl_haplo_kernel<KTM, MODE><<<n, VL_THREADS, smem_haplo<KTM>(), stream>>>(probs, tiles);
+  vl_haplo_kernel<KTM, MODE, SPLIT><<<n, VL_THREADS, smem_haplo<KTM>(), stream>>>(probs, tiles);
   return cudaGetLastError();
 }
-template <int KTM, int MODE>
+template <int KTM, int MODE, bool SPLIT>
 cudaError_t launch_cluster(const VlProblem* probs, const int2* tiles, int n, int* done_count, int4* pstat,
                            cudaStream_t stream) {
   cudaError_t e = cudaFuncSetAttribute(vl_cluster_kernel<KTM, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -951,7 +966,7 @@ cudaError_t launch_cluster(const VlProblem* probs, const int2* tiles, int n, int
   return cudaGetLastError();
 }
 
-template <int KTM, int MODE>
+template <int KTM, int MODE, bool SPLIT>
 cudaError_t launch_chunk(const VlProblem* probs, const int2* htiles, int n_ht, const int2* ztiles, int n_zt,
                          int n_updates, const int* chunk_base, int* hticket, int* zticket, int* done_count, int4* pstat,
                          cudaStream_t stream) {
@@ -964,27 +979,27 @@ cudaError_t launch_chunk(const VlProblem* probs, const int2* htiles, int n_ht, c
     const size_t deep = (size_t)104 * 1024;      // two CTAs per SM
     if (deep > smem) { stage_doubles = (int)((deep - (VL_THREADS / 32) * 8 * KTM * sizeof(double)) / sizeof(double)); smem = deep; }
   }
-  cudaError_t e = cudaFuncSetAttribute(vl_chunk_kernel<KTM, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(160 * 1024));
+  cudaError_t e = cudaFuncSetAttribute(vl_chunk_kernel<KTM, MODE, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(160 * 1024));
   if (e != cudaSuccess) return e;
   const long long blocks = (long long)n_updates * (n_ht + n_zt);
   if (blocks > 0x7fffffffLL) return cudaErrorInvalidValue;
-  vl_chunk_kernel<KTM, MODE><<<(unsigned)blocks, VL_THREADS, smem, stream>>>(probs, htiles, n_ht, ztiles, n_zt, chunk_base,
+  vl_chunk_kernel<KTM, MODE, SPLIT><<<(unsigned)blocks, VL_THREADS, smem, stream>>>(probs, htiles, n_ht, ztiles, n_zt, chunk_base,
                                                                             hticket, zticket, done_count, pstat, stage_doubles);
   return cudaGetLastError();
 }
 
-template <int KTM, int MODE>
+template <int KTM, int MODE, bool SPLIT>
 cudaError_t chunk_occupancy(int deep, int* ctas_per_sm, int* smem_bytes, int* regs) {
   size_t smem = std::max(smem_haplo<KTM>(), smem_cluster<KTM>());
   if (deep) smem = std::max(smem, (size_t)104 * 1024);
-  cudaError_t e = cudaFuncSetAttribute(vl_chunk_kernel<KTM, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(160 * 1024));
+  cudaError_t e = cudaFuncSetAttribute(vl_chunk_kernel<KTM, MODE, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(160 * 1024));
   if (e != cudaSuccess) return e;
   cudaFuncAttributes at;
-  e = cudaFuncGetAttributes(&at, vl_chunk_kernel<KTM, MODE>);
+  e = cudaFuncGetAttributes(&at, vl_chunk_kernel<KTM, MODE, SPLIT>);
   if (e != cudaSuccess) return e;
   *regs = at.numRegs;
   *smem_bytes = (int)(smem + at.sharedSizeBytes);
-  return cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas_per_sm, vl_chunk_kernel<KTM, MODE>, VL_THREADS, smem);
+  return cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas_per_sm, vl_chunk_kernel<KTM, MODE, SPLIT>, VL_THREADS, smem);
 }
 
 }  // namespace
@@ -993,23 +1008,32 @@ int vl_class_of_tiles(int kt) { return kt <= 2 ? 0 : (kt <= 4 ? 1 : (kt <= 8 ? 2
 int vl_class_capacity(int cls) { return 2 << cls; }
 
 #define VL_DISPATCH(FN, ...)                                                             \
-  switch (cls * 2 + (mode == VL_MODE_LEP ? 1 : 0)) {                                     \
-    case 0: return FN<2, VL_MODE_UQS>(__VA_ARGS__);                                      \
-    case 1: return FN<2, VL_MODE_LEP>(__VA_ARGS__);                                      \
-    case 2: return FN<4, VL_MODE_UQS>(__VA_ARGS__);                                      \
-    case 3: return FN<4, VL_MODE_LEP>(__VA_ARGS__);                                      \
-    case 4: return FN<8, VL_MODE_UQS>(__VA_ARGS__);                                      \
-    case 5: return FN<8, VL_MODE_LEP>(__VA_ARGS__);                                      \
-    case 6: return FN<16, VL_MODE_UQS>(__VA_ARGS__);                                     \
-    case 7: return FN<16, VL_MODE_LEP>(__VA_ARGS__);                                     \
+  switch ((cls * 2 + (mode == VL_MODE_LEP ? 1 : 0)) * 2 + (split ? 1 : 0)) {               \
+    case 0: return FN<2, VL_MODE_UQS, false>(__VA_ARGS__);                               \
+    case 1: return FN<2, VL_MODE_UQS, true>(__VA_ARGS__);                                \
+    case 2: return FN<2, VL_MODE_LEP, false>(__VA_ARGS__);                               \
+    case 3: return FN<2, VL_MODE_LEP, true>(__VA_ARGS__);                                \
+    case 4: return FN<4, VL_MODE_UQS, false>(__VA_ARGS__);                               \
+    case 5: return FN<4, VL_MODE_UQS, true>(__VA_ARGS__);                                \
+    case 6: return FN<4, VL_MODE_LEP, false>(__VA_ARGS__);                               \
+    case 7: return FN<4, VL_MODE_LEP, true>(__VA_ARGS__);                                \
+    case 8: return FN<8, VL_MODE_UQS, false>(__VA_ARGS__);                               \
+    case 9: return FN<8, VL_MODE_UQS, true>(__VA_ARGS__);                                \
+    case 10: return FN<8, VL_MODE_LEP, false>(__VA_ARGS__);                              \
+    case 11: return FN<8, VL_MODE_LEP, true>(__VA_ARGS__);                               \
+    case 12: return FN<16, VL_MODE_UQS, false>(__VA_ARGS__);                             \
+    case 13: return FN<16, VL_MODE_UQS, true>(__VA_ARGS__);                              \
+    case 14: return FN<16, VL_MODE_LEP, false>(__VA_ARGS__);                             \
+    case 15: return FN<16, VL_MODE_LEP, true>(__VA_ARGS__);                              \
     default: return cudaErrorInvalidValue;                                               \
   }
 
 cudaError_t vl_chunk_occupancy(int cls, int mode, int deep, int* ctas_per_sm, int* smem_bytes, int* regs) {
+  const int split = 0;
   VL_DISPATCH(chunk_occupancy, deep, ctas_per_sm, smem_bytes, regs)
 }
 
-cudaError_t vl_launch_haplo(int cls, int mode, const VlProblem* probs, const int2* tiles, int n_tiles,
+cudaError_t vl_launch_haplo(int cls, int mode, int split, const VlProblem* probs, const int2* tiles, int n_tiles,
                             cudaStream_t stream) {
   if (n_tiles <= 0) return cudaSuccess;
   VL_DISPATCH(launch_haplo, probs, tiles, n_tiles, stream)
@@ -1017,11 +1041,12 @@ cudaError_t vl_launch_haplo(int cls, int mode, const VlProblem* probs, const int
 
 cudaError_t vl_launch_cluster(int cls, int mode, const VlProblem* probs, const int2* tiles, int n_tiles,
                               int* done_count, int4* pstat, cudaStream_t stream) {
+  const int split = 0;
   if (n_tiles <= 0) return cudaSuccess;
   VL_DISPATCH(launch_cluster, probs, tiles, n_tiles, done_count, pstat, stream)
 }
 
-cudaError_t vl_launch_chunk(int cls, int mode, const VlProblem* probs, const int2* htiles, int n_ht,
+cudaError_t vl_launch_chunk(int cls, int mode, int split, const VlProblem* probs, const int2* htiles, int n_ht,
                             const int2* ztiles, int n_zt, int n_updates, const int* chunk_base, int* hticket,
                             int* zticket, int* done_count, int4* pstat, cudaStream_t stream) {
   if (n_ht <= 0 || n_zt <= 0 || n_updates <= 0) return cudaSuccess;

@@ -19,7 +19,7 @@ int vl_debug_resident_cycles(unsigned long long* out16, int reset);
 cudaError_t vl_launch_resident(int mode, const VlProblem* probs, const int* plist, int n, int n_iter, size_t smem,
                                int* done_count, int4* pstat, cudaStream_t stream);
 
-cudaError_t vl_launch_haplo(int cls, int mode, const VlProblem* probs, const int2* tiles, int n_tiles,
+cudaError_t vl_launch_haplo(int cls, int mode, int split, const VlProblem* probs, const int2* tiles, int n_tiles,
                             cudaStream_t stream);
 // pstat[p] receives (still running, tiles needed next, valid slots, updates done) from the scalar
 // update that the last read tile of restart p performs
@@ -27,7 +27,7 @@ cudaError_t vl_launch_cluster(int cls, int mode, const VlProblem* probs, const i
                               int* done_count, int4* pstat, cudaStream_t stream);
 // n_updates updates of one kernel class in one launch (vl_chunk_kernel): chunk_base[p] = updates
 // restart p had completed when the chunk was scheduled, hticket[p] and zticket[p] zeroed by the caller
-cudaError_t vl_launch_chunk(int cls, int mode, const VlProblem* probs, const int2* htiles, int n_ht,
+cudaError_t vl_launch_chunk(int cls, int mode, int split, const VlProblem* probs, const int2* htiles, int n_ht,
                             const int2* ztiles, int n_zt, int n_updates, const int* chunk_base, int* hticket,
                             int* zticket, int* done_count, int4* pstat, cudaStream_t stream);
 cudaError_t vl_launch_init(const VlProblem* probs, int n_probs, int4* pstat, cudaStream_t stream);
@@ -43,5 +43,7 @@ cudaError_t vl_launch_init_rows(const double* raw, const double* w, double* z, d
                                 cudaStream_t stream);
 cudaError_t vl_launch_exp_test(const double* x, double* out, int n, cudaStream_t stream);
 // per-phase cycle counters of restart 0 in the general-path kernels (see vl_kernels.cu); 2 unless -DVL_RS_PROFILE
+// id of a haplotype tile in the tile lists: column tile, which part of the reads, of how many parts
+inline int vl_htile_id(int tile, int split, int n_split) { return n_split > 1 ? (tile | (split << 20) | (n_split << 24)) : tile; }
 int vl_debug_general_cycles(unsigned long long* out20, int reset);
 cudaError_t vl_chunk_occupancy(int cls, int mode, int deep, int* ctas_per_sm, int* smem_bytes, int* regs);

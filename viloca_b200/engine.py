@@ -297,8 +297,12 @@ class CaviBatch:
                 if want_cluster:
                     bufs["mean_cluster"] = self._buffer((i, "mean_cluster"), (n, k), np.float64, pinned)
                     res[i].mean_cluster = capi.f64_ptr(bufs["mean_cluster"])
-                bufs["alpha"] = np.empty(k, np.float64)
-                bufs["mean_log_pi"] = np.empty(k, np.float64)
+                if pinned:      # (a pageable destination would turn these two copies into blocking ones)
+                    small = self._buffer(("small",), (nw, 2, capi.MAX_CLUSTERS), np.float64, True)
+                    bufs["alpha"], bufs["mean_log_pi"] = small[i, 0, :k], small[i, 1, :k]
+                else:
+                    bufs["alpha"] = np.empty(k, np.float64)
+                    bufs["mean_log_pi"] = np.empty(k, np.float64)
                 bufs["scalars"] = np.empty(capi.SCALAR_STRIDE, np.float64)
                 res[i].alpha = capi.f64_ptr(bufs["alpha"])
                 res[i].mean_log_pi = capi.f64_ptr(bufs["mean_log_pi"])

@@ -223,6 +223,29 @@ int vl_batch_profile_step(vl_batch* batch, int32_t n_updates, double* ms_out, in
 int vl_batch_problem_stats(vl_batch* batch, int32_t* out, int32_t n_problems);
 
 /*
+ * Host-only (no CUDA call): a window's read file -> compact tensors, the native form of
+ * load_and_process_reads (use_quality_scores/preparation.py:24-90; learn_error_params/preparation.py:51-94).
+ *
+ * vl_reads_parse: `fasta` = the bytes of w-<ref>-<beg>-<end>.reads.fas (one sequence line per record; the
+ * buffer must stay alive until vl_reads_free).  unique != 0 collapses identical read strings into the row
+ * of their first occurrence.  Returns the number of raw reads, of rows, and the window length.  Fails
+ * (vl_last_error) on records of unequal length, multi-line sequences or an empty file; callers fall
+ * back to their generic FASTA reader then.
+ * vl_reads_fill: codes [n_rows][length] (index in `alphabet`, 255 otherwise), weights [n_rows]
+ * (multiplicity), mean_qualities [n_rows][length] = the reference's running mean (q * w + q_new) / (w + 1)
+ * in file order, then 0 -> 2 (quality_kind 0: none, 1: int64 [n_raw][length], 2: float64), row_of [n_raw],
+ * id_spans [n_raw][2] and seq_spans [n_rows][2] = (offset, length) of the record ids / row sequences inside
+ * `fasta` (any of the last three may be NULL).
+ */
+typedef struct vl_reads vl_reads;
+int vl_reads_parse(const char* fasta, size_t n_bytes, int32_t unique, vl_reads** out, int32_t* n_raw_out,
+                   int32_t* n_rows_out, int32_t* length_out);
+int vl_reads_fill(const vl_reads* reads, const char* alphabet, const void* qualities, int32_t quality_kind,
+                  uint8_t* codes, double* weights, double* mean_qualities, int32_t* row_of, int64_t* id_spans,
+                  int64_t* seq_spans);
+void vl_reads_free(vl_reads* reads);
+
+/*
  * Test hook: the exponential the softmax epilogues use (valid for x <= 0, -inf allowed) applied
  * to n host values on `device`.  It replaces CUDA's exp() in the kernels because FP64 latency
  * bounds the epilogues; tests compare it with the host's exp, including the underflow boundary

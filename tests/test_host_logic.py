@@ -211,3 +211,94 @@ def test_window_snvs_match_reference_on_fixture_windows(golden_dir, name):
     got = sw.cooccurring_mutations(haps, ref_seq, g["chrom"], g["beg"], g["end"])
     exp = [{k: v for k, v in r.items() if v is not None} for r in g["cooccurring"]]
     assert got == exp
+
+
+def test_parallel_job_loading_equals_serial(golden_dir, tmp_path):
+    """load_jobs spreads window preparation over worker processes (the reference's Pool over windows);
+    the prepared tensors and seeded initial states are identical to loading in-process."""
+    from oracle import bam_windows
+    names = ["hiv_3120", "hiv_2500_3starts", "sars_24520", "amplicon_90", "longreads_2900"]
+    meta = json.load(open(os.path.join(golden_dir, "bam_windows", "expected.json")))
+
+    def make_jobs():
+        jobs = []
+        for k, name in enumerate(names + names[:2]):
+            d = tmp_path / f"{k}"
+            d.mkdir(exist_ok=True)
+            _, f_reads, f_ref, f_q = bam_windows.materialize(os.path.join(golden_dir, "bam_windows", name, "window.npz"), str(d))
+            m = meta[name]
+            jobs.append(_common.WindowJob(mode="uqs", freads_in=f_reads, fref_in=f_ref, fname_qualities=f_q, output_dir="./",
+                                          n_starts=m["n_starts"], K=m["K"], alpha0=1e-4, seed=m["seed"]))
+        return jobs
+
+    serial = _common.load_jobs(make_jobs(), workers=1)
+    pooled = _common.load_jobs(make_jobs(), workers=3)
+    assert len(serial) == len(pooled) == 7
+    for a, b in zip(serial, pooled):
+        assert a.freads_in.split("/")[-1] == b.freads_in.split("/")[-1]
+        for key in ("codes", "weights", "ref_codes", "init_cluster", "init_scalars", "log_hit", "log_off"):
+            assert np.array_equal(getattr(a.window, key), getattr(b.window, key)), key
+        assert a.prepared.read_ids == b.prepared.read_ids
+
+
+# ---------------------------------------------------------------------------------------
+# native read preparation (SURVEY 8(f) row 1) against the Python restatement of the reference
+# ---------------------------------------------------------------------------------------
+
+def _same_prepared(a, b):
+    assert a.n_raw == b.n_raw
+    assert a.codes.dtype == b.codes.dtype and np.array_equal(a.codes, b.codes)
+    assert a.weights.dtype == b.weights.dtype and np.array_equal(a.weights, b.weights)
+    assert (a.qualities is None) == (b.qualities is None)
+    if a.qualities is not None:
+        assert a.qualities.dtype == b.qualities.dtype and np.array_equal(a.qualities, b.qualities)   # bit for bit
+    assert a.read_ids == b.read_ids and a.sequences == b.sequences
+
+
+@pytest.mark.parametrize("seed,n_raw,length,unique,with_q", [(0, 400, 31, True, True), (1, 150, 7, True, True),
+                                                             (2, 300, 12, False, True), (3, 500, 9, True, False),
+                                                             (4, 1, 5, True, True), (5, 64, 1, True, True)])
+def test_native_read_preparation_equals_generic(tmp_path, seed, n_raw, length, unique, with_q):
+    """Random windows with many duplicates, N, lower case, gaps, Q = 0, float or int qualities, CRLF."""
+    rng = np.random.default_rng(seed)
+    pool = ["".join(rng.choice(list("ACGT-Nacgt"), size=length, p=[.2, .2, .2, .2, .05, .05, .025, .025, .025, .025]))
+            for _ in range(max(1, n_raw // 6))]
+    seqs = [pool[int(rng.integers(len(pool)))] for _ in range(n_raw)]
+    path = tmp_path / "w-X-1-9.reads.fas"
+    eol = "\r\n" if seed % 2 else "\n"
+    with open(path, "w", newline="") as fh:
+        for i, s_ in enumerate(seqs):
+            fh.write(f">read_{i}  {i % 7} extra words{eol}{s_}{eol}")
+    quals = None
+    if with_q:
+        quals = rng.integers(0, 42, size=(n_raw, length)).astype(np.int64)
+        if seed == 1:
+            quals = quals.astype(np.float64) + 0.25
+    generic = _common.prepare_reads(*_common.read_window_fasta(str(path)), quals, "ACGT-", unique)
+    native = _common.prepare_reads_file(str(path), quals, "ACGT-", unique)
+    _same_prepared(native, generic)
+
+
+def test_native_read_preparation_on_reference_fixtures(golden_dir, tmp_path):
+    """data_4 and the BAM-cut windows: the native reader gives the reference's prepared tensors."""
+    from oracle import bam_windows
+    for name in ("hiv_3120", "sars_24520", "amplicon_90", "longreads_2900"):
+        _, f_reads, _, f_q = bam_windows.materialize(os.path.join(golden_dir, "bam_windows", name, "window.npz"), str(tmp_path))
+        q = np.load(f_q, allow_pickle=True)
+        _same_prepared(_common.prepare_reads_file(f_reads, q, "ACGT-", True),
+                       _common.prepare_reads(*_common.read_window_fasta(f_reads), q, "ACGT-", True))
+    d4 = os.path.join(golden_dir, "data4", "w-HXB2-2335-2535.reads.fas")
+    q4 = np.load(os.path.join(golden_dir, "data4", "w-HXB2-2335-2535.qualities.npy"), allow_pickle=True)
+    p = _common.prepare_reads_file(d4, q4, "ACGT-", True)
+    assert p.codes.shape == (80, 201) and int(p.weights.sum()) == 87
+
+
+def test_native_read_preparation_falls_back_and_reports(tmp_path):
+    wrapped = tmp_path / "wrapped.fas"
+    wrapped.write_text(">a 1\nACGT\nAC\n>b 2\nACGT\nAC\n")                 # multi-line records: generic reader
+    p = _common.prepare_reads_file(str(wrapped), None, "ACGT-", True)
+    assert p.sequences == ["ACGTAC"] and p.read_ids == [["a", "b"]]
+    ragged = tmp_path / "ragged.fas"
+    ragged.write_text(">a\nACGT\n>b\nACG\n")
+    with pytest.raises(ValueError):
+        _common.prepare_reads_file(str(ragged), None, "ACGT-", True)

@@ -64,6 +64,7 @@ EXPORTS = (
     "vl_batch_fetch", "vl_batch_set_state", "vl_batch_merge_haplo", "vl_batch_profile_step",
     "vl_batch_last_device_ms", "vl_batch_set_option", "vl_batch_problem_stats",
     "vl_window_plan", "vl_window_plan_capacity", "vl_debug_counters", "vl_debug_exp", "vl_debug_occupancy",
+    "vl_reads_parse", "vl_reads_fill", "vl_reads_free",
 )
 
 
@@ -100,6 +101,11 @@ def _load():
     lib.vl_window_plan_capacity.argtypes = [C.c_int32]
     lib.vl_window_plan_capacity.restype = C.c_int32
     lib.vl_window_plan.argtypes = [C.POINTER(WindowDesc), _i32p, C.POINTER(C.c_int64), _i32p]
+    lib.vl_reads_parse.argtypes = [C.c_char_p, C.c_size_t, C.c_int32, C.POINTER(C.c_void_p), _i32p, _i32p, _i32p]
+    lib.vl_reads_fill.argtypes = [C.c_void_p, C.c_char_p, C.c_void_p, C.c_int32, _u8p, _f64p, _f64p, _i32p,
+                                  C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
+    lib.vl_reads_free.argtypes = [C.c_void_p]
+    lib.vl_reads_free.restype = None
     lib.vl_debug_occupancy.argtypes = [C.c_int32] * 4 + [_i32p] * 3
     lib.vl_debug_exp.argtypes = [C.c_int32, _f64p, _f64p, C.c_int32]
     lib.vl_debug_counters.argtypes = [C.POINTER(C.c_uint64), C.c_int32]
@@ -113,6 +119,10 @@ def _load():
 
 
 lib = _load()
+
+
+def last_error() -> str:
+    return lib.vl_last_error().decode("utf-8", "replace")
 
 
 def check(rc: int) -> None:

@@ -14,12 +14,14 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB_DIR = os.path.join(HERE, "lib")
 LIB_PATH = os.path.join(LIB_DIR, "libviloca_b200.so")
-SOURCES = ["vl_kernels.cu", "vl_resident.cu", "vl_api.cu"]
+SOURCES = ["vl_kernels.cu", "vl_resident.cu", "vl_api.cu", "vl_prepare.cu"]
 HEADERS = ["vl_device.cuh", "vl_cavi.cuh", "vl_launch.h", os.path.join("..", "..", "include", "viloca_b200.h")]
 # vl_kernels.cu: vl_chunk_kernel runs many dependent updates in one launch, so state written by
 # one CTA is read by later CTAs of the same launch, possibly on an SM whose L1 still holds the old
 # line: global loads of that file are cached in L2 only (the operand streams through TMA anyway).
-EXTRA_FLAGS = {"vl_kernels.cu": ["-Xptxas", "-dlcm=cg"]}
+EXTRA_FLAGS = {"vl_kernels.cu": ["-Xptxas", "-dlcm=cg"],
+               # host arithmetic that must match NumPy bit for bit (running mean of the qualities): no FMA contraction
+               "vl_prepare.cu": ["-Xcompiler", "-ffp-contract=off"]}
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
     "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden",
@@ -60,7 +62,8 @@ def build(force: bool = False, verbose: bool = False, profile: bool = False) -> 
         if proc.wait() != 0:
             raise subprocess.CalledProcessError(proc.returncode, cmd)
     if force or _stale(LIB_PATH, objs):
-        cmd = [_nvcc(), "-shared", "-o", LIB_PATH] + objs + ["-lcudart_static", "-lrt", "-lpthread", "-ldl"]
+        cmd = [_nvcc(), "-shared", "-o", LIB_PATH] + objs + ["-lcudart_static", "-lrt", "-lpthread", "-ldl",
+                                                           "-Xlinker", "--no-undefined"]   # an unresolved symbol fails here, not at load time
         if verbose:
             print(" ".join(cmd), file=sys.stderr)
         subprocess.run(cmd, check=True)

@@ -452,6 +452,9 @@ void identity_layout(int K, int K8, std::vector<int>& lay, std::vector<int>& gat
 
 }  // namespace
 
+// for the other translation units of the library (declared in vl_launch.h)
+int vl_set_error(const char* msg) { return fail(msg); }
+
 extern "C" {
 #pragma GCC visibility push(default)
 

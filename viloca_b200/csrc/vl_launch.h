@@ -43,6 +43,8 @@ cudaError_t vl_launch_init_rows(const double* raw, const double* w, double* z, d
                                 cudaStream_t stream);
 cudaError_t vl_launch_exp_test(const double* x, double* out, int n, cudaStream_t stream);
 // per-phase cycle counters of restart 0 in the general-path kernels (see vl_kernels.cu); 2 unless -DVL_RS_PROFILE
+// records a message for vl_last_error and returns 1 (vl_api.cu)
+int vl_set_error(const char* msg);
 // id of a haplotype tile in the tile lists: column tile, which part of the reads, of how many parts
 inline int vl_htile_id(int tile, int split, int n_split) { return n_split > 1 ? (tile | (split << 20) | (n_split << 24)) : tile; }
 int vl_debug_general_cycles(unsigned long long* out20, int reset);

@@ -96,6 +96,60 @@ def prepare_reads(ids: Sequence[str], seqs: Sequence[str], qualities: Optional[n
     return PreparedWindow(codes=codes, weights=w, qualities=q, read_ids=read_ids, sequences=rows, n_raw=n_raw)
 
 
+def prepare_reads_file(path: str, qualities: Optional[np.ndarray], alphabet: str, unique_modus: bool) -> PreparedWindow:
+    """The window's read file through the native reader (``vl_reads_parse`` / ``vl_reads_fill``): the same
+    PreparedWindow as ``prepare_reads(*read_window_fasta(path), ...)`` bit for bit, without the per-record
+    Python loops.  Files the native reader does not take (multi-line sequences, qualities that are not
+    a dense (n_raw, length) int64 / float64 array, non-ASCII alphabets) go through the generic path."""
+    import ctypes as C
+    from .. import _capi as capi
+    with open(path, "rb") as fh:
+        text = fh.read()
+    q_kind, q = 0, None
+    if qualities is not None:
+        q = np.asarray(qualities)
+        if q.dtype == np.int64 and q.ndim == 2:
+            q_kind = 1
+        elif q.dtype == np.float64 and q.ndim == 2:
+            q_kind = 2
+        else:
+            q_kind = -1
+    ok = q_kind >= 0 and len(alphabet) < 250 and all(ord(c) < 128 for c in alphabet)
+    handle, n_raw, n_rows, length = C.c_void_p(), C.c_int32(0), C.c_int32(0), C.c_int32(0)
+    if ok and capi.lib.vl_reads_parse(text, len(text), 1 if unique_modus else 0, C.byref(handle), C.byref(n_raw),
+                                      C.byref(n_rows), C.byref(length)) != 0:
+        ok = False
+        if "equal length" in capi.last_error() or "without reads" in capi.last_error():
+            raise ValueError(capi.last_error())
+    if ok and q is not None and q.shape != (n_raw.value, length.value):
+        capi.lib.vl_reads_free(handle)
+        ok = False
+    if not ok:
+        return prepare_reads(*read_window_fasta(path), qualities, alphabet, unique_modus)
+    try:
+        nr, nu, ln = n_raw.value, n_rows.value, length.value
+        codes = np.empty((nu, ln), dtype=np.uint8)
+        weights = np.empty(nu, dtype=np.float64)
+        mean_q = np.empty((nu, ln), dtype=np.float64) if q is not None else None
+        row_of = np.empty(nr, dtype=np.int32)
+        id_spans = np.empty((nr, 2), dtype=np.int64)
+        seq_spans = np.empty((nu, 2), dtype=np.int64)
+        qc = np.ascontiguousarray(q) if q is not None else None
+        capi.check(capi.lib.vl_reads_fill(
+            handle, alphabet.encode("ascii"), qc.ctypes.data_as(C.c_void_p) if qc is not None else None, max(q_kind, 0),
+            capi.u8_ptr(codes), capi.f64_ptr(weights), capi.f64_ptr(mean_q), capi.i32_ptr(row_of),
+            id_spans.ctypes.data_as(C.POINTER(C.c_int64)), seq_spans.ctypes.data_as(C.POINTER(C.c_int64))))
+    finally:
+        capi.lib.vl_reads_free(handle)
+    ids = [text[a:a + n].decode("ascii", "replace") for a, n in id_spans.tolist()]
+    read_ids = [[] for _ in range(nu)]
+    for i, r in enumerate(row_of.tolist()):
+        read_ids[r].append(ids[i])
+    rows = [text[a:a + n].decode("ascii", "replace") for a, n in seq_spans.tolist()]
+    w = weights.astype(np.int64) if unique_modus else weights
+    return PreparedWindow(codes=codes, weights=w, qualities=mean_q, read_ids=read_ids, sequences=rows, n_raw=nr)
+
+
 def load_reference(path: str, alphabet: str, upper: bool):
     """First record of the reference FASTA -> (codes, id).  uqs upper-cases the sequence
     (use_quality_scores/preparation.py:163-165); lep does not, so lower-case bases are outside
@@ -142,12 +196,11 @@ class WindowJob:
         from ..engine import Window
         if self.alphabet != ALPHABET:
             raise ValueError("the engine is built for the alphabet 'ACGT-' (B = 5)")
-        ids, seqs = read_window_fasta(self.freads_in)
         quals = None
         if self.mode == "uqs":
             with open(self.fname_qualities, "rb") as fh:
                 quals = np.load(fh, allow_pickle=True)
-        self.prepared = prepare_reads(ids, seqs, quals, self.alphabet, self.unique_modus)
+        self.prepared = prepare_reads_file(self.freads_in, quals, self.alphabet, self.unique_modus)
         self.ref_codes, _, self.ref_seq = load_reference(self.fref_in, self.alphabet, upper=(self.mode == "uqs"))
         p = self.prepared
         n = p.codes.shape[0]
@@ -160,6 +213,33 @@ class WindowJob:
                              conv_thres=self.convergence_threshold, max_iter=self.max_iter,
                              name=self.output_name, **kw)
         return self
+
+
+def _load_one(job: WindowJob) -> WindowJob:
+    return job.load()
+
+
+def load_jobs(jobs: Sequence[WindowJob], workers: Optional[int] = None) -> list:
+    """Read and prepare the windows of ``jobs`` (FASTA / qualities -> compact tensors, seeded initial
+    states).  This is host work of the same order as the GPU run itself (per window: parsing, the
+    first-seen dedup, two logs per base, N x K Dirichlet draws per restart), so it is spread over
+    worker processes the way the reference spreads its windows (shotgun.py:527-538:
+    ``Pool(max_proc)``).  ``workers`` = None: cpu_count() - 1, at most one per window; 0 or 1: in this
+    process.  The workers never touch CUDA; results are identical to loading serially."""
+    jobs = list(jobs)
+    todo = [j for j in jobs if j.window is None]
+    if workers is None:
+        workers = max(1, (os.cpu_count() or 2) - 1)
+    workers = min(workers, len(todo))
+    if workers <= 1 or len(todo) < 4:
+        for j in todo:
+            j.load()
+        return jobs
+    import multiprocessing as mp
+    with mp.get_context("fork").Pool(workers) as pool:
+        loaded = pool.map(_load_one, todo, chunksize=max(1, len(todo) // (4 * workers)))
+    it = iter(loaded)
+    return [j if j.window is not None else next(it) for j in jobs]
 
 
 def _result_dicts(job: WindowJob, outcome, restart: int, state: dict):
@@ -282,8 +362,7 @@ def run_jobs(jobs: Sequence[WindowJob], device: int = 0) -> list:
     from ..engine import CaviBatch
     for job in jobs:
         os.makedirs(job.output_dir, exist_ok=True)
-        if job.window is None:
-            job.load()
+    jobs = load_jobs(jobs)
     finished = []
     with CaviBatch([j.window for j in jobs], device=device) as batch:
         batch.upload()

@@ -63,9 +63,10 @@ def snv_tables(jobs, finished, threshold: float = 0.9) -> list:
     return out
 
 
-def run_dpm_batch(runlist, devices: Optional[Sequence[int]] = None, collect: bool = False):
+def run_dpm_batch(runlist, devices: Optional[Sequence[int]] = None, collect: bool = False,
+                  load_workers: Optional[int] = None):
     import torch
-    jobs = [j.load() for j in jobs_from_runlist(runlist)]
+    jobs = _common.load_jobs(jobs_from_runlist(runlist), workers=load_workers)    # a process pool, like the reference's
     if not jobs:
         return ([], []) if collect else None
     if devices is None:

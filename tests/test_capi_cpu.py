@@ -12,8 +12,13 @@ from viloca_b200 import _capi as capi
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
+def _header_text():
+    with open(os.path.join(ROOT, "include", "viloca_b200.h")) as fh:
+        return fh.read()
+
+
 def _declared_symbols():
-    text = open(os.path.join(ROOT, "include", "viloca_b200.h")).read()
+    text = _header_text()
     text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
     return sorted(set(re.findall(r"\b(vl_[a-z_0-9]+)\s*\(", text)))
 
@@ -28,7 +33,7 @@ def test_library_exports_every_declared_symbol():
 
 
 def test_struct_layout_matches_header_constants():
-    text = open(os.path.join(ROOT, "include", "viloca_b200.h")).read()
+    text = _header_text()
     for macro, value in (("VL_N_BASES", capi.N_BASES), ("VL_CODE_N", capi.CODE_N), ("VL_MAX_CLUSTERS", capi.MAX_CLUSTERS),
                          ("VL_INIT_STRIDE", capi.INIT_STRIDE), ("VL_SCALAR_STRIDE", capi.SCALAR_STRIDE),
                          ("VL_STATUS_MAXITER", capi.STATUS_MAXITER), ("VL_MODE_LEP", capi.MODE_LEP)):

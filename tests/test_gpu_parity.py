@@ -11,8 +11,20 @@ import os
 import numpy as np
 import pytest
 
+
 import _bridge as br
 from oracle import cavi_oracle as orc
+
+
+def _text(path):
+    with open(path) as fh:
+        return fh.read()
+
+
+def _json_file(path):
+    with open(path) as fh:
+        return json.load(fh)
+
 
 pytestmark = pytest.mark.gpu
 
@@ -183,8 +195,7 @@ def test_data4_window_files_end_to_end(golden_dir, tmp_path):
     for (_, _, pg, _), (_, _, pe, _) in zip(got, exp):
         assert abs(pg - pe) <= ENG_TOL * abs(pe)
         assert (pg >= 0.9) == (pe >= 0.9)          # the threshold shorah_snv applies (-p 0.9)
-    assert open(out_dir + stem + ".reads-cor.fas").read() == \
-        open(os.path.join(d, "expected_seed42.reads-cor.fas")).read()
+    assert _text(out_dir + stem + ".reads-cor.fas") == _text(os.path.join(d, "expected_seed42.reads-cor.fas"))
 
 
 BAM_WINDOWS = ["hiv_3120", "hiv_2500_3starts", "sars_24520", "amplicon_90", "longreads_2900"]
@@ -199,7 +210,7 @@ def test_bam_fixture_windows_end_to_end(golden_dir, tmp_path, name):
     from oracle import bam_windows
     from viloca_b200.local_haplotype_inference.use_quality_scores import run_dpm_mfa
     d = os.path.join(golden_dir, "bam_windows", name)
-    meta = json.load(open(os.path.join(golden_dir, "bam_windows", "expected.json")))[name]
+    meta = _json_file(os.path.join(golden_dir, "bam_windows", "expected.json"))[name]
     stem, f_reads, f_ref, f_q = bam_windows.materialize(os.path.join(d, "window.npz"), str(tmp_path))
     assert stem == meta["stem"]
     out_dir = os.path.join(str(tmp_path), "out") + "/"
@@ -211,7 +222,7 @@ def test_bam_fixture_windows_end_to_end(golden_dir, tmp_path, name):
     for (_, _, pg, _), (_, _, pe, _) in zip(got, exp):
         assert abs(pg - pe) <= ENG_TOL * abs(pe) + 1e-300
         assert (pg >= 0.9) == (pe >= 0.9)
-    assert open(out_dir + stem + ".reads-cor.fas").read() == open(os.path.join(d, "expected.reads-cor.fas")).read()
+    assert _text(out_dir + stem + ".reads-cor.fas") == _text(os.path.join(d, "expected.reads-cor.fas"))
 
 
 def test_batched_hook_snv_tables_match_reference(golden_dir, tmp_path, monkeypatch):
@@ -220,8 +231,8 @@ def test_batched_hook_snv_tables_match_reference(golden_dir, tmp_path, monkeypat
     reference's shorah_snv.parseWindow / get_cooccuring_muts_haplo_df give on the reference's files."""
     from oracle import bam_windows
     from viloca_b200 import shotgun_hook
-    meta = json.load(open(os.path.join(golden_dir, "bam_windows", "expected.json")))
-    gold = json.load(open(os.path.join(golden_dir, "snv_windows.json")))["windows"]
+    meta = _json_file(os.path.join(golden_dir, "bam_windows", "expected.json"))
+    gold = _json_file(os.path.join(golden_dir, "snv_windows.json"))["windows"]
     monkeypatch.chdir(tmp_path)
     runlist = []
     for name in BAM_WINDOWS:
@@ -252,7 +263,7 @@ def test_bam_fixture_windows_trajectory(golden_dir, tmp_path, name):
     from oracle import bam_windows
     from viloca_b200.local_haplotype_inference import _common
     d = os.path.join(golden_dir, "bam_windows", name)
-    meta = json.load(open(os.path.join(golden_dir, "bam_windows", "expected.json")))[name]
+    meta = _json_file(os.path.join(golden_dir, "bam_windows", "expected.json"))[name]
     _, f_reads, f_ref, f_q = bam_windows.materialize(os.path.join(d, "window.npz"), str(tmp_path))
     job = _common.WindowJob(mode="uqs", freads_in=f_reads, fref_in=f_ref, fname_qualities=f_q, output_dir="./",
                             n_starts=1, K=meta["K"], alpha0=1e-4, seed=meta["seed"])

@@ -6,10 +6,22 @@ import os
 import numpy as np
 import pytest
 
+
 from viloca_b200 import fasta, scheduler, synthetic, tensors
 from viloca_b200.local_haplotype_inference import _common
 from viloca_b200.local_haplotype_inference.learn_error_params import preparation as prep_lep
 from viloca_b200.local_haplotype_inference.use_quality_scores import preparation as prep_uqs
+
+
+def _text(path):
+    with open(path) as fh:
+        return fh.read()
+
+
+def _json_file(path):
+    with open(path) as fh:
+        return json.load(fh)
+
 
 STEM = "w-REF-1-24"
 
@@ -90,7 +102,8 @@ def test_fasta_roundtrip_and_header_conventions(tmp_path):
     path = str(tmp_path / "x.fas")
     fasta.write([("haplotype0", "hap_0 | posterior=0.5 ave_reads=3", "A" * 130),
                  ("read7", "|posterior=1", "ACGT")], path)
-    text = open(path).read().split("\n")
+    with open(path) as fh:
+        text = fh.read().split("\n")
     assert text[0] == ">haplotype0 hap_0 | posterior=0.5 ave_reads=3"
     assert [len(x) for x in text[1:4]] == [60, 60, 10]
     assert text[4] == ">read7 |posterior=1"
@@ -178,7 +191,7 @@ def test_snv_random_pairs_match_reference_functions(golden_dir):
     """300 random reference / haplotype pairs with deletions and inserted 'X' columns, expected tables
     from the unmodified _compare_ref_to_read / __mutations_in_haplotype (oracle/make_golden.py)."""
     from viloca_b200 import snv_windows as sw
-    pairs = json.load(open(os.path.join(golden_dir, "snv_windows.json")))["pairs"]
+    pairs = _json_file(os.path.join(golden_dir, "snv_windows.json"))["pairs"]
     assert len(pairs) == 300
     for c in pairs:
         pre = sw.mark_inserted_gaps(c["ref"], c["seq"])
@@ -198,7 +211,7 @@ def test_window_snvs_match_reference_on_fixture_windows(golden_dir, name):
     """parseWindow / get_cooccuring_muts_haplo_df of the reference on the expected support files of the
     fixture windows, against the in-memory functions fed with the same haplotypes."""
     from viloca_b200 import fasta, snv_windows as sw
-    g = json.load(open(os.path.join(golden_dir, "snv_windows.json")))["windows"][name]
+    g = _json_file(os.path.join(golden_dir, "snv_windows.json"))["windows"][name]
     if name == "data4":
         support = os.path.join(golden_dir, "data4", "expected_seed42.reads-support.fas")
         ref_seq = next(iter(fasta.parse(os.path.join(golden_dir, "data4", "w-HXB2-2335-2535.ref.fas")))).seq
@@ -218,7 +231,7 @@ def test_parallel_job_loading_equals_serial(golden_dir, tmp_path):
     the prepared tensors and seeded initial states are identical to loading in-process."""
     from oracle import bam_windows
     names = ["hiv_3120", "hiv_2500_3starts", "sars_24520", "amplicon_90", "longreads_2900"]
-    meta = json.load(open(os.path.join(golden_dir, "bam_windows", "expected.json")))
+    meta = _json_file(os.path.join(golden_dir, "bam_windows", "expected.json"))
 
     def make_jobs():
         jobs = []
@@ -232,7 +245,7 @@ def test_parallel_job_loading_equals_serial(golden_dir, tmp_path):
         return jobs
 
     serial = _common.load_jobs(make_jobs(), workers=1)
-    pooled = _common.load_jobs(make_jobs(), workers=3)
+    pooled = _common.load_jobs(make_jobs(), workers=2)
     assert len(serial) == len(pooled) == 7
     for a, b in zip(serial, pooled):
         assert a.freads_in.split("/")[-1] == b.freads_in.split("/")[-1]

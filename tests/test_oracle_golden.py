@@ -7,8 +7,15 @@ import os
 import numpy as np
 import pytest
 
+
 import _bridge as br
 from oracle import cavi_oracle as orc
+
+
+def _json_file(path):
+    with open(path) as fh:
+        return json.load(fh)
+
 
 
 def _load(golden_dir, name):
@@ -117,7 +124,7 @@ def test_data4_known_answer(golden_dir):
     """tests/data_4 window, Q = 30, seed 42 -> 54 iterations, ELBO
     -1943.9785808934962 (numpy 2.3.5 / scipy 1.18.1)."""
     d = os.path.join(golden_dir, "data4")
-    meta = json.load(open(os.path.join(d, "expected.json")))["seed42"]
+    meta = _json_file(os.path.join(d, "expected.json"))["seed42"]
     assert meta["n_iterations"] == 54 and meta["n_unique"] == 80 and meta["sum_weights"] == 87
     assert meta["elbo"] == pytest.approx(-1943.9785808934962, rel=1e-13)
     from viloca_b200.local_haplotype_inference import _common
@@ -149,7 +156,7 @@ def test_bam_fixture_windows(golden_dir, tmp_path, name):
     history to 1e-12 (real Phred qualities, deletions, N padding, Q~10 long reads)."""
     from oracle import bam_windows
     from viloca_b200.local_haplotype_inference import _common
-    meta = json.load(open(os.path.join(golden_dir, "bam_windows", "expected.json")))[name]
+    meta = _json_file(os.path.join(golden_dir, "bam_windows", "expected.json"))[name]
     _, f_reads, f_ref, f_q = bam_windows.materialize(os.path.join(golden_dir, "bam_windows", name, "window.npz"), str(tmp_path))
     ids, seqs = _common.read_window_fasta(f_reads)
     p = _common.prepare_reads(ids, seqs, np.load(f_q, allow_pickle=True), "ACGT-", True)

@@ -219,24 +219,35 @@ def _load_one(job: WindowJob) -> WindowJob:
     return job.load()
 
 
+def _load_cost_seconds(job: WindowJob) -> float:
+    """Rough host time of WindowJob.load: parsing / dedup ~ 12 ns per byte of the read file, the seeded
+    Dirichlet draws ~ 120 ns per (read, cluster, restart)."""
+    try:
+        size = os.path.getsize(job.freads_in)
+    except OSError:
+        return 0.0
+    return 12e-9 * size + 1.2e-7 * (size / 200.0) * job.K * job.n_starts
+
+
 def load_jobs(jobs: Sequence[WindowJob], workers: Optional[int] = None) -> list:
     """Read and prepare the windows of ``jobs`` (FASTA / qualities -> compact tensors, seeded initial
-    states).  This is host work of the same order as the GPU run itself (per window: parsing, the
-    first-seen dedup, two logs per base, N x K Dirichlet draws per restart), so it is spread over
-    worker processes the way the reference spreads its windows (shotgun.py:527-538:
-    ``Pool(max_proc)``).  ``workers`` = None: cpu_count() - 1, at most one per window; 0 or 1: in this
-    process.  The workers never touch CUDA; results are identical to loading serially."""
+    states).  For large windows this is host work of the same order as the GPU run itself (N x K
+    Dirichlet draws per restart), so it can be spread over worker processes the way the reference
+    spreads its windows (shotgun.py:527-538: ``Pool(max_proc)``).  ``workers`` = None: a pool of
+    cpu_count() - 1 processes if the estimated serial time exceeds a few seconds, else in this process;
+    0 or 1: in this process.  Workers are spawned (not forked: the parent may hold CUDA and threads),
+    never touch CUDA, and give results identical to loading serially."""
     jobs = list(jobs)
     todo = [j for j in jobs if j.window is None]
     if workers is None:
-        workers = max(1, (os.cpu_count() or 2) - 1)
+        workers = max(1, (os.cpu_count() or 2) - 1) if sum(_load_cost_seconds(j) for j in todo) > 8.0 else 1
     workers = min(workers, len(todo))
-    if workers <= 1 or len(todo) < 4:
+    if workers <= 1:
         for j in todo:
             j.load()
         return jobs
     import multiprocessing as mp
-    with mp.get_context("fork").Pool(workers) as pool:
+    with mp.get_context("spawn").Pool(workers) as pool:
         loaded = pool.map(_load_one, todo, chunksize=max(1, len(todo) // (4 * workers)))
     it = iter(loaded)
     return [j if j.window is not None else next(it) for j in jobs]

@@ -134,7 +134,6 @@ __device__ __forceinline__ bool vl_haplo_body(const VlProblem* __restrict__ prob
   constexpr int NB = (8 * KTM + 31) / 32;        // 32-slot groups (lanes = slots in the sparse part)
   constexpr int KSM = vl_ks(KTM);
   constexpr int DM_STAGE = VL_H_NC * VL_PT;            // doubles
-  constexpr int ST_STRIDE = DM_STAGE + VL_H_NC * KSM;   // dm | wz
   extern __shared__ __align__(128) unsigned char vl_smem[];
   double* stg = reinterpret_cast<double*>(vl_smem);
   __shared__ uint64_t bars[VL_MAX_STAGES];

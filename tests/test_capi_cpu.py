@@ -161,3 +161,25 @@ def test_engine_refuses_to_run_without_gpu():
     win = synthetic.make_window(spec, 0, n_reads=30, length=24)
     with pytest.raises(capi.EngineError):
         engine.CaviBatch([win])
+
+
+def test_reads_reader_error_behaviour():
+    """vl_reads_parse / vl_reads_fill report bad input through the int return + vl_last_error, like
+    the rest of the ABI; a failed parse leaves no handle behind."""
+    h, a, b, c = C.c_void_p(), C.c_int32(0), C.c_int32(0), C.c_int32(0)
+    assert capi.lib.vl_reads_parse(None, 0, 1, C.byref(h), C.byref(a), C.byref(b), C.byref(c)) == 1
+    assert "NULL" in capi.last_error()
+    assert capi.lib.vl_reads_parse(b"", 0, 1, C.byref(h), C.byref(a), C.byref(b), C.byref(c)) == 1
+    assert "without reads" in capi.last_error()
+    text = b">r1 5\nACGT\n>r2 7\nACG\n"
+    assert capi.lib.vl_reads_parse(text, len(text), 1, C.byref(h), C.byref(a), C.byref(b), C.byref(c)) == 1
+    assert "equal length" in capi.last_error()
+    text = b">r1 5\nACGTN\n>r2 7\nACGTN\n>r3 9\nacgt-\n"
+    assert capi.lib.vl_reads_parse(text, len(text), 1, C.byref(h), C.byref(a), C.byref(b), C.byref(c)) == 0
+    assert (a.value, b.value, c.value) == (3, 2, 5)
+    codes = np.zeros((2, 5), dtype=np.uint8)
+    w = np.zeros(2)
+    assert capi.lib.vl_reads_fill(h, b"ACGT-", None, 1, capi.u8_ptr(codes), capi.f64_ptr(w), None, None, None, None) == 1
+    assert capi.lib.vl_reads_fill(h, b"ACGT-", None, 0, capi.u8_ptr(codes), capi.f64_ptr(w), None, None, None, None) == 0
+    capi.lib.vl_reads_free(h)
+    assert codes.tolist() == [[0, 1, 2, 3, 255], [255, 255, 255, 255, 4]] and w.tolist() == [2.0, 1.0]

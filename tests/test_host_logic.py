@@ -315,3 +315,17 @@ def test_native_read_preparation_falls_back_and_reports(tmp_path):
     ragged.write_text(">a\nACGT\n>b\nACG\n")
     with pytest.raises(ValueError):
         _common.prepare_reads_file(str(ragged), None, "ACGT-", True)
+
+
+def test_corrected_reads_writer_equals_generic_fasta_writer(tmp_path):
+    """correct_reads formats the sequence lines once per haplotype; the file is what the generic
+    record writer gives (analyze_results.py:9-23), wrapped lines, empty sequences and odd ids included."""
+    rng = np.random.default_rng(3)
+    state = {}
+    for k, length in enumerate((201, 60, 61, 0, 1)):
+        state[f"haplotype{k}"] = "".join(rng.choice(list("ACGT-"), length))
+        state[f"assignedReads{k}"] = [f"read_{i}_{k}" for i in range(20)] + ["|posterior=1", "x y"]
+    records = [(rid, "|posterior=1", state[f"haplotype{k}"]) for k in range(5) for rid in state[f"assignedReads{k}"]]
+    fasta.write(records, str(tmp_path / "a.fas"))
+    _common.correct_reads(state, str(tmp_path / "b.fas"))
+    assert (tmp_path / "a.fas").read_text() == (tmp_path / "b.fas").read_text()

@@ -35,16 +35,21 @@ def _record(title: str, chunks: list) -> Record:
     return Record(id=first, description=title, seq="".join(chunks))
 
 
-def format_record(rec_id: str, description: str, seq: str, width: int = 60) -> str:
+def format_title(rec_id: str, description: str) -> str:
     if description and description.split(None, 1)[0] == rec_id:
-        title = description
-    elif description:
-        title = f"{rec_id} {description}"
-    else:
-        title = rec_id
-    lines = [f">{title}"]
-    lines.extend(seq[i:i + width] for i in range(0, len(seq), width))
-    return "\n".join(lines) + "\n"
+        return description
+    if description:
+        return f"{rec_id} {description}"
+    return rec_id
+
+
+def format_body(seq: str, width: int = 60) -> str:
+    """The sequence lines of a record (wrapped at ``width``), each with its newline."""
+    return "".join(seq[i:i + width] + "\n" for i in range(0, len(seq), width))
+
+
+def format_record(rec_id: str, description: str, seq: str, width: int = 60) -> str:
+    return ">" + format_title(rec_id, description) + "\n" + format_body(seq, width)
 
 
 def write(records: Iterable[tuple], path: str) -> int:

@@ -329,11 +329,15 @@ def correct_reads(state: dict, path: str) -> None:
     n_hap = len([k for k in state if k.startswith("haplotype")])
     if n_hap == 0:
         return
-    records = []
+    # every read of a haplotype gets the same sequence lines: format them once per haplotype
+    parts = []
     for k in range(n_hap):
-        for read_id in state["assignedReads" + str(k)]:
-            records.append((read_id, "|posterior=1", state["haplotype" + str(k)]))
-    fasta.write(records, path)
+        body = fasta.format_body(state["haplotype" + str(k)])
+        tail = " |posterior=1\n" + body                 # fasta.format_title(id, "|posterior=1") for any other id
+        parts.extend(">" + read_id + tail if read_id != "|posterior=1" else ">|posterior=1\n" + body
+                     for read_id in state["assignedReads" + str(k)])
+    with open(path, "w") as fh:
+        fh.write("".join(parts))
 
 
 def _record_history_run(job: WindowJob, batch, window_index: int):

@@ -269,10 +269,10 @@ def group_haplotypes(mean_haplo: np.ndarray, alphabet: str = ALPHABET):
     """get_unique_haplotypes (analyze_results.py:102-107, 144-157): per-position argmax (first
     maximum wins), identical strings grouped, groups sorted lexicographically."""
     idx = np.argmax(mean_haplo, axis=2)
-    table = np.array(list(alphabet))
+    letters = np.frombuffer(alphabet.encode("ascii"), dtype=np.uint8)[idx]       # (K, L) bytes
     groups = {}
     for k in range(idx.shape[0]):
-        groups.setdefault("".join(table[idx[k]]), []).append(k)
+        groups.setdefault(letters[k].tobytes().decode("ascii"), []).append(k)
     return sorted(groups.items())
 
 

@@ -246,8 +246,9 @@ def test_parallel_job_loading_equals_serial(golden_dir, tmp_path):
 
     serial = _common.load_jobs(make_jobs(), workers=1)
     pooled = _common.load_jobs(make_jobs(), workers=2)
-    assert len(serial) == len(pooled) == 7
-    for a, b in zip(serial, pooled):
+    threaded = _common.load_jobs(make_jobs())                # small windows: the thread pool
+    assert len(serial) == len(pooled) == len(threaded) == 7
+    for a, b in list(zip(serial, pooled)) + list(zip(serial, threaded)):
         assert a.freads_in.split("/")[-1] == b.freads_in.split("/")[-1]
         for key in ("codes", "weights", "ref_codes", "init_cluster", "init_scalars", "log_hit", "log_off"):
             assert np.array_equal(getattr(a.window, key), getattr(b.window, key)), key

@@ -231,16 +231,27 @@ def _load_cost_seconds(job: WindowJob) -> float:
 
 def load_jobs(jobs: Sequence[WindowJob], workers: Optional[int] = None) -> list:
     """Read and prepare the windows of ``jobs`` (FASTA / qualities -> compact tensors, seeded initial
-    states).  For large windows this is host work of the same order as the GPU run itself (N x K
-    Dirichlet draws per restart), so it can be spread over worker processes the way the reference
-    spreads its windows (shotgun.py:527-538: ``Pool(max_proc)``).  ``workers`` = None: a pool of
-    cpu_count() - 1 processes if the estimated serial time exceeds a few seconds, else in this process;
-    0 or 1: in this process.  Workers are spawned (not forked: the parent may hold CUDA and threads),
-    never touch CUDA, and give results identical to loading serially."""
+    states).  This is host work of the same order as the GPU run itself, so it is spread over the host
+    cores the way the reference spreads its windows (shotgun.py:527-538: ``Pool(max_proc)``):
+    ``workers`` = None picks by estimated serial time -- a pool of cpu_count() - 1 spawned processes
+    above a few seconds (large windows: N x K Dirichlet draws per restart), otherwise a handful of
+    threads (the native reader, NumPy's loops and file reads release the GIL; 20 -> 7 ms per
+    5 000-read window on 8 cores); 0 or 1: in this process; n > 1: n processes.  Workers never touch
+    CUDA (spawned, not forked: the parent may hold CUDA and threads); results are identical to
+    loading serially."""
     jobs = list(jobs)
     todo = [j for j in jobs if j.window is None]
+    cores = os.cpu_count() or 2
     if workers is None:
-        workers = max(1, (os.cpu_count() or 2) - 1) if sum(_load_cost_seconds(j) for j in todo) > 8.0 else 1
+        if sum(_load_cost_seconds(j) for j in todo) > 8.0:
+            workers = max(1, cores - 1)
+        else:
+            if len(todo) >= 4 and cores > 2:
+                from concurrent.futures import ThreadPoolExecutor
+                with ThreadPoolExecutor(min(8, cores - 1)) as ex:
+                    list(ex.map(_load_one, todo))
+                return jobs
+            workers = 1
     workers = min(workers, len(todo))
     if workers <= 1:
         for j in todo:

@@ -23,6 +23,11 @@ Fixtures:
                                   on the expected support files above, plus random reference /
                                   haplotype pairs (deletions, inserted 'X' columns) through
                                   _compare_ref_to_read and __mutations_in_haplotype
+  lep_finish/                     a learn_error_params window run to the end of its loop (the reference's
+                                  update_eqs.update / elbo_eqs.compute_elbo under the as-written control
+                                  flow of learn_error_params/cavi.py:135-199; the shipped driver raises) and
+                                  finished by the UNMODIFIED analyze_results.summarize_results /
+                                  haplotypes_to_fasta / correct_reads (learn_error_params/analyze_results.py)
   bam_windows/                    windows with real bases and qualities cut from the reference's
                                   BAM fixtures tests/data_2,3,6,7 (oracle/bam_windows.py) and the
                                   files run_dpm_mfa.main writes for them
@@ -353,6 +358,86 @@ def golden_data4():
         json.dump(meta, fh, indent=1)
 
 
+def golden_lep_finish():
+    """learn_error_params end to end.  The shipped lep driver raises (TypeError / NameError, SURVEY.md
+    section 8(a) L-C1), so the loop is driven here exactly as learn_error_params/cavi.py:135-199 is
+    written (minus the appends to undefined lists), with the reference's own update_eqs.update and
+    elbo_eqs.compute_elbo; the finishing steps and both writers are the unmodified reference functions."""
+    from viloca.local_haplotype_inference.learn_error_params import analyze_results, elbo_eqs, initialization
+    from viloca.local_haplotype_inference.learn_error_params import preparation, update_eqs
+    d = os.path.join(GOLD, "lep_finish")
+    os.makedirs(d, exist_ok=True)
+    meta = {}
+    for name, (wseed, n_raw, length, called, K, seed, unique) in {
+        "a": (41, 70, 40, 34, 12, 27, True),
+        "b": (43, 50, 32, None, 8, 5, False),
+    }.items():
+        codes, quals, ref = small_window(wseed, n_raw, length, called=called)
+        codes[7] = codes[2]; codes[11] = codes[2]; codes[30] = codes[4]; codes[31] = codes[4]      # duplicates
+        stem = f"w-LEP{name}-1-{length}"
+        write_window_files(d, stem, codes, quals, ref)
+        os.remove(os.path.join(d, stem + ".qualities.npy"))          # the mode reads no qualities
+        f_reads, f_ref = os.path.join(d, stem + ".reads.fas"), os.path.join(d, stem + ".ref.fas")
+        reference_seq, _ = preparation.load_reference_seq(f_ref)
+        reference_binary = preparation.reference2binary(reference_seq, "ACGT-")
+        reads_list = preparation.load_fasta2reads_list(f_reads, "ACGT-", unique)
+        reads_seq_binary, reads_weights = preparation.reads_list_to_array(reads_list)
+        st0 = initialization.draw_init_state(K, 1e-4, "ACGT-", reads_list, reference_binary, default_rng(seed=seed))
+        st0.update({"lnB_alpha0": lnB(st0["alpha"]), "betaln_a0_b0": betaln(st0["gamma_a"], st0["gamma_b"]),
+                    "betaln_c0_d0": betaln(st0["theta_c"], st0["theta_d"])})
+        it, n_updates, converged, message, history, cur = 0, 0, False, "", [], st0
+        while (converged is False) or (it < 10):
+            if it <= 1:
+                cur.update({"digamma_alpha_sum": digamma(cur["alpha"].sum(axis=0)),
+                            "digamma_a_b_sum": digamma(cur["gamma_a"] + cur["gamma_b"]),
+                            "digamma_c_d_sum": digamma(cur["theta_c"] + cur["theta_d"])})
+            cur = update_eqs.update(reads_seq_binary, reads_weights, reads_list, reference_binary, st0, cur)
+            elbo = elbo_eqs.compute_elbo(reads_weights, reads_seq_binary, reference_binary, st0, cur)
+            n_updates += 1
+            if it % 2 == 0:
+                history.append(elbo)
+            if it > 1:
+                if np.isnan(elbo):
+                    message = "Error: ELBO is nan."
+                    break
+                elif (history[-2] > elbo) and np.abs(elbo - history[-2]) > 1e-08:
+                    message = "Error: ELBO is decreasing."
+                    break
+                elif np.abs(elbo - history[-2]) < 1e-03:
+                    converged = True
+                    it += 1
+                    message = "ELBO converged."
+                else:
+                    it = 0
+            cur.update({"elbo": elbo})
+            it += 1
+        cur.update({"elbo": elbo})
+        summary = analyze_results.summarize_results(cur, "ACGT-", reads_seq_binary, reads_weights, reads_list,
+                                                    reference_binary, reference_seq)
+        cur.update(summary)
+        analyze_results.haplotypes_to_fasta(cur, os.path.join(d, f"expected_{name}.reads-support.fas"))
+        analyze_results.correct_reads(cur, os.path.join(d, f"expected_{name}.reads-cor.fas"))
+        n_hap = len([k for k in summary if k.startswith("haplotype")])
+        meta[name] = {
+            "stem": stem, "K": K, "seed": seed, "unique": unique, "n_rows": len(reads_list),
+            "n_updates": n_updates, "n_iterations": int(it), "exit_message": message, "elbo": float(elbo),
+            "history_elbo": [float(x) for x in history],
+            "haplotypes": [summary[f"haplotype{k}"] for k in range(n_hap)],
+            "posteriors": [float(summary[f"approximatePosterior{k}"]) for k in range(n_hap)],
+            "weights": [int(summary[f"weight{k}"]) for k in range(n_hap)],
+            "assigned_unique": [list(summary[f"assignedUniqueReads{k}"]) for k in range(n_hap)],
+            "assigned_all": [list(summary[f"assignedReads{k}"]) for k in range(n_hap)],
+        }
+        np.savez_compressed(os.path.join(d, f"state_{name}.npz"), mean_cluster=cur["mean_cluster"],
+                            mean_haplo=cur["mean_haplo"], mean_log_theta=np.array(cur["mean_log_theta"]),
+                            mean_log_gamma=np.array(cur["mean_log_gamma"]), alpha=cur["alpha"])
+        print(f"lep_finish {name}: {n_updates} updates, {message} elbo {elbo}, {n_hap} haplotypes, weights {meta[name]['weights']}")
+    import numpy, scipy
+    meta["versions"] = {"numpy": numpy.__version__, "scipy": scipy.__version__}
+    with open(os.path.join(d, "expected.json"), "w") as fh:
+        json.dump(meta, fh, indent=1)
+
+
 BAM_WINDOWS = [
     # name, BAM, reference FASTA, start (0-based), length, max reads, n_starts, K, seed
     ("hiv_3120", "data_2/REF_aln.bam", "data_2/cohort_consensus.fasta", 3120, 201, 300, 1, 100, 42),
@@ -498,6 +583,7 @@ if __name__ == "__main__":
     golden_init()
     golden_prep()
     golden_data4()
+    golden_lep_finish()
     golden_bam_windows()
     golden_snv()
     print("wrote", GOLD)

@@ -66,10 +66,14 @@ def scalars_of(state, mode):
 
 
 def rel_err(a, b, floor=1e-290):
-    """max relative error over entries whose reference magnitude is above ``floor``."""
+    """max relative error over entries whose reference magnitude is above ``floor``; where the
+    reference is below it (exact zeros, deep subnormals) the value must be below ``1e10 * floor`` too,
+    otherwise the error is infinite (a non-zero where the reference has a zero is never ignored)."""
     a = np.asarray(a, dtype=np.float64)
     b = np.asarray(b, dtype=np.float64)
     mask = np.abs(b) > floor
+    if (np.abs(a[~mask]) > 1e10 * floor).any() or np.isnan(a).any() != np.isnan(b).any():
+        return float("inf")
     if not mask.any():
         return 0.0
     return float(np.max(np.abs(a[mask] - b[mask]) / np.abs(b[mask])))

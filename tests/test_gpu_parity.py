@@ -556,6 +556,49 @@ def test_lep_entry_point_writes_outputs(golden_dir, tmp_path):
     assert os.path.getsize(out_dir + stem + ".reads-cor.fas") > 0
 
 
+@pytest.mark.parametrize("name", ["a", "b"])
+def test_lep_entry_point_reproduces_reference_files(golden_dir, tmp_path, name):
+    """learn_error_params through the drop-in entry point against files written by the UNMODIFIED
+    analyze_results.summarize_results / haplotypes_to_fasta / correct_reads (tests/golden/lep_finish:
+    the reference's equations under its as-written loop): identical haplotypes, ids, ave_reads and
+    corrected reads, posteriors to 1e-9; the device finishing contraction runs in lep mode."""
+    from viloca_b200.local_haplotype_inference.learn_error_params import run_dpm_mfa
+    d = os.path.join(golden_dir, "lep_finish")
+    meta = _json_file(os.path.join(d, "expected.json"))[name]
+    stem = meta["stem"]
+    out_dir = str(tmp_path) + "/"
+    job = dict(freads_in=os.path.join(d, stem + ".reads.fas"), fref_in=os.path.join(d, stem + ".ref.fas"),
+               output_dir=out_dir, n_starts=1, K=meta["K"], alpha0=0.0001, unique_modus=meta["unique"], seed=meta["seed"])
+    (state, result), = run_dpm_mfa.main_batch([job])
+    assert (result["n_iterations"], result["exit_message"]) == (meta["n_iterations"], meta["exit_message"])
+    assert br.rel_err(np.array(result["history_elbo"]), np.array(meta["history_elbo"])) < ENG_TOL
+    got = _parse_support(out_dir + stem + ".reads-support.fas")
+    exp = _parse_support(os.path.join(d, f"expected_{name}.reads-support.fas"))
+    assert [(i, s, w) for i, s, _, w in got] == [(i, s, w) for i, s, _, w in exp]
+    for (_, _, pg, _), (_, _, pe, _) in zip(got, exp):
+        assert abs(pg - pe) <= ENG_TOL * abs(pe) + 1e-300
+        assert (pg >= 0.9) == (pe >= 0.9)
+    assert _text(out_dir + stem + ".reads-cor.fas") == _text(os.path.join(d, f"expected_{name}.reads-cor.fas"))
+    n_hap = len(meta["haplotypes"])
+    assert [state[f"haplotype{k}"] for k in range(n_hap)] == meta["haplotypes"]
+    assert [state[f"weight{k}"] for k in range(n_hap)] == meta["weights"]
+    assert [state[f"assignedUniqueReads{k}"] for k in range(n_hap)] == meta["assigned_unique"]
+    assert [state[f"assignedReads{k}"] for k in range(n_hap)] == meta["assigned_all"]
+    assert br.rel_err(np.array([state[f"approximatePosterior{k}"] for k in range(n_hap)]), np.array(meta["posteriors"])) < ENG_TOL
+    # the same run through the reference-shaped numeric seam (learn_error_params/cavi.py:71-85)
+    from viloca_b200.local_haplotype_inference.learn_error_params import cavi, preparation
+    reference_seq, _ = preparation.load_reference_seq(job["fref_in"])
+    reference_binary = preparation.reference2binary(reference_seq, "ACGT-")
+    reads_list = preparation.load_fasta2reads_list(job["freads_in"], "ACGT-", meta["unique"])
+    reads_seq_binary, reads_weights = preparation.reads_list_to_array(reads_list)
+    init, cur, res = cavi.run_cavi(meta["K"], 0.0001, "ACGT-", reference_binary, reference_seq, reads_list, reads_seq_binary,
+                                   reads_weights, 0, out_dir, False, np.random.default_rng(seed=meta["seed"]), meta["seed"])
+    assert (res["n_iterations"], res["exit_message"], res["exitflag"]) == (meta["n_iterations"], meta["exit_message"], 0)
+    assert [cur[f"haplotype{k}"] for k in range(n_hap)] == meta["haplotypes"]
+    assert [res[f"weight{k}"] for k in range(n_hap)] == meta["weights"]
+    assert set(init) >= {"alpha", "mean_log_pi", "theta_c", "theta_d", "mean_log_theta", "gamma_a", "gamma_b", "mean_haplo", "mean_cluster"}
+
+
 def test_reference_signature_run_cavi(golden_dir):
     """cavi.run_cavi with the reference's dense arguments (use_quality_scores/cavi.py:70-84)."""
     from viloca_b200.local_haplotype_inference.use_quality_scores import cavi

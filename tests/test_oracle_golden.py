@@ -183,3 +183,41 @@ def test_init_draw_order(golden_dir):
             assert np.array_equal(z, g[f"{mode}_{seed}_mean_cluster"])
             n = 4 if mode == "uqs" else 8
             assert np.array_equal(sc[:n], g[f"{mode}_{seed}_scalars"])
+
+
+@pytest.mark.parametrize("name", ["a", "b"])
+def test_lep_loop_and_finishing_match_reference(golden_dir, name):
+    """learn_error_params end to end (tests/golden/lep_finish, generated by oracle/make_golden.py from the
+    unmodified update_eqs / elbo_eqs under the as-written loop and the unmodified
+    analyze_results.summarize_results): the oracle's loop takes the same number of updates and leaves
+    the same ELBO history; its finishing steps give the same haplotypes, weights and assignments."""
+    from viloca_b200.local_haplotype_inference import _common
+    d = os.path.join(golden_dir, "lep_finish")
+    meta = _json_file(os.path.join(d, "expected.json"))[name]
+    ids, seqs = _common.read_window_fasta(os.path.join(d, meta["stem"] + ".reads.fas"))
+    p = _common.prepare_reads(ids, seqs, None, "ACGT-", meta["unique"])
+    assert p.codes.shape[0] == meta["n_rows"]
+    ref_codes, _, _ = _common.load_reference(os.path.join(d, meta["stem"] + ".ref.fas"), "ACGT-", upper=False)
+    reads = orc.onehot_from_codes(p.codes)
+    ref = orc.onehot_from_codes(ref_codes)
+    w = np.asarray(p.weights, dtype=np.float64)
+    init = orc.draw_init_state("lep", meta["K"], 1e-4, p.codes.shape[1], p.codes.shape[0], ref,
+                               np.random.default_rng(meta["seed"]))
+    traj = orc.run("lep", w, ref, reads, init)
+    assert (traj.n_updates, traj.n_iterations, traj.exit_message) == (meta["n_updates"], meta["n_iterations"], meta["exit_message"])
+    np.testing.assert_allclose(np.array(traj.history_elbo), np.array(meta["history_elbo"]), rtol=1e-13)
+    st = traj.state
+    g = np.load(os.path.join(d, f"state_{name}.npz"))
+    np.testing.assert_allclose(st["mean_cluster"], g["mean_cluster"], rtol=1e-12, atol=0)
+    np.testing.assert_allclose(st["mean_haplo"], g["mean_haplo"], rtol=1e-12, atol=0)
+    groups = orc.unique_haplotypes(st["mean_haplo"])
+    assert [s for s, _ in groups] == meta["haplotypes"]
+    merged = orc.merge_clusters(st["mean_cluster"], groups)
+    h_m = orc.lep_update_mean_haplo(reads, w, ref, merged, st["mean_log_theta"], st["mean_log_gamma"])
+    np.testing.assert_allclose(np.array(orc.haplotype_posteriors(h_m, groups)), np.array(meta["posteriors"]), rtol=1e-11)
+    member, weight = orc.assignments(merged, w)
+    assert [int(x) for x in weight] == meta["weights"]
+    for j in range(len(groups)):
+        rows = np.nonzero(member[:, j])[0]
+        assert [p.read_ids[n][0] for n in rows] == meta["assigned_unique"][j]
+        assert [rid for n in rows for rid in p.read_ids[n]] == meta["assigned_all"][j]

@@ -10,7 +10,8 @@ from viloca_b200 import _capi as capi, engine, synthetic  # noqa: E402
 
 name = sys.argv[1] if len(sys.argv) > 1 else "hiv5k_uqs"
 nw = int(sys.argv[2]) if len(sys.argv) > 2 and int(sys.argv[2]) > 0 else None
-wins = [w.pin() for w in synthetic.make_workload(name, nw)]
+idx = [int(x) for x in os.environ["VL_WINDOWS"].split(",")] if os.environ.get("VL_WINDOWS") else None   # e.g. VL_WINDOWS=80,83
+wins = [w.pin() for w in synthetic.make_workload(name, nw, indices=idx)]
 H = [("wait published", 6), ("prologue", 0), ("operand loop", 1), ("warp reduction", 2), ("sparse", 3),
      ("softmax epilogue", 4), ("sums", 5), ("signal", 7)]
 Z = [("wait published", 14), ("wait haplotype tiles", 15), ("prologue", 8), ("operand loop", 9), ("sparse", 10),

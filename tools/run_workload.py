@@ -20,7 +20,8 @@ if os.environ.get("VL_N_READS"):
     kw["n_reads"] = int(os.environ["VL_N_READS"])
 if os.environ.get("VL_MAX_ITER"):
     kw["max_iter"] = int(os.environ["VL_MAX_ITER"])
-wins = [w.pin() for w in synthetic.make_workload(name, nw, **kw)]
+idx = [int(x) for x in os.environ["VL_WINDOWS"].split(",")] if os.environ.get("VL_WINDOWS") else None   # e.g. VL_WINDOWS=80,83
+wins = [w.pin() for w in synthetic.make_workload(name, nw, indices=idx, **kw)]
 print(f"{name}: {len(wins)} windows, N_unique {[w.n_reads for w in wins[:4]]}, L {wins[0].length}, restarts {wins[0].n_starts}",
       flush=True)
 resident = os.environ.get("VL_RESIDENT", "0") != "0"

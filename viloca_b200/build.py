@@ -42,17 +42,24 @@ def _stale(target: str, deps: list[str]) -> bool:
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force: bool = False, verbose: bool = False, profile: bool = False) -> str:
-    """``profile=True`` compiles the resident kernel's cycle counters in (vl_debug_counters)."""
+def build(force: bool = False, verbose: bool = False, profile: bool = False, defines=(), tag: str = "") -> str:
+    """``profile=True`` compiles the per-phase cycle counters in (vl_debug_counters) and builds
+    ``libviloca_b200_prof.so`` next to the product library (select it with VILOCA_B200_LIB);
+    ``defines`` / ``tag`` build an experimental variant ``libviloca_b200_<tag>.so`` the same way."""
     os.makedirs(LIB_DIR, exist_ok=True)
     headers = [os.path.normpath(os.path.join(CSRC, h)) for h in HEADERS]
+    if profile and not tag:
+        tag = "prof"
+    suffix = ("_" + tag) if tag else ""
+    lib_path = os.path.join(LIB_DIR, "libviloca_b200" + suffix + ".so")
+    extra_defs = ["-D" + d for d in defines]
     objs, jobs = [], []
     for src in SOURCES:
         src_path = os.path.join(CSRC, src)
-        obj = os.path.join(LIB_DIR, src.replace(".cu", ".o"))
+        obj = os.path.join(LIB_DIR, src.replace(".cu", suffix + ".o"))
         objs.append(obj)
         if force or _stale(obj, [src_path] + headers):
-            cmd = [_nvcc()] + NVCC_FLAGS + (["-DVL_RS_PROFILE"] if profile else []) + EXTRA_FLAGS.get(src, []) + \
+            cmd = [_nvcc()] + NVCC_FLAGS + (["-DVL_RS_PROFILE"] if profile else []) + extra_defs + EXTRA_FLAGS.get(src, []) + \
                 ["-c", src_path, "-o", obj]
             if verbose:
                 cmd.insert(1, "-Xptxas=-v")
@@ -61,15 +68,17 @@ def build(force: bool = False, verbose: bool = False, profile: bool = False) -> 
     for cmd, proc in jobs:
         if proc.wait() != 0:
             raise subprocess.CalledProcessError(proc.returncode, cmd)
-    if force or _stale(LIB_PATH, objs):
-        cmd = [_nvcc(), "-shared", "-o", LIB_PATH] + objs + ["-lcudart_static", "-lrt", "-lpthread", "-ldl",
+    if force or _stale(lib_path, objs):
+        cmd = [_nvcc(), "-shared", "-o", lib_path] + objs + ["-lcudart_static", "-lrt", "-lpthread", "-ldl",
                                                            "-Xlinker", "--no-undefined"]   # an unresolved symbol fails here, not at load time
         if verbose:
             print(" ".join(cmd), file=sys.stderr)
         subprocess.run(cmd, check=True)
-    return LIB_PATH
+    return lib_path
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv or "--profile" in sys.argv, verbose="-v" in sys.argv,
-                profile="--profile" in sys.argv))
+    _defs = [a[2:] for a in sys.argv[1:] if a.startswith("-D")]
+    _tag = next((a.split("=", 1)[1] for a in sys.argv[1:] if a.startswith("--tag=")), "")
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv, profile="--profile" in sys.argv,
+                defines=_defs, tag=_tag))

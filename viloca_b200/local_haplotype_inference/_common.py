@@ -193,7 +193,7 @@ class WindowJob:
         return self.output_dir + window_id + "-"
 
     def load(self):
-        from ..engine import Window
+        from ..window import Window
         if self.alphabet != ALPHABET:
             raise ValueError("the engine is built for the alphabet 'ACGT-' (B = 5)")
         quals = None
@@ -306,12 +306,15 @@ def summarize(job: WindowJob, batch, window_index: int, restart: int, state: dic
         posterior = np.cumprod(vals)[-1] if len(vals) else 1     # left-to-right product
         rows = np.nonzero(member[:, j])[0]
         assigned = [rid for n in rows for rid in p.read_ids[n]]
+        # uqs lists every raw read in both keys (analyze_results.py:121-133); lep's unique list holds
+        # only the representative id of each row (learn_error_params/analyze_results.py:236-243)
+        assigned_unique = [p.read_ids[n][0] for n in rows] if job.mode == "lep" else list(assigned)
         weight = mult[rows].sum()
         weight = int(weight) if job.unique_modus else int(round(float(weight)))
         summary.update({
             "haplotype" + str(j): seq,
             "approximatePosterior" + str(j): posterior,
-            "assignedUniqueReads" + str(j): list(assigned),
+            "assignedUniqueReads" + str(j): assigned_unique,
             "assignedReads" + str(j): list(assigned),
             "weight" + str(j): weight,
         })

@@ -12,7 +12,7 @@ from dataclasses import dataclass
 import numpy as np
 
 from . import init_state, tensors
-from .engine import Window
+from .window import Window
 
 GAP = 4          # code of '-'
 CODE_N = tensors.CODE_N
@@ -140,7 +140,9 @@ def make_window(spec: WorkloadSpec, index: int, master_seed: int = 0, n_reads: i
     return win
 
 
-def make_workload(name: str, n_windows: int | None = None, master_seed: int = 0, **kw) -> list:
+def make_workload(name: str, n_windows: int | None = None, master_seed: int = 0, indices=None, **kw) -> list:
+    """The first ``n_windows`` windows of a workload (default: all), or the windows ``indices``."""
     spec = WORKLOADS[name]
-    n = spec.n_windows if n_windows is None else n_windows
-    return [make_window(spec, i, master_seed, **kw) for i in range(n)]
+    if indices is None:
+        indices = range(spec.n_windows if n_windows is None else n_windows)
+    return [make_window(spec, i, master_seed, **kw) for i in indices]

@@ -124,7 +124,7 @@ def profiled_run(batch, ops):
     vl_batch_run.  Returns per-kernel totals over the run and over its all-clusters-live start."""
     batch.upload()
     tot = {k: {"ms": 0.0, "launches": 0, "executed": 0.0, "algorithmic": 0.0, "dense_equivalent": 0.0, "bytes": 0.0}
-           for k in ("haplo", "cluster", "scalar", "resident")}
+           for k in ("haplo", "cluster")}
     first = None
     n_chunks = 0
     while True:
@@ -142,9 +142,6 @@ def profiled_run(batch, ops):
             for key in ("executed", "algorithmic", "dense_equivalent"):
                 tot[k][key] += n * 0.5 * (wb[key] + wa[key])
             tot[k]["bytes"] += n * 0.5 * (wb["bytes_" + k] + wa["bytes_" + k])
-        for k in ("scalar", "resident"):
-            tot[k]["ms"] += prof[k][0]
-            tot[k]["launches"] += prof[k][1]
         if n_chunks == 0:
             first = {k: dict(v) for k, v in tot.items()}
         n_chunks += 1

@@ -153,17 +153,9 @@ void vl_batch_destroy(vl_batch* batch);
  */
 #define VL_OPT_SKIP_DEAD 1
 /*
- * VL_OPT_RESIDENT (default 0): 1 lets restarts whose live clusters fit 4 tiles and whose operand
- * fits one SM's shared memory iterate inside a persistent one-CTA-per-restart kernel (one pass
- * over the operand per update, no launches); 0 keeps every restart on the general-path
- * kernels (haplotype tiles + read tiles of every update).  Same results to rounding; pays off
- * when the batch holds many more restarts than the GPU has SMs.  May be
- * changed between runs.
- */
-#define VL_OPT_RESIDENT 2
-/*
  * VL_OPT_FUSED_CHUNKS (default 1): vl_batch_run enqueues a whole chunk of updates of a kernel
- * class as ONE launch whose blocks wait on per-restart counters in device memory, instead of two
+ * class as ONE launch of persistent worker CTAs that claim tiles from per-restart scheduling words in
+ * device memory (launches of different classes side by side on their own streams), instead of two
  * launches per update; 0 restores the per-update launches (vl_batch_step and
  * vl_batch_profile_step always use those).  Same arithmetic, bit-identical results.
  */
@@ -209,8 +201,7 @@ int vl_batch_merge_haplo(vl_batch* batch, int32_t window, int32_t restart,
  * Like vl_batch_step, but brackets every launch with CUDA events on the launching stream and
  * returns the summed device time per kernel (ms) and the launch counts, arrays of 4:
  * [0] haplotype update, [1] responsibility update incl. the scalar update its last CTA per
- * restart performs (general path, one launch each per update), [2] unused (0), [3] resident
- * kernel (one launch does all n_updates of its restarts).
+ * restart performs (one launch each per update), [2], [3] unused (0).
  * Used by bench.py for the live roofline numbers; not a fast path.
  */
 int vl_batch_profile_step(vl_batch* batch, int32_t n_updates, double* ms_out, int64_t* n_out);
@@ -263,9 +254,8 @@ int vl_debug_occupancy(int32_t device, int32_t kernel_class, int32_t mode, int32
                        int32_t* smem_bytes, int32_t* registers);
 
 /*
- * Development aid: per-phase cycle counters, 36 values: [0..15] one CTA of the resident kernel,
- * [16..35] tile 0 of restart 0 in the general-path kernels (slot meanings in vl_resident.cu /
- * vl_kernels.cu).  Fails unless the library was built with -DVL_RS_PROFILE
+ * Development aid: per-phase cycle counters, 36 values: [0..15] unused (0), [16..35] tile 0 of
+ * restart 0 (slot meanings in vl_kernels.cu).  Fails unless the library was built with -DVL_RS_PROFILE
  * (python -m viloca_b200.build --profile).
  */
 int vl_debug_counters(uint64_t* out36, int32_t reset);

@@ -298,15 +298,14 @@ def test_free_running_against_oracle(mode, n_raw, L, K):
 
 @pytest.mark.parametrize("mode,n_raw,L,K,R", [("uqs", 400, 201, 100, 1), ("lep", 300, 120, 24, 1), ("uqs", 300, 150, 30, 3),
                                               ("lep", 400, 201, 100, 2), ("uqs", 90, 40, 8, 1)])
-def test_resident_kernel_against_oracle(mode, n_raw, L, K, R):
-    """The persistent one-CTA-per-restart kernel (VL_OPT_RESIDENT): restarts enter it as soon as
-    their layout fits 4 cluster tiles (from the first update when K <= 32) and may alternate with
-    the per-iteration kernels at chunk boundaries; same trajectories as the reference."""
+def test_small_shapes_and_restarts_against_oracle(mode, n_raw, L, K, R):
+    """Small windows (one read tile, K below one slot tile) and several restarts per window: every
+    restart follows the reference's trajectory."""
     from viloca_b200 import synthetic
     engine = _engine()
     spec = dataclasses.replace(_spec(mode, K, int(L * 0.75)), n_starts=R)
     win = synthetic.make_window(spec, 5, n_reads=n_raw, length=L)
-    with engine.CaviBatch([win], resident=True) as b:
+    with engine.CaviBatch([win]) as b:
         b.upload()
         b.run()
         for r in range(R):
@@ -323,8 +322,8 @@ def test_resident_kernel_against_oracle(mode, n_raw, L, K, R):
 
 
 def test_fused_chunks_equal_per_update_launches():
-    """vl_batch_run's one-launch-per-chunk kernel (blocks waiting on per-restart counters) does
-    the same arithmetic as two launches per update: bit-identical results."""
+    """vl_batch_run's one-launch-per-chunk kernel (persistent workers that claim tiles from per-restart
+    scheduling words) does the same arithmetic as two launches per update: bit-identical results."""
     from viloca_b200 import synthetic
     engine = _engine()
     shapes = [("uqs", 400, 201, 100), ("lep", 200, 90, 40), ("uqs", 150, 64, 12), ("uqs", 1, 9, 5), ("lep", 300, 130, 128)]

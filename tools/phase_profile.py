@@ -20,8 +20,7 @@ def main():
     nw = int(sys.argv[2]) if len(sys.argv) > 2 else None
     wins = synthetic.make_workload(name, nw)
     rows = []
-    resident = os.environ.get("VL_RESIDENT", "0") != "0"
-    with engine.CaviBatch(wins, resident=resident) as b:
+        with engine.CaviBatch(wins) as b:
         b.upload()
         done = 0
         for upto in (0, 8, 32, 128, 512, 1024, 2048, 3072, 4096, 6144):
@@ -41,7 +40,6 @@ def main():
             row = {"update": upto, "running": int(run.sum()), "mean_slots": float(st[run, 2].mean()),
                    "mean_tiles": float(st[run, 1].mean()),
                    "haplo_us": 1e3 * prof["haplo"][0] / 4, "cluster_us": 1e3 * prof["cluster"][0] / 4,
-                   "scalar_us": 1e3 * prof["scalar"][0] / 4, "resident_us": 1e3 * prof["resident"][0] / 4,
                    "launches_per_update": sum(v[1] for v in prof.values()) / 4,
                    "step_wall_us_per_update": 1e6 * dt / max(upto, 1) if dt else None}
             rows.append(row)

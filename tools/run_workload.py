@@ -3,7 +3,7 @@
     python tools/run_workload.py [workload] [n_windows] [repeats]
 
 Environment: VL_N_READS / VL_MAX_ITER override the raw reads per window and the iteration cap
-(bounded samples of the large workloads), VL_RESIDENT / VL_FUSED select engine options.
+(bounded samples of the large workloads), VL_FUSED=0 selects the per-phase launches.
 """
 import os
 import sys
@@ -24,9 +24,8 @@ idx = [int(x) for x in os.environ["VL_WINDOWS"].split(",")] if os.environ.get("V
 wins = [w.pin() for w in synthetic.make_workload(name, nw, indices=idx, **kw)]
 print(f"{name}: {len(wins)} windows, N_unique {[w.n_reads for w in wins[:4]]}, L {wins[0].length}, restarts {wins[0].n_starts}",
       flush=True)
-resident = os.environ.get("VL_RESIDENT", "0") != "0"
 fused = os.environ.get("VL_FUSED", "1") != "0"
-with engine.CaviBatch(wins, resident=resident, fused_chunks=fused) as b:
+with engine.CaviBatch(wins, fused_chunks=fused) as b:
     for _ in range(rep):
         t0 = time.perf_counter(); b.upload(); t1 = time.perf_counter()
         n = b.run(); t2 = time.perf_counter()

@@ -12,7 +12,6 @@ from . import build as _build
 
 ABI_VERSION = 2
 OPT_SKIP_DEAD = 1
-OPT_RESIDENT = 2
 OPT_FUSED_CHUNKS = 3
 N_BASES = 5
 CODE_N = 255

@@ -14,7 +14,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB_DIR = os.path.join(HERE, "lib")
 LIB_PATH = os.path.join(LIB_DIR, "libviloca_b200.so")
-SOURCES = ["vl_kernels.cu", "vl_resident.cu", "vl_api.cu", "vl_prepare.cu"]
+SOURCES = ["vl_kernels.cu", "vl_api.cu", "vl_prepare.cu"]
 HEADERS = ["vl_device.cuh", "vl_cavi.cuh", "vl_launch.h", os.path.join("..", "..", "include", "viloca_b200.h")]
 # vl_kernels.cu: vl_chunk_kernel runs many dependent updates in one launch, so state written by
 # one CTA is read by later CTAs of the same launch, possibly on an SM whose L1 still holds the old

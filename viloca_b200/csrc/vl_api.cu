@@ -58,7 +58,7 @@ struct Layout {
   int n_problems = 0;
   size_t data_begin = 0, data_end = 0;   // zero-filled on upload
   size_t probs = 0, states = 0, done = 0, pstat = 0;
-  size_t htiles = 0, ztiles = 0, rlist = 0, cbase = 0, hticket = 0, zticket = 0;
+  size_t htiles = 0, ztiles = 0, rlist = 0, cbase = 0, ctl = 0, nlive = 0;
   size_t raw_codes = 0, raw_lt = 0, raw_lo = 0;      // staging of one window's raw arrays
   size_t export_h = 0, export_z = 0;
   size_t tmp_z = 0, tmp_wz = 0, tmp_h = 0, tmp_g = 0, tmp_gm = 0, tmp_hpart = 0, tmp_group = 0, tmp_prob = 0,
@@ -261,8 +261,8 @@ int build_layout(const vl_window_desc* w, int n, Layout& lay, std::string& err) 
   lay.ztiles = take(lay.n_ztiles_total * sizeof(int2));
   lay.rlist = take((size_t)lay.n_problems * sizeof(int));
   lay.cbase = take((size_t)lay.n_problems * sizeof(int));
-  lay.hticket = take((size_t)lay.n_problems * sizeof(int));
-  lay.zticket = take((size_t)lay.n_problems * sizeof(int));
+  lay.ctl = take((size_t)lay.n_problems * sizeof(VlCtl));
+  lay.nlive = take(VL_N_CLASSES * 4 * sizeof(int));
   lay.raw_codes = take(max_nl);
   lay.raw_lt = take(max_nl * 8);
   lay.raw_lo = take(max_nl * 8);
@@ -301,15 +301,20 @@ struct vl_batch {
   int2* h_htiles = nullptr; int2* h_ztiles = nullptr; int4* h_pstat = nullptr;
   int* h_rlist = nullptr;
   int* h_cbase = nullptr;
+  int* h_nlive = nullptr;
   unsigned char* h_arena = nullptr;    // pinned image of every window's small arrays (maps, sparse lists)
-  int n_res[2] = {};                   // restarts scheduled on the resident kernel, per mode
-  size_t off_res[2] = {}, smem_res[2] = {};
-  // general path: tile lists per kernel class and variant v = mode (bit 0: lep) + 2 * (window with split haplotype tiles)
-  int n_ht[VL_N_CLASSES][4] = {}, n_zt[VL_N_CLASSES][4] = {};
-  size_t off_ht[VL_N_CLASSES][4] = {}, off_zt[VL_N_CLASSES][4] = {};
+  // tile lists (per-phase launches) and restart lists (chunk launches) per kernel class and variant
+  // v = mode (bit 0: lep) + 2 * (window with split haplotype tiles)
+  int n_ht[VL_N_CLASSES][4] = {}, n_zt[VL_N_CLASSES][4] = {}, n_rs[VL_N_CLASSES][4] = {};
+  size_t off_ht[VL_N_CLASSES][4] = {}, off_zt[VL_N_CLASSES][4] = {}, off_rs[VL_N_CLASSES][4] = {};
+  int want_workers[VL_N_CLASSES][4] = {};   // tiles the restarts of a list can have in flight at once
   int n_sched = 0;
   bool sched_dirty = true;
-  int skip_dead = 1, resident = 0, fused = 1;
+  int skip_dead = 1, fused = 1;
+  cudaStream_t class_stream[VL_N_CLASSES * 4] = {};   // chunk launches of different classes run side by side
+  cudaEvent_t ev_fork = nullptr, ev_join[VL_N_CLASSES * 4] = {};
+  int occ[VL_N_CLASSES][4][2] = {};    // resident CTAs per SM of the chunk kernel (class, variant, deep), 0 = not asked yet
+  int n_sms = 148;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   double last_ms = 0.0;
   bool uploaded = false;
@@ -323,30 +328,27 @@ struct vl_batch {
 
 namespace {
 
-// Where the still-running restarts go next: the resident kernel (narrow layouts that fit one
-// SM's shared memory) or the general path, there grouped by kernel class (layout width) and mode.
+// Where the still-running restarts go next: grouped by kernel class (layout width), mode and
+// whether the window's haplotype tiles are split.  Tile lists serve the per-phase launches, restart
+// lists the chunk launches.
 int schedule(vl_batch* b) {
   const Layout& L = b->lay;
   std::vector<int2> ht[VL_N_CLASSES][4], zt[VL_N_CLASSES][4];
-  std::vector<int> res[2];
-  const size_t smem_limit = vl_resident_smem_limit();
+  std::vector<int> rs[VL_N_CLASSES][4];
   b->n_sched = 0;
-  b->smem_res[0] = b->smem_res[1] = 0;
+  for (int c = 0; c < VL_N_CLASSES; ++c)
+    for (int m = 0; m < 4; ++m) b->want_workers[c][m] = 0;
   for (int p : b->order) {
     const int4 st = b->pstat[p];
     if (st.x == 0) continue;
     const VlProblem& P = b->probs[p];
     const int cls = vl_class_of_tiles(st.y), m = P.mode == VL_MODE_LEP ? 1 : 0;
-    const int nct = P.NCs / VL_PT;
-    if (b->resident && st.y <= VL_RS_MAX_KT && nct <= VL_RS_MAX_CT && vl_resident_smem_bytes(nct, st.y) <= smem_limit) {
-      res[m].push_back(p);
-      b->smem_res[m] = std::max(b->smem_res[m], vl_resident_smem_bytes(nct, st.y));
-      continue;
-    }
     const int v = m + (P.n_hsplit > 1 ? 2 : 0);
     for (int sp = 0; sp < P.n_hsplit; ++sp)
       for (int t = 0; t < P.n_htiles; ++t) ht[cls][v].push_back(make_int2(p, vl_htile_id(t, sp, P.n_hsplit)));
     for (int t = 0; t < P.n_ztiles; ++t) zt[cls][v].push_back(make_int2(p, t));
+    rs[cls][v].push_back(p);
+    b->want_workers[cls][v] += std::max(P.n_htiles * P.n_hsplit, P.n_ztiles);
     ++b->n_sched;
   }
   size_t ho = 0, zo = 0, ro = 0;
@@ -354,32 +356,17 @@ int schedule(vl_batch* b) {
     for (int m = 0; m < 4; ++m) {
       b->n_ht[c][m] = (int)ht[c][m].size(); b->off_ht[c][m] = ho;
       b->n_zt[c][m] = (int)zt[c][m].size(); b->off_zt[c][m] = zo;
+      b->n_rs[c][m] = (int)rs[c][m].size(); b->off_rs[c][m] = ro;
       std::copy(ht[c][m].begin(), ht[c][m].end(), b->h_htiles + ho);
       std::copy(zt[c][m].begin(), zt[c][m].end(), b->h_ztiles + zo);
-      ho += ht[c][m].size(); zo += zt[c][m].size();
+      std::copy(rs[c][m].begin(), rs[c][m].end(), b->h_rlist + ro);
+      ho += ht[c][m].size(); zo += zt[c][m].size(); ro += rs[c][m].size();
     }
-  for (int m = 0; m < 2; ++m) {
-    b->n_res[m] = (int)res[m].size(); b->off_res[m] = ro;
-    std::copy(res[m].begin(), res[m].end(), b->h_rlist + ro);
-    ro += res[m].size();
-  }
   cudaStream_t s = b->stream;
   if (ho) VL_CUDA(cudaMemcpyAsync(b->dev<int2>(L.htiles), b->h_htiles, ho * sizeof(int2), cudaMemcpyHostToDevice, s));
   if (zo) VL_CUDA(cudaMemcpyAsync(b->dev<int2>(L.ztiles), b->h_ztiles, zo * sizeof(int2), cudaMemcpyHostToDevice, s));
   if (ro) VL_CUDA(cudaMemcpyAsync(b->dev<int>(L.rlist), b->h_rlist, ro * sizeof(int), cudaMemcpyHostToDevice, s));
   b->sched_dirty = false;
-  return 0;
-}
-
-// n_iter updates of the restarts scheduled on the resident kernel (each CTA iterates on its own)
-int launch_resident(vl_batch* b, int n_iter, int64_t* launches) {
-  const Layout& L = b->lay;
-  for (int m = 0; m < 2; ++m)
-    if (b->n_res[m] > 0) {
-      VL_CUDA(vl_launch_resident(m ? VL_MODE_LEP : VL_MODE_UQS, b->d_probs(), b->dev<int>(L.rlist) + b->off_res[m],
-                                 b->n_res[m], n_iter, b->smem_res[m], b->d_done(), b->d_pstat(), b->stream));
-      *launches += 1;
-    }
   return 0;
 }
 
@@ -401,28 +388,59 @@ int launch_phase(vl_batch* b, int phase, int64_t* launches) {
   return 0;
 }
 
-// n_iter updates of every scheduled restart with one launch per kernel class (vl_chunk_kernel)
+// n_iter updates of every scheduled restart: one launch of persistent workers per kernel class and
+// variant (vl_sched_kernel), the launches side by side on their own streams.  A launch gets as many
+// workers as its restarts can have tiles in flight, at most what fits the GPU; when several launches
+// together want more SMs than there are, each gets its share.
 int run_chunk_fused(vl_batch* b, int n_iter, int64_t* launches) {
   const Layout& L = b->lay;
   const int np = L.n_problems;
   for (int p = 0; p < np; ++p) b->h_cbase[p] = b->pstat[p].w;
   VL_CUDA(cudaMemcpyAsync(b->dev<int>(L.cbase), b->h_cbase, (size_t)np * sizeof(int), cudaMemcpyHostToDevice, b->stream));
-  VL_CUDA(cudaMemsetAsync(b->dev<int>(L.hticket), 0, (size_t)np * sizeof(int), b->stream));
-  VL_CUDA(cudaMemsetAsync(b->dev<int>(L.zticket), 0, (size_t)np * sizeof(int), b->stream));
-  if (launch_resident(b, n_iter, launches)) return 1;
+  VL_CUDA(cudaMemsetAsync(b->dev<VlCtl>(L.ctl), 0, (size_t)np * sizeof(VlCtl), b->stream));
+  struct Launch { int c, m, deep, occ, workers; double sms; };
+  std::vector<Launch> todo;
+  double sm_demand = 0.0;
   for (int c = 0; c < VL_N_CLASSES; ++c)
-    for (int m = 0; m < 4; ++m)
-      if (b->n_ht[c][m] > 0) {
-        VL_CUDA(vl_launch_chunk(c, (m & 1) ? VL_MODE_LEP : VL_MODE_UQS, m >> 1, b->d_probs(), b->dev<int2>(L.htiles) + b->off_ht[c][m],
-                                b->n_ht[c][m], b->dev<int2>(L.ztiles) + b->off_zt[c][m], b->n_zt[c][m], n_iter,
-                                b->dev<int>(L.cbase), b->dev<int>(L.hticket), b->dev<int>(L.zticket), b->d_done(), b->d_pstat(), b->stream));
-        *launches += 1;
+    for (int m = 0; m < 4; ++m) {
+      b->h_nlive[c * 4 + m] = b->n_rs[c][m];
+      if (b->n_rs[c][m] == 0) continue;
+      Launch l{c, m, b->want_workers[c][m] <= 2 * b->n_sms ? 1 : 0, 0, 0, 0.0};
+      int& occ = b->occ[c][m][l.deep];
+      if (occ == 0) {
+        int smem = 0, regs = 0;
+        VL_CUDA(vl_sched_occupancy(c, (m & 1) ? VL_MODE_LEP : VL_MODE_UQS, m >> 1, l.deep, &occ, &smem, &regs));
+        if (occ <= 0) return fail("the chunk kernel does not fit an SM");
       }
+      l.occ = occ;
+      l.workers = std::min(b->want_workers[c][m], occ * b->n_sms);
+      l.sms = (double)l.workers / occ;
+      sm_demand += l.sms;
+      todo.push_back(l);
+    }
+  if (todo.empty()) return 0;
+  VL_CUDA(cudaMemcpyAsync(b->dev<int>(L.nlive), b->h_nlive, VL_N_CLASSES * 4 * sizeof(int), cudaMemcpyHostToDevice, b->stream));
+  const double scale = sm_demand > b->n_sms ? b->n_sms / sm_demand : 1.0;
+  const bool fork = todo.size() > 1;
+  if (fork) VL_CUDA(cudaEventRecord(b->ev_fork, b->stream));
+  for (const Launch& l : todo) {
+    const int i = l.c * 4 + l.m;
+    cudaStream_t s = fork ? b->class_stream[i] : b->stream;
+    if (fork) VL_CUDA(cudaStreamWaitEvent(s, b->ev_fork, 0));
+    const int workers = std::max(1, std::min(l.workers, (int)(l.sms * scale * l.occ + 0.5)));
+    VL_CUDA(vl_launch_sched(l.c, (l.m & 1) ? VL_MODE_LEP : VL_MODE_UQS, l.m >> 1, b->d_probs(), b->dev<int>(L.rlist) + b->off_rs[l.c][l.m],
+                            b->n_rs[l.c][l.m], n_iter, b->dev<int>(L.cbase), b->dev<VlCtl>(L.ctl), b->dev<int>(L.nlive) + i,
+                            b->d_done(), b->d_pstat(), workers, l.deep, s));
+    *launches += 1;
+    if (fork) {
+      VL_CUDA(cudaEventRecord(b->ev_join[i], s));
+      VL_CUDA(cudaStreamWaitEvent(b->stream, b->ev_join[i], 0));
+    }
+  }
   return 0;
 }
 
 int run_iterations(vl_batch* b, int n_iter, int64_t* launches) {
-  if (launch_resident(b, n_iter, launches)) return 1;
   for (int it = 0; it < n_iter; ++it)
     for (int phase = 0; phase < 2; ++phase)
       if (launch_phase(b, phase, launches)) return 1;
@@ -572,6 +590,13 @@ int vl_batch_create(vl_batch** out, int32_t device, const vl_window_desc* window
   VL_CREATE_CUDA(cudaMallocHost(reinterpret_cast<void**>(&b->h_pstat), (size_t)L.n_problems * sizeof(int4)));
   VL_CREATE_CUDA(cudaMallocHost(reinterpret_cast<void**>(&b->h_rlist), (size_t)L.n_problems * sizeof(int)));
   VL_CREATE_CUDA(cudaMallocHost(reinterpret_cast<void**>(&b->h_cbase), (size_t)L.n_problems * sizeof(int)));
+  VL_CREATE_CUDA(cudaMallocHost(reinterpret_cast<void**>(&b->h_nlive), VL_N_CLASSES * 4 * sizeof(int)));
+  for (int i = 0; i < VL_N_CLASSES * 4; ++i) {
+    VL_CREATE_CUDA(cudaStreamCreateWithFlags(&b->class_stream[i], cudaStreamNonBlocking));
+    VL_CREATE_CUDA(cudaEventCreateWithFlags(&b->ev_join[i], cudaEventDisableTiming));
+  }
+  VL_CREATE_CUDA(cudaEventCreateWithFlags(&b->ev_fork, cudaEventDisableTiming));
+  VL_CREATE_CUDA(cudaDeviceGetAttribute(&b->n_sms, cudaDevAttrMultiProcessorCount, device));
   VL_CREATE_CUDA(cudaMallocHost(reinterpret_cast<void**>(&b->h_arena), std::max<size_t>(L.arena_bytes, 1)));
   VL_CREATE_CUDA(cudaEventCreate(&b->ev0));
   VL_CREATE_CUDA(cudaEventCreate(&b->ev1));
@@ -591,6 +616,12 @@ void vl_batch_destroy(vl_batch* b) {
   if (b->h_pstat) cudaFreeHost(b->h_pstat);
   if (b->h_rlist) cudaFreeHost(b->h_rlist);
   if (b->h_cbase) cudaFreeHost(b->h_cbase);
+  if (b->h_nlive) cudaFreeHost(b->h_nlive);
+  for (int i = 0; i < VL_N_CLASSES * 4; ++i) {
+    if (b->class_stream[i]) cudaStreamDestroy(b->class_stream[i]);
+    if (b->ev_join[i]) cudaEventDestroy(b->ev_join[i]);
+  }
+  if (b->ev_fork) cudaEventDestroy(b->ev_fork);
   if (b->h_arena) cudaFreeHost(b->h_arena);
   if (b->ev0) cudaEventDestroy(b->ev0);
   if (b->ev1) cudaEventDestroy(b->ev1);
@@ -600,7 +631,6 @@ void vl_batch_destroy(vl_batch* b) {
 int vl_batch_set_option(vl_batch* b, int32_t option, int32_t value) {
   if (!b) return fail("batch is NULL");
   if (option == VL_OPT_SKIP_DEAD) { b->skip_dead = value ? 1 : 0; return 0; }
-  if (option == VL_OPT_RESIDENT) { b->resident = value ? 1 : 0; b->sched_dirty = true; return 0; }
   if (option == VL_OPT_FUSED_CHUNKS) { b->fused = value ? 1 : 0; return 0; }
   return fail("unknown option");
 }
@@ -799,8 +829,6 @@ int vl_batch_profile_step(vl_batch* b, int32_t n_updates, double* ms_out, int64_
   };
   if (b->sched_dirty && schedule(b)) return 1;
   VL_CUDA(cudaStreamSynchronize(b->stream));
-  // the resident restarts do all n_updates in one launch; the general path is timed per kernel
-  if (timed(3, [&](int64_t* n) { return launch_resident(b, n_updates, n); })) return 1;
   for (int it = 0; it < n_updates; ++it)
     for (int phase = 0; phase < 2; ++phase)
       if (timed(phase, [&](int64_t* n) { return launch_phase(b, phase, n); })) return 1;
@@ -1006,7 +1034,7 @@ int vl_debug_occupancy(int32_t device, int32_t kernel_class, int32_t mode, int32
   if (kernel_class < 0 || kernel_class >= VL_N_CLASSES) return fail("kernel_class out of range");
   VL_CUDA(cudaSetDevice(device));
   int c = 0, sm = 0, r = 0;
-  VL_CUDA(vl_chunk_occupancy(kernel_class, mode, deep, &c, &sm, &r));
+  VL_CUDA(vl_sched_occupancy(kernel_class, mode, 0, deep, &c, &sm, &r));
   *ctas_per_sm = c; *smem_bytes = sm; *registers = r;
   return 0;
 }
@@ -1026,8 +1054,8 @@ int vl_debug_exp(int32_t device, const double* x, double* out, int32_t n) {
 
 int vl_debug_counters(uint64_t* out36, int32_t reset) {
   static_assert(sizeof(unsigned long long) == sizeof(uint64_t), "counter width");
-  int rc = vl_debug_resident_cycles(reinterpret_cast<unsigned long long*>(out36), reset);
-  if (rc == 0) rc = vl_debug_general_cycles(reinterpret_cast<unsigned long long*>(out36 + 16), reset);
+  for (int i = 0; i < 16; ++i) out36[i] = 0;
+  int rc = vl_debug_general_cycles(reinterpret_cast<unsigned long long*>(out36 + 16), reset);
   if (rc == 2) return fail("library built without -DVL_RS_PROFILE");
   return rc ? fail("cudaMemcpyFromSymbol failed") : 0;
 }

@@ -83,6 +83,15 @@ struct VlState {
   int pad_;
 };
 
+// Scheduling word of one (window, restart) problem inside a chunk launch (vl_sched_kernel); zeroed by the
+// host before every chunk.  Phase 2k = haplotype tiles of the chunk's update k, 2k + 1 = its read tiles.
+struct VlCtl {
+  unsigned long long claim;   // (phase << 32) | next tile of that phase to hand out; VL_PHASE_LEFT once the restart left the chunk
+  int done;                   // tiles of the current phase that have finished
+  int pad_;
+};
+#define VL_PHASE_LEFT 0x7fffffffu
+
 // Read-only description of one (window, restart) problem.
 struct VlProblem {
   int mode, N, L, K;
@@ -141,6 +150,10 @@ __device__ __forceinline__ void vl_dmma(double (&d)[2], double a, double b) {
 
 __device__ __forceinline__ void vl_mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" :: "r"(vl_smem_u32(bar)), "r"(count) : "memory");
+}
+// An mbarrier must be invalidated before its memory is initialised again (persistent CTAs run tile after tile).
+__device__ __forceinline__ void vl_mbar_inval(uint64_t* bar) {
+  asm volatile("mbarrier.inval.shared::cta.b64 [%0];\n" :: "r"(vl_smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ void vl_fence_mbar_init() {
   asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");

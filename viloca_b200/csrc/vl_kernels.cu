@@ -79,7 +79,7 @@ __device__ __forceinline__ bool vl_wait_published(const VlState* S, int target) 
     for (unsigned spin = 0; *pub < target; ++spin) {
       if (*act == 0) { r = 0; break; }
       __nanosleep(spin < 4096 ? 40 : 1000);
-      if (spin > (1u << 27)) __trap();       // bounded (~2 min): a lost dependency is an error, not a hang
+      if (spin > (1u << 24)) __trap();       // bounded (~20 s): a lost dependency is an error, not a hang
     }
     if (*act == 0) r = 0;
     ok = r;
@@ -130,7 +130,7 @@ __device__ __noinline__ bool vl_split_combine(const VlProblem& P, double* T, int
 // 1024 padded reads run the SPLIT = false instantiation, which is the code they always had.
 template <int KTM, int MODE, bool SPLIT>
 __device__ __forceinline__ bool vl_haplo_body(const VlProblem* __restrict__ probs, const int2 tm, const int stage_doubles,
-                                              const int* zticket, const int z_want, const int pub_want) {
+                                              const bool early, const int pub_want) {
   constexpr int NB = (8 * KTM + 31) / 32;        // 32-slot groups (lanes = slots in the sparse part)
   constexpr int KSM = vl_ks(KTM);
   constexpr int DM_STAGE = VL_H_NC * VL_PT;            // doubles
@@ -139,7 +139,7 @@ __device__ __forceinline__ bool vl_haplo_body(const VlProblem* __restrict__ prob
   __shared__ uint64_t bars[VL_MAX_STAGES];
   __shared__ double red[VL_THREADS / 32][4];
 
-  GK_DECL(tm.x == 0 && tm.y == 0);
+  GK_DECL(tm.x == 0 && (tm.y & 0xFFFFFF) == 0);
   const VlProblem& P = probs[tm.x];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, q = lane & 3;
   // Large windows: n_hsplit CTAs share the reads of a column tile;
@@ -147,32 +147,22 @@ __device__ __forceinline__ bool vl_haplo_body(const VlProblem* __restrict__ prob
   // (the split travels in the tile id -- vl_htile_id -- so that no tile waits for a load to learn its tile)
   const int ty = SPLIT ? (tm.y & 0xFFFFF) : tm.y, split = SPLIT ? ((tm.y >> 20) & 0xF) : 0;
   const int n_split = SPLIT ? max(1, (tm.y >> 24) & 0xF) : 1;
-  // Inside a chunk launch (zticket != nullptr) the operand loop starts as soon as the read tiles
-  // of the previous update have written w z -- it needs that update's layout width only
-  // (ktring) -- and overlaps the scalar update; the state is read after it has been published.
+  // Inside the scheduler kernel (early) the tile is handed out as soon as the read tiles of the
+  // previous update have written w z: the operand loop needs that update's layout width only
+  // (ktring) and overlaps the scalar update; the state is read after it has been published.
   // This tile's static maps go to shared memory up front (one memory latency, overlapped).
   __shared__ VlState sS;
   __shared__ int s_tpos[VL_PT], s_collb[VL_PT], s_poscol[VL_PT][VL_B], s_ep[VL_PT][VL_B + 1];
   __shared__ unsigned s_refb[VL_PT];
   __shared__ int s_kt_old;
-  const bool early = zticket != nullptr;
   if (tid < VL_PT) {
     s_tpos[tid] = P.tile_pos[(size_t)ty * VL_PT + tid];
     s_collb[tid] = P.col_lb[(size_t)ty * VL_PT + tid];
   }
   if (early) {
     if (tid == 0) {
-      int kt = -1;
-      const volatile int* t = zticket;
-      const volatile int* act = &P.st->active;
-      for (unsigned spin = 0; *t < z_want; ++spin) {
-        if (*act == 0) break;
-        __nanosleep(spin < 4096 ? 40 : 1000);
-        if (spin > (1u << 27)) __trap();
-      }
-      if (*t >= z_want) kt = *reinterpret_cast<const volatile int*>(&P.st->ktring[(pub_want + 1) & 1]);
+      s_kt_old = *reinterpret_cast<const volatile int*>(&P.st->ktring[(pub_want + 1) & 1]);
       __threadfence();
-      s_kt_old = kt;
     }
   } else {
     vl_load_state(&sS, P.st, tid);
@@ -258,6 +248,10 @@ __device__ __forceinline__ bool vl_haplo_body(const VlProblem* __restrict__ prob
     }
   });
 
+  // (every thread is past its last wait: the barriers are given back so that the next tile this
+  // CTA runs -- the scheduler kernel's workers are persistent -- may initialise them again)
+  if (tid == 0)
+    for (int s = 0; s < nstg; ++s) vl_mbar_inval(&bars[s]);
   // ---- the stage buffers are free now: T [16][K8] and Cm [16][5][K8] live in them; the four
   // warps add their partial sums over the reads into T one after the other (fixed order) ----
   GK_TICK(1);
@@ -421,7 +415,7 @@ __device__ __forceinline__ bool vl_haplo_body(const VlProblem* __restrict__ prob
 template <int KTM, int MODE, bool SPLIT>
 __global__ void __launch_bounds__(VL_THREADS, vl_min_ctas(KTM))
 vl_haplo_kernel(const VlProblem* __restrict__ probs, const int2* __restrict__ tiles) {
-  vl_haplo_body<KTM, MODE, SPLIT>(probs, tiles[blockIdx.x], 0, nullptr, 0, 0);
+  vl_haplo_body<KTM, MODE, SPLIT>(probs, tiles[blockIdx.x], 0, false, 0);
 }
 
 // =========================================================================================
@@ -429,10 +423,12 @@ vl_haplo_kernel(const VlProblem* __restrict__ probs, const int2* __restrict__ ti
 // entries of read n; uqs logits = ltsum[n] - Y + mean_log_pi, softmax over the slots with the
 // ghost slot counted ghost_mult times.  CTA = 64 reads x all slots; warp = 16 reads.
 // =========================================================================================
+// vl_cluster_tile: one tile up to its per-tile record; returns false if the restart is not running in this
+// kernel class.  vl_cluster_close: what the tile that finishes last does for its restart.  sS receives the
+// restart's state as it was before the update.
 template <int KTM, int MODE>
-__device__ __forceinline__ void vl_cluster_body(const VlProblem* __restrict__ probs, const int2 tm,
-                                                int* __restrict__ done_count, int4* __restrict__ pstat,
-                                                const int stage_doubles, int* zticket) {
+__device__ __forceinline__ bool vl_cluster_tile(const VlProblem* __restrict__ probs, const int2 tm,
+                                                const int stage_doubles, VlState& sS) {
   constexpr int KSM = vl_ks(KTM), K8M = 8 * KTM;
   constexpr int DM_STAGE = VL_ZT_READS * VL_PT;        // doubles
   constexpr int ST_STRIDE = DM_STAGE + VL_PT * KSM;    // dm | gm
@@ -446,14 +442,13 @@ __device__ __forceinline__ void vl_cluster_body(const VlProblem* __restrict__ pr
   const VlProblem& P = probs[tm.x];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, q = lane & 3;
   // state and mean_log_pi of the slots in shared memory: one latency, off the epilogue's path
-  __shared__ VlState sS;
   __shared__ double s_mlp[VL_MAX_CLUSTERS];
   vl_load_state(&sS, P.st, tid);
   s_mlp[tid] = (tid < 8 * P.KT) ? __ldcg(P.mlp_lay + tid) : 0.0;
   __syncthreads();
   const VlState* S = &sS;
   const int ktl = S->ktl;
-  if (S->active == 0 || ktl > KTM || S->ktl_z > KTM) return;
+  if (S->active == 0 || ktl > KTM || S->ktl_z > KTM) return false;
 
   const int Npad = P.Npad;
   const int KS = vl_ks(ktl), K8 = 8 * ktl;
@@ -527,6 +522,8 @@ __device__ __forceinline__ void vl_cluster_body(const VlProblem* __restrict__ pr
     }
   });
 
+  if (tid == 0)
+    for (int s = 0; s < nstg; ++s) vl_mbar_inval(&bars[s]);
   GK_TICK(9);
   // ---- sparse entries of this thread's two reads ----
   {
@@ -667,102 +664,214 @@ __device__ __forceinline__ void vl_cluster_body(const VlProblem* __restrict__ pr
     }
   }
 
-  // ---- the read tile that finishes last closes the iteration of its restart: fixed-order sums
-  // of the per-tile records, then the scalar update (no separate launch, no host decision) ----
-  static_assert(VL_THREADS == VL_MAX_CLUSTERS, "one thread per cluster");
-  __shared__ int s_last;
-  __shared__ VlScalarSmem sm;
-  VlState* Sw = P.st;
-  __threadfence();
-  __syncthreads();
-  if (tid == 0) {
-    if (zticket != nullptr) atomicAdd(zticket, 1);       // w z of this tile is visible: the next haplotype tiles may start
-    s_last = (atomicAdd(&Sw->ticket, 1) == P.n_ztiles - 1);
-  }
-  __syncthreads();
   GK_TICK(12);
-#ifdef VL_RS_PROFILE
-  if (gk_on_) atomicAdd(&vl_gk_cycles[17], 1ull);
-  const bool gk_last_ = tm.x == 0 && threadIdx.x == 0;
-  long long gk_t2_ = clock64();
-#endif
-  if (!s_last) return;
-  __threadfence();
-  if (tid == 0) Sw->ticket = 0;
+  return true;
+}
+
+// The read tile of a restart that finishes last closes the update: fixed-order sums of the per-tile
+// records, then the scalar update (no separate launch, no host decision).  R = the state before the update.
+template <int MODE>
+__device__ __forceinline__ void vl_cluster_close(const VlProblem& P, const VlState& R, int* __restrict__ done_count,
+                                                 int4* __restrict__ pstat_entry) {
+  static_assert(VL_THREADS == VL_MAX_CLUSTERS, "one thread per cluster");
+  __shared__ VlScalarSmem sm;
+  const int tid = threadIdx.x;
+  const int K8 = 8 * R.ktl, K8rec = 8 * P.KT, ZS = K8rec + VL_ZP_EXTRA;
   for (int c = tid; c < K8 + 7; c += VL_THREADS) {
     if (c < K8) sm.cs[c] = vl_ordered_sum(P.zpart + c, ZS, P.n_ztiles);
     else if (c < K8 + 4) sm.sc[c - K8] = vl_ordered_sum(P.zpart + K8rec + (c - K8), ZS, P.n_ztiles);
     else sm.sc[4 + (c - K8 - 4)] = vl_ordered_sum(P.hpart + (c - K8 - 4), VL_HP_STRIDE, P.n_htiles);
   }
-  vl_scalar_update<0>(P, sS, Sw, sm, tid, done_count, pstat + tm.x);
-#ifdef VL_RS_PROFILE
-  if (gk_last_) atomicAdd(&vl_gk_cycles[13], (unsigned long long)(clock64() - gk_t2_));
-#endif
+  vl_scalar_update<0>(P, R, P.st, sm, tid, done_count, pstat_entry);
+}
+
+// one tile of a per-phase launch (vl_cluster_kernel): the last tile of a restart is found with a ticket
+template <int KTM, int MODE>
+__device__ __forceinline__ void vl_cluster_body(const VlProblem* __restrict__ probs, const int2 tm,
+                                                int* __restrict__ done_count, int4* __restrict__ pstat) {
+  __shared__ VlState sS;
+  __shared__ int s_last;
+  if (!vl_cluster_tile<KTM, MODE>(probs, tm, 0, sS)) return;
+  const VlProblem& P = probs[tm.x];
+  VlState* Sw = P.st;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) s_last = (atomicAdd(&Sw->ticket, 1) == P.n_ztiles - 1);
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  if (threadIdx.x == 0) Sw->ticket = 0;
+  vl_cluster_close<MODE>(P, sS, done_count, pstat + tm.x);
 }
 
 template <int KTM, int MODE>
 __global__ void __launch_bounds__(VL_THREADS, vl_min_ctas(KTM))
 vl_cluster_kernel(const VlProblem* __restrict__ probs, const int2* __restrict__ tiles,
                   int* __restrict__ done_count, int4* __restrict__ pstat) {
-  vl_cluster_body<KTM, MODE>(probs, tiles[blockIdx.x], done_count, pstat, 0, nullptr);
+  vl_cluster_body<KTM, MODE>(probs, tiles[blockIdx.x], done_count, pstat);
 }
 
 // =========================================================================================
-// A whole chunk of updates of one kernel class in ONE launch.  Block b works on update
-// b / (n_ht + n_zt) of the chunk: first the haplotype tiles of every scheduled restart, then
-// their read tiles.  Dependencies are per restart and point to lower block indices only (blocks
-// are dispatched in index order): a haplotype tile of update u starts its operand loop when all
-// read tiles of update u - 1 have signalled (zticket: their w z is visible; the loop overlaps the
-// scalar update of u - 1) and reads the state once the restart has published u completed updates
-// (VlState::pub, written last by the scalar update); a read tile waits for the published state and
-// for all haplotype tiles of its update (hticket).  No launch latency and no kernel boundary
-// between the steps, and restarts advance independently of each other inside the chunk.
+// A whole chunk of updates of one kernel class in ONE launch of persistent worker CTAs.  Every
+// scheduled restart has a scheduling word (VlCtl) that names its current phase -- the haplotype
+// tiles of update k of the chunk, then its read tiles -- and the next tile of it to hand out.  A
+// worker claims a tile with one atomicAdd on that word, runs it, counts it done; the worker that
+// finishes the last tile of a phase opens the next one.  No worker ever waits for a tile that
+// nobody runs: a phase is opened only when everything it reads has been written, with one
+// exception, the haplotype tiles of update k + 1, which are opened when the last read tile of
+// update k has arrived and wait (after their operand loop) for the scalar update that this very
+// tile's CTA is running.  Restarts advance independently of each other; a restart that leaves its
+// loop, finishes the chunk, or whose layout outgrows the kernel class is marked VL_PHASE_LEFT.
+// Nothing depends on the order in which the hardware dispatches blocks.
 // =========================================================================================
+__device__ __forceinline__ int vl_phase_tiles(const VlProblem& P, unsigned phase) {
+  return (phase & 1u) ? P.n_ztiles : P.n_htiles * P.n_hsplit;
+}
+
+// Warp 0 of a worker: find a restart with a tile to hand out and claim it.  task = (problem, phase,
+// tile index); problem < 0 when every restart of the launch has left the chunk.
+__device__ __forceinline__ void vl_sched_claim(const VlProblem* __restrict__ probs, const int* __restrict__ rlist,
+                                               const int n_r, VlCtl* ctl, const int* n_live, int& cursor, int* task) {
+  const int lane = threadIdx.x & 31;
+  unsigned idle = 0;
+  for (;;) {
+    int got_p = -1;
+    unsigned got_phase = 0, got_idx = 0;
+    for (int base = 0; base < n_r && got_p < 0; base += 32) {
+      const int slot = base + lane;
+      int p = -1;
+      bool open = false;
+      if (slot < n_r) {
+        int at = cursor + slot;
+        if (at >= n_r) at -= n_r;
+        p = rlist[at];
+        const unsigned long long w = *reinterpret_cast<const volatile unsigned long long*>(&ctl[p].claim);
+        const unsigned phase = (unsigned)(w >> 32), idx = (unsigned)w;
+        open = phase != VL_PHASE_LEFT && idx < (unsigned)vl_phase_tiles(probs[p], phase);
+      }
+      unsigned cand = __ballot_sync(0xffffffffu, open);
+      while (cand && got_p < 0) {
+        const int src = __ffs(cand) - 1;
+        cand &= cand - 1;
+        unsigned long long old = 0;
+        if (lane == src) old = atomicAdd(&ctl[p].claim, 1ull);
+        old = __shfl_sync(0xffffffffu, old, src);
+        const int pp = __shfl_sync(0xffffffffu, p, src);
+        const unsigned phase = (unsigned)(old >> 32), idx = (unsigned)old;
+        if (phase != VL_PHASE_LEFT && idx < (unsigned)vl_phase_tiles(probs[pp], phase)) {
+          got_p = pp; got_phase = phase; got_idx = idx;
+          int at = cursor + base + src;          // the next search starts at this restart: its next tile is likely open
+          if (at >= n_r) at -= n_r;
+          cursor = at;
+        }
+      }
+    }
+    if (got_p >= 0) {
+      if (lane == 0) { task[0] = got_p; task[1] = (int)got_phase; task[2] = (int)got_idx; }
+      return;
+    }
+    if (*reinterpret_cast<const volatile int*>(n_live) <= 0) {
+      if (lane == 0) task[0] = -1;
+      return;
+    }
+    if (++idle > (1u << 26)) __trap();           // minutes without any tile to run although restarts are live: an error, not a hang
+    __nanosleep(idle < 64 ? 20 : 200);
+  }
+}
+
 template <int KTM, int MODE, bool SPLIT>
 __global__ void __launch_bounds__(VL_THREADS, vl_min_ctas(KTM))
-vl_chunk_kernel(const VlProblem* __restrict__ probs, const int2* __restrict__ htiles, int n_ht,
-                const int2* __restrict__ ztiles, int n_zt, const int* __restrict__ chunk_base,
-                int* hticket, int* zticket, int* __restrict__ done_count, int4* __restrict__ pstat,
-                const int stage_doubles) {
-  const int per_update = n_ht + n_zt;
-  const int it = blockIdx.x / per_update, r = blockIdx.x - it * per_update;
-  const bool is_h = r < n_ht;
-  const int2 tm = is_h ? htiles[r] : ztiles[r - n_ht];
-  const VlProblem& P = probs[tm.x];
-  const VlState* S = P.st;
-  GK_DECL(tm.x == 0 && tm.y == 0);
-  const int pub_want = chunk_base[tm.x] + it;
-  if (is_h) {
-    if (!vl_haplo_body<KTM, MODE, SPLIT>(probs, tm, stage_doubles, zticket + tm.x, it * P.n_ztiles, pub_want)) return;
-#ifdef VL_RS_PROFILE
-    gk_t_ = clock64();
-#endif
-    __threadfence();
+vl_sched_kernel(const VlProblem* __restrict__ probs, const int* __restrict__ rlist, const int n_r, const int n_iter,
+                const int* __restrict__ chunk_base, VlCtl* ctl, int* n_live, int* __restrict__ done_count,
+                int4* __restrict__ pstat, const int stage_doubles) {
+  __shared__ int s_task[4];
+  __shared__ int s_flag;
+  __shared__ VlState sZ;                     // a read tile's copy of the state before the update
+  const int tid = threadIdx.x;
+  int cursor = (int)(blockIdx.x % (unsigned)n_r);
+  for (;;) {
+    if (tid < 32) vl_sched_claim(probs, rlist, n_r, ctl, n_live, cursor, s_task);
     __syncthreads();
-    if (threadIdx.x == 0) atomicAdd(&hticket[tm.x], 1);
-    GK_TICK(7);
-    return;
-  }
-  if (!vl_wait_published(S, pub_want)) return;        // the restart left its loop
-  GK_TICK(14);
-  {
-    const volatile int* kt = &S->ktl;
-    const volatile int* ktz = &S->ktl_z;
-    if (*kt > KTM || *ktz > KTM) return;         // layout outgrew this class: its haplotype tiles bail out too
-  }
-  if (threadIdx.x == 0) {
-    const volatile int* t = &hticket[tm.x];
-    const int want = (it + 1) * P.n_htiles;
-    for (unsigned spin = 0; *t < want; ++spin) {
-      __nanosleep(spin < 4096 ? 40 : 1000);
-      if (spin > (1u << 27)) __trap();
+    const int p = s_task[0];
+    const unsigned phase = (unsigned)s_task[1];
+    const int idx = s_task[2];
+    __syncthreads();                         // s_task is rewritten by the next claim
+    if (p < 0) return;
+    const VlProblem& P = probs[p];
+    VlCtl* C = ctl + p;
+    const int k = (int)(phase >> 1);
+    __threadfence();                         // what the claim word promised is visible to every thread of the CTA
+    if ((phase & 1u) == 0) {
+      // ---- haplotype tile of update k ----
+      const int t = idx % P.n_htiles, sp = idx / P.n_htiles;
+      const int2 tm = make_int2(p, P.n_hsplit > 1 ? (t | (sp << 20) | (P.n_hsplit << 24)) : t);
+      GK_DECL(p == 0 && idx == 0);
+      asm volatile("fence.proxy.async;\n" ::: "memory");      // its bulk copies read what other CTAs wrote
+      vl_haplo_body<KTM, MODE, SPLIT>(probs, tm, stage_doubles, true, chunk_base[p] + k);
+#ifdef VL_RS_PROFILE
+      gk_t_ = clock64();
+#endif
+      __threadfence();
+      __syncthreads();
+      if (tid == 0) {
+        if (atomicAdd(&C->done, 1) == P.n_htiles * P.n_hsplit - 1) {
+          // last tile of the phase.  Every tile has seen the published state, so it is final here.
+          __threadfence();
+          const VlState* S = P.st;
+          const int active = *reinterpret_cast<const volatile int*>(&S->active);
+          const int ktl = *reinterpret_cast<const volatile int*>(&S->ktl);
+          C->done = 0;
+          __threadfence();
+          if (active == 0 || ktl > KTM) {    // left its loop, or the layout grew past this kernel class: the host reschedules it
+            atomicExch(&C->claim, (unsigned long long)VL_PHASE_LEFT << 32);
+            __threadfence();
+            atomicSub(n_live, 1);
+          } else {
+            atomicExch(&C->claim, (unsigned long long)(phase + 1u) << 32);
+          }
+        }
+      }
+      GK_TICK(7);
+    } else {
+      // ---- read tile of update k ----
+      GK_DECL(p == 0 && idx == 0);
+      asm volatile("fence.proxy.async;\n" ::: "memory");
+      const bool ran = vl_cluster_tile<KTM, MODE>(probs, make_int2(p, idx), stage_doubles, sZ);
+      __threadfence();
+      __syncthreads();
+      if (tid == 0) s_flag = (atomicAdd(&C->done, 1) == P.n_ztiles - 1) ? 1 : 0;
+      __syncthreads();
+      if (s_flag) {
+        __threadfence();
+        const bool more = k + 1 < n_iter;
+        if (tid == 0) {
+          C->done = 0;
+          __threadfence();
+          // the haplotype tiles of the next update may start their operand loops while this CTA does the
+          // scalar update (they read w z, which is complete, and wait for the published state afterwards)
+          if (ran && more) atomicExch(&C->claim, (unsigned long long)(phase + 1u) << 32);
+        }
+#ifdef VL_RS_PROFILE
+        const bool gk_last_ = p == 0 && tid == 0;
+        long long gk_t2_ = clock64();
+#endif
+        if (ran) vl_cluster_close<MODE>(P, sZ, done_count, pstat + p);
+#ifdef VL_RS_PROFILE
+        if (gk_last_) atomicAdd(&vl_gk_cycles[13], (unsigned long long)(clock64() - gk_t2_));
+#endif
+        if (!ran || !more) {
+          __syncthreads();
+          if (tid == 0) {
+            __threadfence();
+            atomicExch(&C->claim, (unsigned long long)VL_PHASE_LEFT << 32);
+            __threadfence();
+            atomicSub(n_live, 1);
+          }
+        }
+      }
     }
-    __threadfence();
+    __syncthreads();
   }
-  __syncthreads();
-  GK_TICK(15);
-  asm volatile("fence.proxy.async;\n" ::: "memory");
-  vl_cluster_body<KTM, MODE>(probs, tm, done_count, pstat, stage_doubles, zticket + tm.x);
 }
 
 // One thread per problem: state_init_dict of draw_init_state (initialization.py:6-43), the
@@ -965,40 +1074,45 @@ cudaError_t launch_cluster(const VlProblem* probs, const int2* tiles, int n, int
   return cudaGetLastError();
 }
 
-template <int KTM, int MODE, bool SPLIT>
-cudaError_t launch_chunk(const VlProblem* probs, const int2* htiles, int n_ht, const int2* ztiles, int n_zt,
-                         int n_updates, const int* chunk_base, int* hticket, int* zticket, int* done_count, int4* pstat,
-                         cudaStream_t stream) {
-  // With few tiles per update the SMs are mostly idle and one restart's update is a chain of
-  // latencies: give every CTA enough shared memory to have (nearly) all its operand stages in
-  // flight at once.  Otherwise size it for residency.  Same arithmetic either way.
+// Shared memory of a worker: sized for residency, or -- when the launch has few tiles in flight, the SMs
+// are mostly idle and one restart's update is a chain of latencies -- enough to have (nearly) all
+// operand stages of a tile in flight at once.  Same arithmetic either way.
+template <int KTM>
+size_t sched_smem(bool deep, int* stage_doubles) {
   size_t smem = std::max(smem_haplo<KTM>(), smem_cluster<KTM>());
-  int stage_doubles = 0;
-  if (std::max(n_ht, n_zt) <= 148 * 2) {
-    const size_t deep = (size_t)104 * 1024;      // two CTAs per SM
-    if (deep > smem) { stage_doubles = (int)((deep - (VL_THREADS / 32) * 8 * KTM * sizeof(double)) / sizeof(double)); smem = deep; }
+  *stage_doubles = 0;
+  const size_t big = (size_t)104 * 1024;        // two CTAs per SM
+  if (deep && big > smem) {
+    *stage_doubles = (int)((big - (VL_THREADS / 32) * 8 * KTM * sizeof(double)) / sizeof(double));
+    smem = big;
   }
-  cudaError_t e = cudaFuncSetAttribute(vl_chunk_kernel<KTM, MODE, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(160 * 1024));
-  if (e != cudaSuccess) return e;
-  const long long blocks = (long long)n_updates * (n_ht + n_zt);
-  if (blocks > 0x7fffffffLL) return cudaErrorInvalidValue;
-  vl_chunk_kernel<KTM, MODE, SPLIT><<<(unsigned)blocks, VL_THREADS, smem, stream>>>(probs, htiles, n_ht, ztiles, n_zt, chunk_base,
-                                                                            hticket, zticket, done_count, pstat, stage_doubles);
-  return cudaGetLastError();
+  return smem;
 }
 
 template <int KTM, int MODE, bool SPLIT>
-cudaError_t chunk_occupancy(int deep, int* ctas_per_sm, int* smem_bytes, int* regs) {
-  size_t smem = std::max(smem_haplo<KTM>(), smem_cluster<KTM>());
-  if (deep) smem = std::max(smem, (size_t)104 * 1024);
-  cudaError_t e = cudaFuncSetAttribute(vl_chunk_kernel<KTM, MODE, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(160 * 1024));
+cudaError_t sched_occupancy(int deep, int* ctas_per_sm, int* smem_bytes, int* regs) {
+  int sd = 0;
+  const size_t smem = sched_smem<KTM>(deep != 0, &sd);
+  cudaError_t e = cudaFuncSetAttribute(vl_sched_kernel<KTM, MODE, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(160 * 1024));
   if (e != cudaSuccess) return e;
   cudaFuncAttributes at;
-  e = cudaFuncGetAttributes(&at, vl_chunk_kernel<KTM, MODE, SPLIT>);
+  e = cudaFuncGetAttributes(&at, vl_sched_kernel<KTM, MODE, SPLIT>);
   if (e != cudaSuccess) return e;
   *regs = at.numRegs;
   *smem_bytes = (int)(smem + at.sharedSizeBytes);
-  return cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas_per_sm, vl_chunk_kernel<KTM, MODE, SPLIT>, VL_THREADS, smem);
+  return cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas_per_sm, vl_sched_kernel<KTM, MODE, SPLIT>, VL_THREADS, smem);
+}
+
+template <int KTM, int MODE, bool SPLIT>
+cudaError_t launch_sched(const VlProblem* probs, const int* rlist, int n_r, int n_updates, const int* chunk_base,
+                         VlCtl* ctl, int* n_live, int* done_count, int4* pstat, int n_workers, int deep, cudaStream_t stream) {
+  int stage_doubles = 0;
+  const size_t smem = sched_smem<KTM>(deep != 0, &stage_doubles);
+  cudaError_t e = cudaFuncSetAttribute(vl_sched_kernel<KTM, MODE, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(160 * 1024));
+  if (e != cudaSuccess) return e;
+  vl_sched_kernel<KTM, MODE, SPLIT><<<(unsigned)n_workers, VL_THREADS, smem, stream>>>(probs, rlist, n_r, n_updates, chunk_base, ctl,
+                                                                                  n_live, done_count, pstat, stage_doubles);
+  return cudaGetLastError();
 }
 
 }  // namespace
@@ -1027,9 +1141,8 @@ int vl_class_capacity(int cls) { return 2 << cls; }
     default: return cudaErrorInvalidValue;                                               \
   }
 
-cudaError_t vl_chunk_occupancy(int cls, int mode, int deep, int* ctas_per_sm, int* smem_bytes, int* regs) {
-  const int split = 0;
-  VL_DISPATCH(chunk_occupancy, deep, ctas_per_sm, smem_bytes, regs)
+cudaError_t vl_sched_occupancy(int cls, int mode, int split, int deep, int* ctas_per_sm, int* smem_bytes, int* regs) {
+  VL_DISPATCH(sched_occupancy, deep, ctas_per_sm, smem_bytes, regs)
 }
 
 cudaError_t vl_launch_haplo(int cls, int mode, int split, const VlProblem* probs, const int2* tiles, int n_tiles,
@@ -1045,11 +1158,11 @@ cudaError_t vl_launch_cluster(int cls, int mode, const VlProblem* probs, const i
   VL_DISPATCH(launch_cluster, probs, tiles, n_tiles, done_count, pstat, stream)
 }
 
-cudaError_t vl_launch_chunk(int cls, int mode, int split, const VlProblem* probs, const int2* htiles, int n_ht,
-                            const int2* ztiles, int n_zt, int n_updates, const int* chunk_base, int* hticket,
-                            int* zticket, int* done_count, int4* pstat, cudaStream_t stream) {
-  if (n_ht <= 0 || n_zt <= 0 || n_updates <= 0) return cudaSuccess;
-  VL_DISPATCH(launch_chunk, probs, htiles, n_ht, ztiles, n_zt, n_updates, chunk_base, hticket, zticket, done_count, pstat, stream)
+cudaError_t vl_launch_sched(int cls, int mode, int split, const VlProblem* probs, const int* rlist, int n_r, int n_updates,
+                            const int* chunk_base, VlCtl* ctl, int* n_live, int* done_count, int4* pstat, int n_workers,
+                            int deep, cudaStream_t stream) {
+  if (n_r <= 0 || n_updates <= 0 || n_workers <= 0) return cudaSuccess;
+  VL_DISPATCH(launch_sched, probs, rlist, n_r, n_updates, chunk_base, ctl, n_live, done_count, pstat, n_workers, deep, stream)
 }
 
 cudaError_t vl_launch_init(const VlProblem* probs, int n_probs, int4* pstat, cudaStream_t stream) {

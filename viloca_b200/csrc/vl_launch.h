@@ -9,27 +9,18 @@
 int vl_class_of_tiles(int kt);
 int vl_class_capacity(int cls);
 
-// Resident kernel (vl_resident.cu): one persistent CTA per restart, whole iterations on one SM.
-#define VL_RS_MAX_KT 4     // widest layout it handles, in 8-slot tiles
-#define VL_RS_MAX_CT 16    // most 16-column operand tiles
-size_t vl_resident_smem_bytes(int n_col_tiles, int kt);   // dynamic shared memory one restart needs
-size_t vl_resident_smem_limit();
-// per-phase cycle counters of one resident CTA; returns 2 unless built with -DVL_RS_PROFILE
-int vl_debug_resident_cycles(unsigned long long* out16, int reset);
-cudaError_t vl_launch_resident(int mode, const VlProblem* probs, const int* plist, int n, int n_iter, size_t smem,
-                               int* done_count, int4* pstat, cudaStream_t stream);
-
 cudaError_t vl_launch_haplo(int cls, int mode, int split, const VlProblem* probs, const int2* tiles, int n_tiles,
                             cudaStream_t stream);
 // pstat[p] receives (still running, tiles needed next, valid slots, updates done) from the scalar
 // update that the last read tile of restart p performs
 cudaError_t vl_launch_cluster(int cls, int mode, const VlProblem* probs, const int2* tiles, int n_tiles,
                               int* done_count, int4* pstat, cudaStream_t stream);
-// n_updates updates of one kernel class in one launch (vl_chunk_kernel): chunk_base[p] = updates
-// restart p had completed when the chunk was scheduled, hticket[p] and zticket[p] zeroed by the caller
-cudaError_t vl_launch_chunk(int cls, int mode, int split, const VlProblem* probs, const int2* htiles, int n_ht,
-                            const int2* ztiles, int n_zt, int n_updates, const int* chunk_base, int* hticket,
-                            int* zticket, int* done_count, int4* pstat, cudaStream_t stream);
+// n_updates updates of the restarts rlist[0..n_r) of one kernel class in one launch of n_workers persistent
+// CTAs (vl_sched_kernel): chunk_base[p] = updates restart p had completed when the chunk was scheduled,
+// ctl[p] zeroed and *n_live = n_r set by the caller; deep = large shared memory per worker (few tiles in flight)
+cudaError_t vl_launch_sched(int cls, int mode, int split, const VlProblem* probs, const int* rlist, int n_r, int n_updates,
+                            const int* chunk_base, VlCtl* ctl, int* n_live, int* done_count, int4* pstat, int n_workers,
+                            int deep, cudaStream_t stream);
 cudaError_t vl_launch_init(const VlProblem* probs, int n_probs, int4* pstat, cudaStream_t stream);
 cudaError_t vl_launch_prepare(const uint8_t* codes, const double* lt, const double* lo, const int* col_lb,
                               double* dm, double* mcount, double* ltsum, int N, int L, int Npad, int NCs,
@@ -48,4 +39,4 @@ int vl_set_error(const char* msg);
 // id of a haplotype tile in the tile lists: column tile, which part of the reads, of how many parts
 inline int vl_htile_id(int tile, int split, int n_split) { return n_split > 1 ? (tile | (split << 20) | (n_split << 24)) : tile; }
 int vl_debug_general_cycles(unsigned long long* out20, int reset);
-cudaError_t vl_chunk_occupancy(int cls, int mode, int deep, int* ctas_per_sm, int* smem_bytes, int* regs);
+cudaError_t vl_sched_occupancy(int cls, int mode, int split, int deep, int* ctas_per_sm, int* smem_bytes, int* regs);

@@ -46,7 +46,7 @@ class CaviBatch:
     """All (window, restart) problems of ``windows`` on one device."""
 
     def __init__(self, windows: Sequence[Window], device: int = 0, stream: Optional[int] = None,
-                 skip_dead: bool = True, resident: bool = False, fused_chunks: bool = True):
+                 skip_dead: bool = True, fused_chunks: bool = True):
         if not windows:
             raise ValueError("empty batch")
         self.windows = list(windows)
@@ -68,7 +68,6 @@ class CaviBatch:
         self.launches = 0
         if not skip_dead:
             capi.check(capi.lib.vl_batch_set_option(self._handle, capi.OPT_SKIP_DEAD, 0))
-        capi.check(capi.lib.vl_batch_set_option(self._handle, capi.OPT_RESIDENT, 1 if resident else 0))
         capi.check(capi.lib.vl_batch_set_option(self._handle, capi.OPT_FUSED_CHUNKS, 1 if fused_chunks else 0))
 
     # -- lifetime ------------------------------------------------------------------------
@@ -111,12 +110,12 @@ class CaviBatch:
 
     def profile_step(self, n_updates: int):
         """Per-kernel device time (ms) and launch counts over ``n_updates`` iterations:
-        {"haplo": (ms, n), "cluster": (ms, n), "scalar": (ms, n), "resident": (ms, n)}."""
+        {"haplo": (ms, n), "cluster": (ms, n)}."""
         ms = (C.c_double * 4)()
         cnt = (C.c_int64 * 4)()
         capi.check(capi.lib.vl_batch_profile_step(self._handle, int(n_updates), ms, cnt))
         self.launches += int(sum(cnt))
-        return {k: (float(ms[i]), int(cnt[i])) for i, k in enumerate(("haplo", "cluster", "scalar", "resident"))}
+        return {k: (float(ms[i]), int(cnt[i])) for i, k in enumerate(("haplo", "cluster"))}
 
     def problem_stats(self) -> np.ndarray:
         """(n_problems, 4) int32: running, 8-cluster tiles, clusters in the layout, updates."""
@@ -250,7 +249,7 @@ class CaviBatch:
 
 def run_windows(windows: Sequence[Window], device: int = 0, **options) -> list:
     """upload + run + fetch of one batch: the end-to-end call with host buffers.  ``options``
-    are the keyword options of :class:`CaviBatch` (skip_dead, resident, fused_chunks)."""
+    are the keyword options of :class:`CaviBatch` (skip_dead, fused_chunks)."""
     with CaviBatch(windows, device=device, **options) as batch:
         batch.upload()
         batch.run()

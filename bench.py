@@ -2,10 +2,11 @@
 """Benchmark of the CAVI hot path (BASELINE.json: CAVI windows/sec at 1/2/4/8 B200 vs the
 host-CPU reference).
 
-A *step* is one pass of the hot path over one batch of synthetic input: every window of one
-synthetic genome per GPU (workload ``hiv5k_uqs`` = BASELINE configs[1]: HIV-1 9.7 kb, window
-201, 5,000x coverage, 5 haplotypes, use_quality_scores, K = 100 -> 145 windows), each run to
-the end of its CAVI loop.
+A *step* is one pass of the hot path over one synthetic genome: every window of the workload,
+each run to the end of its CAVI loop.  Default workload ``sars_amplicon`` = BASELINE configs[3],
+the largest configuration that fits one GPU (SARS-CoV-2 amplicon mode, ~400 bp inserts, 20,000x
+coverage, 10 lineages, use_quality_scores, K = 100 -> 98 windows); ``hiv5k_uqs`` (configs[1]) and a
+bounded shard of ``sars_ont`` (configs[4]) are measured after it and reported under ``extra``.
 
   value   windows (x restarts) per second with the window tensors already resident in HBM:
           only the device time of the iteration loop (CUDA events) is counted
@@ -14,19 +15,19 @@ the end of its CAVI loop.
   roofline  the dominant kernel over a whole run, every launch bracketed by CUDA events on the
           launching stream (a separate, untimed pass over the same workload): algorithmic HBM
           bytes and executed / algorithmic FP64 flops per launch against the measured HBM copy
-          bandwidth (MEASURED_PEAKS.json) and the FP64 tensor (DMMA) ceiling measured on this
-          pool; the all-clusters-live first updates are reported separately (tensor bound)
-  cpu_baseline  the NumPy oracle port (same einsum calls as the reference) on one host core,
-          bounded sample, extrapolated with the iteration counts the GPU run took
+          bandwidth (MEASURED_PEAKS.json) and the FP64 tensor (DMMA) ceiling measured in the same
+          run (vl_debug_fp64_peak); the all-clusters-live first updates are reported separately
+  cpu_baseline  the reference's own update / ELBO functions (baseline/_ref, unmodified) on one host
+          core, bounded sample, extrapolated with the iteration counts the GPU run took
 
-``--impl reference`` times the reference's CPU algorithm (the oracle port; the reference is
-pure Python/NumPy and cannot be shipped to the GPU box) with its own parallelism: a
-multiprocessing Pool over windows with cpu_count()-1 single-threaded workers
-(viloca/shotgun.py:527-538).
+``--impl reference`` times the reference's CPU implementation with its own parallelism: one
+single-threaded process per window, cpu_count()-1 of them side by side (viloca/shotgun.py:527-538),
+each running a bounded number of CAVI iterations of the unmodified reference modules
+(baseline/ref_driver.py) on a window generated before the clock starts.
 
-Multi-GPU: one process per GPU (torchrun), windows sharded by the host-side longest-first
-scheduler, no data-path collective; weak scaling with fixed per-GPU work (one copy of the same
-synthetic genome per GPU; the shards mix windows of the copies).
+Multi-GPU: one process per GPU (torchrun); the windows of ONE genome are sharded over the ranks by
+the host-side longest-first scheduler (cost = unique reads x window length x clusters x restarts x
+predicted iterations), no data-path collective: strong scaling.
 """
 from __future__ import annotations
 
@@ -57,7 +58,8 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="hiv5k_uqs")
+    ap.add_argument("--workload", default="sars_amplicon")
+    ap.add_argument("--no-extra", action="store_true", help="skip the hiv5k_uqs / sars_ont lines reported under 'extra'")
     ap.add_argument("--windows", type=int, default=None, help="windows per synthetic genome (default: all)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--record-iterations", action="store_true", help="write profiles/bench_iterations.json")
@@ -68,14 +70,34 @@ def dist_env():
     return int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
 
 
-def shard_items(spec, n_windows, world):
-    """Global work list of a weak-scaling job: one copy of the synthetic genome per GPU, every
-    window an independent item; longest-first partition over the ranks (no collective).  The
-    copies are identical (seed 0), so per-GPU work does not depend on the number of GPUs."""
+def config_of(spec, n_windows):
+    """The workload as both arms report it (identical keys and values in both lines)."""
+    return {"workload": spec.name, "mode": spec.mode, "genome_length": spec.genome_length,
+            "window_length": spec.window_length, "windows": n_windows, "coverage": spec.coverage,
+            "n_clusters": spec.n_clusters, "n_starts": spec.n_starts, "haplotypes": spec.n_haplotypes,
+            "l2": "inputs larger than L2 (every window's tensors are re-uploaded each step)"}
+
+
+def predicted_costs(spec, n_windows):
+    """Cost of every window for the longest-first scheduler: reads x length x clusters x restarts
+    x predicted iterations.  The iteration predictor is the committed table of a previous run of
+    the same synthetic genome (profiles/bench_iterations.json: profile-guided, the counts vary
+    10..17178 between windows); without it every window counts the same."""
+    table = load_iteration_table(spec.name)
+    base = float(spec.coverage) * spec.window_length * spec.n_clusters * spec.n_starts
+    if not table or len(table.get("n_updates", [])) != n_windows * spec.n_starts:
+        return [base] * n_windows, "uniform (no iteration table)"
+    it = np.asarray(table["n_updates"], dtype=np.float64).reshape(n_windows, spec.n_starts).sum(axis=1)
+    nr = np.asarray(table["n_reads"], dtype=np.float64)
+    ln = np.asarray(table.get("length", [spec.window_length] * n_windows), dtype=np.float64)
+    return list(nr * ln * spec.n_clusters * it), "profile-guided (profiles/bench_iterations.json)"
+
+
+def shard_windows(spec, n_windows, world):
+    """Strong scaling: the windows of ONE genome, longest first, over the ranks (no collective)."""
     from viloca_b200 import scheduler
-    items = [(sample, w) for sample in range(world) for w in range(n_windows)]
-    costs = [float(spec.coverage) * spec.window_length * spec.n_clusters * spec.n_starts] * len(items)
-    return items, scheduler.lpt_partition(costs, world)
+    costs, how = predicted_costs(spec, n_windows)
+    return scheduler.lpt_partition(costs, world), how
 
 
 def operand_stats(windows):
@@ -194,27 +216,6 @@ class ClockSampler:
 # CPU legs (the only places that may execute oracle/)
 # ------------------------------------------------------------------------------------------
 
-def _oracle_window_iterations(win, n_iter):
-    """Seconds for n_iter oracle iterations (update + ELBO, exactly the reference's per-iteration
-    work incl. its redundant einsums) on one window, single thread."""
-    sys.path.insert(0, os.path.join(ROOT, "tests"))
-    import _bridge as br
-    w, ref, data = br.dense_inputs(win)
-    init = br.oracle_init(win)
-    t0 = time.perf_counter()
-    traj = br.orc.run(win.mode, w, ref, data, init, convergence_threshold=win.conv_thres, max_iterations=n_iter)
-    return time.perf_counter() - t0, traj.n_updates
-
-
-def _pool_worker(arg):
-    name, index, n_iter = arg
-    os.environ["OMP_NUM_THREADS"] = "1"
-    from viloca_b200 import synthetic
-    win = synthetic.make_window(synthetic.WORKLOADS[name], index)
-    dt, n = _oracle_window_iterations(win, n_iter)
-    return dt, n, win.n_reads
-
-
 def load_iteration_table(name):
     try:
         return json.load(open(ITER_TABLE))[name]
@@ -222,24 +223,60 @@ def load_iteration_table(name):
         return None
 
 
-def cpu_baseline_single_core(name, windows, n_updates, budget_s=12.0):
-    """One core, bounded: a few dozen oracle iterations on the first windows, extrapolated to the
-    whole workload with the iteration counts the GPU run actually took (cost/iteration is
-    linear in N_unique)."""
-    spent, read_iters, sample = 0.0, 0.0, []
-    n_iter = 24
+def genome_work(spec, n_windows, windows=None, n_updates=None):
+    """sum over the windows of the genome of (iterations to the end of the loop) x unique reads x
+    window length: the work the reference's dense einsums do is proportional to it.
+    From the GPU run's own counts when given (trajectories are parity-checked identical), else
+    from the committed table of a previous run."""
+    if windows is not None:
+        return float(sum(u * w.n_reads * w.length for w, u in zip(windows, n_updates))), "this run's iteration counts"
+    table = load_iteration_table(spec.name)
+    if not table:
+        return None, "no iteration table"
+    it = np.asarray(table["n_updates"], dtype=np.float64).reshape(n_windows, -1).sum(axis=1)
+    nr = np.asarray(table["n_reads"], dtype=np.float64)
+    ln = np.asarray(table.get("length", [spec.window_length] * n_windows), dtype=np.float64)
+    return float((it * nr * ln).sum()), "profiles/bench_iterations.json"
+
+
+def cpu_baseline_single_core(spec, windows, n_updates_per_window, n_genome_windows, budget_s=15.0):
+    """One core, bounded: a few iterations of the reference's loop body on the first windows,
+    extrapolated to the whole genome with the iteration counts the GPU run actually took."""
+    from baseline import ref_driver
+    spent, work, sample = 0.0, 0.0, []
+    n_iter = 6 if windows[0].n_reads * windows[0].length > 400000 else 24
     for i, win in enumerate(windows[:8]):
-        dt, n = _oracle_window_iterations(win, n_iter)
+        dt, n, _ = ref_driver.time_iterations(win, n_iter)
         spent += dt
-        read_iters += n * win.n_reads
+        work += n * win.n_reads * win.length * win.n_starts ** 0
         sample.append(f"w{i}:{n}it")
         if spent > budget_s:
             break
-    sec_per_read_iter = spent / read_iters
-    total = sum(u * w.n_reads for w, u in zip(windows, n_updates)) * sec_per_read_iter
-    return {"value": len(windows) / total, "unit": UNIT, "cores": 1, "kind": "port",
-            "sample": f"oracle port, {'+'.join(sample)} of {name} ({spent:.1f}s), extrapolated with the GPU run's "
-                      f"per-window iteration counts", "sec_per_read_iteration": sec_per_read_iter}
+    sec_per_unit = spent / work
+    total_work, src = genome_work(spec, n_genome_windows, windows, n_updates_per_window)
+    scale = n_genome_windows / len(windows)          # (a rank's shard at N > 1; the leg only runs at N = 1)
+    return {"value": n_genome_windows / (total_work * scale * sec_per_unit), "unit": UNIT, "cores": 1,
+            "kind": ref_driver.kind(),
+            "sample": f"{'+'.join(sample)} of {spec.name} ({spent:.1f}s of update_eqs.update + elbo_eqs.compute_elbo, "
+                      f"baseline/_ref unmodified), extrapolated with {src}",
+            "sec_per_read_base_iteration": sec_per_unit}
+
+
+def _reference_worker(name, index, n_iter, n_rounds, barrier, queue):
+    """One window's CAVI process of the reference's pool: generate the window (before the clock),
+    then n_rounds times: wait for the start signal, run n_iter iterations, report."""
+    try:
+        from threadpoolctl import threadpool_limits
+        threadpool_limits(1)
+    except Exception:
+        pass
+    from baseline import ref_driver
+    from viloca_b200 import synthetic
+    win = synthetic.make_window(synthetic.WORKLOADS[name], index)
+    for r in range(n_rounds):
+        barrier.wait()
+        dt, n, elbo = ref_driver.time_iterations(win, n_iter)
+        queue.put((r, index, dt, n, win.n_reads, win.length, elbo))
 
 
 def run_reference_arm(args):
@@ -247,43 +284,52 @@ def run_reference_arm(args):
     if rank != 0:
         return
     import multiprocessing as mp
+    from baseline import ref_driver
     from viloca_b200 import synthetic
     spec = synthetic.WORKLOADS[args.workload]
+    n_windows = args.windows or spec.n_windows
     procs = max((os.cpu_count() or 2) - 1, 1)          # shotgun.py:527
-    n_iter = 10
-    table = load_iteration_table(args.workload)
-    mean_updates = float(np.mean(table["n_updates"])) if table else 300.0
-    mean_reads = float(np.mean(table["n_reads"])) if table else None
-    per_step, step_s = [], []
+    heavy = spec.coverage * spec.window_length > 2_000_000
+    n_iter = 4 if heavy else 10
+    rounds = args.warmup + args.steps
     ctx = mp.get_context("fork")
-    with ctx.Pool(processes=procs) as pool:
-        for step in range(args.warmup + args.steps):
-            jobs = [(args.workload, (step * procs + i) % spec.n_windows, n_iter) for i in range(procs)]
-            t0 = time.perf_counter()
-            out = pool.map(_pool_worker, jobs)
-            dt = time.perf_counter() - t0
-            if step >= args.warmup:
-                step_s.append(dt)
-                # windows/s = (window-iterations done / iterations a window needs) / time, corrected
-                # for the sampled windows' size relative to the workload mean
-                scale = 1.0
-                if mean_reads:
-                    scale = float(np.mean([o[2] for o in out])) / mean_reads
-                per_step.append(sum(o[1] for o in out) / mean_updates * scale / dt)
-    value = float(np.mean(per_step))
+    barrier, queue = ctx.Barrier(procs + 1), ctx.Queue()
+    stride = max(n_windows // procs, 1)
+    workers = [ctx.Process(target=_reference_worker, args=(args.workload, (i * stride) % n_windows, n_iter, rounds, barrier, queue),
+                           daemon=True) for i in range(procs)]
+    for w in workers:
+        w.start()
+    rates, step_s, sampled = [], [], set()
+    for r in range(rounds):
+        barrier.wait()                                  # every worker holds its window: the clock starts here
+        t0 = time.perf_counter()
+        out = [queue.get() for _ in range(procs)]
+        dt = time.perf_counter() - t0
+        if r >= args.warmup:
+            step_s.append(dt)
+            rates.append(sum(o[3] * o[4] * o[5] for o in out) / dt)     # read-base-iterations per second of the pool
+            sampled.update(o[1] for o in out)
+    for w in workers:
+        w.join(timeout=10)
+    rate = float(np.mean(rates))
+    total_work, src = genome_work(spec, n_windows)
+    if total_work is None:
+        print(json.dumps({"impl": "reference", "unavailable": "no iteration table (profiles/bench_iterations.json) for " + args.workload}))
+        return
+    value = n_windows / (total_work / rate)
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * float(np.mean(step_s)), "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": args.workload, "mode": spec.mode, "genome_length": spec.genome_length,
-                   "window_length": spec.window_length, "windows_per_gpu": spec.n_windows, "coverage": spec.coverage,
-                   "n_clusters": spec.n_clusters, "n_starts": spec.n_starts, "haplotypes": spec.n_haplotypes,
-                   "parallelism": f"multiprocessing.Pool({procs}) over windows, one single-threaded process per window "
-                                  "(viloca/shotgun.py:527-538)"},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": procs, "kind": "port",
-                         "sample": f"Pool({procs}) x {n_iter} iterations per window per step; converted with "
-                                   f"mean iterations/window = {mean_updates:.1f} "
-                                   f"({'profiles/bench_iterations.json' if table else 'assumed'})"},
+        "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": config_of(spec, n_windows),
+        "parallelism": f"{procs} single-threaded processes side by side, one window each (viloca/shotgun.py:527-538)",
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": procs, "kind": ref_driver.kind(),
+                         "sample": f"per step {procs} windows x {n_iter} iterations of the loop body of run_cavi (cavi.py:120-169; "
+                                   f"update_eqs.update + elbo_eqs.compute_elbo of baseline/_ref, unmodified), windows built before "
+                                   f"the clock starts; windows/s = windows of the genome / (sum over its windows of iterations x "
+                                   f"reads x length [{src}] / measured read-base-iterations per second of the pool), i.e. a "
+                                   f"perfectly balanced pool (the longest window alone would take longer)",
+                         "read_base_iterations_per_sec": rate, "windows_sampled": sorted(sampled)},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
@@ -293,47 +339,21 @@ def run_reference_arm(args):
 # GPU arm
 # ------------------------------------------------------------------------------------------
 
-def run_b200_arm(args):
+def timed_steps(batch, windows, steps, warmup, barrier, device):
+    """warmup untimed steps, then `steps` timed ones: (device ms of the loops, e2e ms, launches,
+    launches of the loop, outcomes, clocks).  A step = upload from pinned host buffers, the
+    loop of every window to its end, results back into pinned host buffers."""
     import torch
-    import torch.distributed as dist
-    from viloca_b200 import engine, synthetic
-
-    rank, world, local_rank = dist_env()
-    if world > 1:
-        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    device = local_rank
-    torch.cuda.set_device(device)
-    spec = synthetic.WORKLOADS[args.workload]
-    n_windows = args.windows or spec.n_windows
-    items, parts = shard_items(spec, n_windows, world)
-    mine = [items[i] for i in parts[rank]]
-    # weak scaling with FIXED per-GPU work: every sample is the same synthetic genome (seed 0), so each
-    # rank runs every window index exactly once whatever the number of GPUs
-    windows = [synthetic.make_window(spec, w, master_seed=0).pin() for sample, w in mine]
-    n_problems = sum(w.n_starts for w in windows)
-
-    def barrier():
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    batch = engine.CaviBatch(windows, device=device)
-    h2d = batch.input_bytes()
-    d2h = 0
-    launches = 0
-    launches_run = 0
     outcomes = None
-    for _ in range(args.warmup):
+    for _ in range(warmup):
         batch.upload(); batch.run(); outcomes = batch.fetch(pinned=True)
     sampler = ClockSampler(device)
     sampler.start()
     barrier()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    run_ms = 0.0
+    run_ms, launches, launches_run = 0.0, 0, 0
     ev0.record()
-    for _ in range(args.steps):
+    for _ in range(steps):
         batch.upload()
         launches += 2 * len(windows) + 1                # operand preparation (2 kernels per window) + init
         n_run = batch.run()
@@ -344,17 +364,83 @@ def run_b200_arm(args):
         launches += 2 * len(windows)                    # mean_haplo / mean_cluster export per window
     ev1.record()
     barrier()
-    e2e_ms = ev0.elapsed_time(ev1)
-    clocks = sampler.stop()
+    return run_ms, ev0.elapsed_time(ev1), launches, launches_run, outcomes, sampler.stop()
+
+
+def d2h_bytes(outcomes, windows):
+    n = 0
     for o, w in zip(outcomes, windows):
-        d2h += w.n_clusters * w.length * 5 * 8 + w.n_reads * w.n_clusters * 8 + 2 * w.n_clusters * 8 + 128
-        d2h += sum(len(r.history_elbo) for r in o.restarts) * 8
+        n += w.n_clusters * w.length * 5 * 8 + w.n_reads * w.n_clusters * 8 + 2 * w.n_clusters * 8 + 128
+        n += sum(len(r.history_elbo) for r in o.restarts) * 8
+    return n
+
+
+def extra_line(name, device, indices=None, steps=2, warmup=1, gen_procs=1, **kw):
+    """A short measurement of another BASELINE config on this GPU (reported under `extra`)."""
+    import torch
+    from viloca_b200 import engine, synthetic
+    spec = synthetic.WORKLOADS[name]
+    t0 = time.perf_counter()
+    windows = [w.pin() for w in synthetic.make_workload(name, indices=indices, procs=gen_procs, **kw)]
+    gen_s = time.perf_counter() - t0
+    n_problems = sum(w.n_starts for w in windows)
+    with engine.CaviBatch(windows, device=device) as batch:
+        run_ms, e2e_ms, _, launches_run, outcomes, _ = timed_steps(batch, windows, steps, warmup, torch.cuda.synchronize, device)
+        ops = operand_stats(windows)
+        updates = [r.n_updates for o in outcomes for r in o.restarts]
+        ex = sum(2.0 * o["Npad"] * o["NCs"] for o, w in zip(ops, windows) for _ in range(w.n_starts))
+        out = {"workload": name, "windows": len(windows), "of_windows": spec.n_windows, "n_starts": spec.n_starts,
+               "n_unique_mean": float(np.mean([w.n_reads for w in windows])), "length_mean": float(np.mean([w.length for w in windows])),
+               "value": n_problems * steps / (run_ms * 1e-3), "unit": "windows x restarts / s", "ms_per_step": run_ms / steps,
+               "e2e": {"value": n_problems * steps / (e2e_ms * 1e-3), "ms_per_step": e2e_ms / steps,
+                       "h2d_bytes_per_step": batch.input_bytes(), "d2h_bytes_per_step": d2h_bytes(outcomes, windows)},
+               "steps": steps, "warmup": warmup, "loop_launches_per_step": launches_run / steps,
+               "iterations": {"mean": float(np.mean(updates)), "max": int(max(updates)), "min": int(min(updates))},
+               "workspace_mb": batch.workspace_bytes / 1e6, "host_generation_s": gen_s}
+        del ex
+    return out
+
+
+def run_b200_arm(args):
+    # host-only work first (the generators fork a pool; nothing has touched CUDA yet)
+    from viloca_b200 import synthetic
+    rank, world, local_rank = dist_env()
+    spec = synthetic.WORKLOADS[args.workload]
+    n_windows = args.windows or spec.n_windows
+    parts, lpt_how = shard_windows(spec, n_windows, world)
+    mine = parts[rank]
+    gen_procs = max(1, min(32, (os.cpu_count() or 2) // max(world, 1)))
+    t_gen = time.perf_counter()
+    windows = synthetic.make_workload(args.workload, indices=mine, procs=gen_procs)
+    t_gen = time.perf_counter() - t_gen
+
+    import torch
+    import torch.distributed as dist
+    from viloca_b200 import _capi as capi, engine
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    device = local_rank
+    torch.cuda.set_device(device)
+    windows = [w.pin() for w in windows]
+    n_problems = sum(w.n_starts for w in windows)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    batch = engine.CaviBatch(windows, device=device)
+    h2d = batch.input_bytes()
+    run_ms, e2e_ms, launches, launches_run, outcomes, clocks = timed_steps(batch, windows, args.steps, args.warmup, barrier, device)
+    d2h = d2h_bytes(outcomes, windows)
 
     # per-kernel roofline numbers: a separate pass with every launch bracketed by CUDA events
     ops = operand_stats(windows)
     ops_per_problem = [o for o, w in zip(ops, windows) for _ in range(w.n_starts)]     # problem = (window, restart)
     prof_tot, prof_first = profiled_run(batch, ops_per_problem)
-    n_updates = [o.restarts[o.best_restart].n_updates for o in outcomes]
+    n_updates_window = [sum(r.n_updates for r in o.restarts) for o in outcomes]
     all_updates = [r.n_updates for o in outcomes for r in o.restarts]
     read_iters = sum(r.n_updates * w.n_reads for o, w in zip(outcomes, windows) for r in o.restarts)
     raw_read_iters = sum(r.n_updates * getattr(w, "n_raw", w.n_reads) for o, w in zip(outcomes, windows) for r in o.restarts)
@@ -364,27 +450,31 @@ def run_b200_arm(args):
     if world > 1:
         tmax = t.clone(); dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
         tsum = t.clone(); dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
+        tmin = t.clone(); dist.all_reduce(tmin, op=dist.ReduceOp.MIN)
     else:
-        tmax = tsum = t
+        tmax = tsum = tmin = t
     run_ms_max, e2e_ms_max = float(tmax[0]), float(tmax[1])
     total_problems = float(tsum[2])
 
-    if args.record_iterations and rank == 0:
+    if args.record_iterations and world == 1:
         os.makedirs(os.path.dirname(ITER_TABLE), exist_ok=True)
         table = {}
         if os.path.exists(ITER_TABLE):
             table = json.load(open(ITER_TABLE))
         table[args.workload] = {"n_updates": all_updates, "n_reads": [w.n_reads for w in windows],
-                                "n_raw": [getattr(w, "n_raw", w.n_reads) for w in windows]}
+                                "n_raw": [getattr(w, "n_raw", w.n_reads) for w in windows],
+                                "length": [w.length for w in windows]}
         json.dump(table, open(ITER_TABLE, "w"))
 
     if rank == 0:
-        kern_ms = {k: v["ms"] for k, v in prof_tot.items()}
+        # FP64 tensor ceiling of THIS GPU, measured now (DMMA m8n8k4 register loop on every SM)
+        peak = C_double()
+        fp64_src = "DMMA m8n8k4 register loop measured in this run (vl_debug_fp64_peak)"
         try:
-            fp64_peak = max(r["tflops"] for r in json.load(open(FP64_PEAK_FILE))["results"] if r["kind"] == "dmma884")
-            fp64_src = "DMMA m8n8k4 register loop measured on this pool, profiles/r01_fp64_peak.json"
-        except (OSError, ValueError, KeyError):
-            fp64_peak, fp64_src = 37.0, "fallback: nominal B200 FP64 tensor peak"
+            capi.check(capi.lib.vl_debug_fp64_peak(device, ctypes_byref(peak)))
+            fp64_peak = float(peak.value)
+        except Exception as exc:                        # noqa: BLE001
+            fp64_peak, fp64_src = 37.0, f"fallback 37 TFLOP/s ({exc})"
         try:
             hbm_peak = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs_sustained"])
             hbm_src = "MEASURED_PEAKS.json hbm_gbs_sustained"
@@ -407,7 +497,7 @@ def run_b200_arm(args):
                     "algorithmic_tflops": t["algorithmic"] / sec * 1e-12,
                     "dense_equivalent_tflops": t["dense_equivalent"] / sec * 1e-12}
 
-        # The timed runs execute both contractions of every update inside vl_chunk_kernel (one
+        # The timed runs execute both contractions of every update inside vl_sched_kernel (one
         # launch per chunk of updates and kernel class): its work is the sum of the two phases,
         # its duration the device time of the timed loop (launch gaps between chunks included).
         both = {k: prof_tot["haplo"][k] + prof_tot["cluster"][k] for k in ("bytes", "executed", "algorithmic", "dense_equivalent")}
@@ -418,7 +508,7 @@ def run_b200_arm(args):
         per_phase = {k: rates(prof_tot[k]) for k in ("haplo", "cluster")}
         start = {k: rates(prof_first[k]) for k in ("haplo", "cluster")}
         roofline = {
-            "bound": bound, "kernel": "vl_chunk_kernel (haplotype-update + responsibility-update tiles of a chunk of updates)",
+            "bound": bound, "kernel": "vl_sched_kernel (haplotype-update + responsibility-update tiles of a chunk of updates)",
             "achieved": fused["gbytes_per_s"] if bound == "hbm" else fused["executed_tflops"],
             "peak": hbm_peak if bound == "hbm" else fp64_peak, "unit": "GB/s" if bound == "hbm" else "TFLOP/s",
             "frac": max(frac_hbm, frac_fp), "traffic": traffic,
@@ -443,14 +533,14 @@ def run_b200_arm(args):
         line = {
             "metric": METRIC, "value": total_problems * args.steps / (run_ms_max * 1e-3), "unit": UNIT,
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": run_ms_max / args.steps,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": args.workload, "mode": spec.mode, "genome_length": spec.genome_length,
-                       "window_length": spec.window_length, "windows_per_gpu": len(windows), "coverage": spec.coverage,
-                       "n_unique_mean": float(np.mean([w.n_reads for w in windows])), "n_clusters": spec.n_clusters,
-                       "n_starts": spec.n_starts, "haplotypes": spec.n_haplotypes, "parallelism": f"windows x{world}", "per_gpu_work": f"the same {n_windows}-window genome on every GPU (seed 0)",
-                       "dense_columns_mean": float(np.mean([o["NC"] for o in ops])),
-                       "sparse_entries_mean": float(np.mean([o["nnz"] for o in ops])),
-                       "l2": "inputs larger than L2 (working set %.0f MB per GPU, re-uploaded every step)" % (batch.workspace_bytes / 1e6)},
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": config_of(spec, n_windows),
+            "parallelism": f"the {n_windows} windows of one genome over {world} GPU(s), longest first; cost = {lpt_how}",
+            "workload_stats": {"windows_rank0": len(windows), "n_unique_mean": float(np.mean([w.n_reads for w in windows])),
+                               "dense_columns_mean": float(np.mean([o["NC"] for o in ops])),
+                               "sparse_entries_mean": float(np.mean([o["nnz"] for o in ops])),
+                               "workspace_mb_rank0": batch.workspace_bytes / 1e6, "host_generation_s": t_gen,
+                               "rank_ms_per_step": {"max": run_ms_max / args.steps, "min": float(tmin[0]) / args.steps}},
             "e2e": {"value": total_problems * args.steps / (e2e_ms_max * 1e-3), "unit": UNIT,
                     "h2d_bytes_per_step": int(float(tsum[6])), "d2h_bytes_per_step": int(float(tsum[7])),
                     "ms_per_step": e2e_ms_max / args.steps},
@@ -462,11 +552,40 @@ def run_b200_arm(args):
             "roofline": roofline,
         }
         if world == 1 and not args.no_cpu_baseline:
-            line["cpu_baseline"] = cpu_baseline_single_core(args.workload, windows, n_updates)
-        print(json.dumps(line), flush=True)
+            line["cpu_baseline"] = cpu_baseline_single_core(spec, windows, n_updates_window, n_windows)
     batch.close()
+    batch = None
+    if rank == 0 and world == 1 and not args.no_extra:
+        extra = {}
+        torch.cuda.empty_cache()
+        for name, kw in EXTRA_WORKLOADS:
+            if name == args.workload:
+                continue
+            try:
+                extra[name] = extra_line(name, device, gen_procs=gen_procs, **kw)
+            except Exception as exc:                    # noqa: BLE001  (an extra line never costs the headline)
+                extra[name] = {"error": repr(exc)}
+            torch.cuda.empty_cache()
+        line["extra"] = extra
+    if rank == 0:
+        print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+# other BASELINE configs measured after the headline workload (N = 1 only): configs[1] whole, and a
+# bounded shard of configs[4] (2 of its 120 windows x 20 restarts: one window's workspace is 10 GB)
+EXTRA_WORKLOADS = (("hiv5k_uqs", {}), ("sars_ont", {"indices": [0, 1]}))
+
+
+def C_double():
+    import ctypes
+    return ctypes.c_double(0.0)
+
+
+def ctypes_byref(x):
+    import ctypes
+    return ctypes.byref(x)
 
 
 def main():

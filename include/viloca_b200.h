@@ -254,6 +254,14 @@ int vl_debug_occupancy(int32_t device, int32_t kernel_class, int32_t mode, int32
                        int32_t* smem_bytes, int32_t* registers);
 
 /*
+ * Measurement aid (bench.py's roofline denominator): sustained FP64 tensor throughput of `device` in
+ * TFLOP/s, measured now with a register-resident loop of the DMMA m8n8k4 instruction the contraction
+ * kernels issue (8 independent accumulators per warp, 16 warps per SM).  The reference has no
+ * counterpart (it is a CPU program; SURVEY.md 8(d) asks for the fraction of the FP64 tensor peak).
+ */
+int vl_debug_fp64_peak(int32_t device, double* tflops);
+
+/*
  * Development aid: per-phase cycle counters, 36 values: [0..15] unused (0), [16..35] tile 0 of
  * restart 0 (slot meanings in vl_kernels.cu).  Fails unless the library was built with -DVL_RS_PROFILE
  * (python -m viloca_b200.build --profile).

@@ -612,3 +612,89 @@ def test_reference_signature_run_cavi(golden_dir):
     for key in ("alpha", "mean_log_pi", "gamma_a", "gamma_b", "mean_log_gamma", "mean_haplo", "mean_cluster", "elbo"):
         assert key in state
     assert br.rel_err(state["alpha"], g["c_s42_alpha"]) < ENG_TOL
+
+
+# ---- full-shape parity: BASELINE.json configs at their real sizes against summaries of the UNMODIFIED
+# reference's results (oracle/make_golden_fullshape.py; the windows are regenerated from their seeds) ----
+
+def _fullshape(golden_dir, name):
+    path = os.path.join(golden_dir, "fullshape", name + ".npz")
+    if not os.path.exists(path):
+        pytest.skip(f"{path} not generated")
+    return np.load(path, allow_pickle=True)
+
+
+def test_full_hiv5k_window_to_convergence_matches_reference_run_cavi(golden_dir):
+    """configs[1] at full size: one whole hiv5k_uqs window through the reference's own cavi.run_cavi to the
+    end of its loop (1 500+ iterations) -- identical iteration count and exit message, every ELBO of the
+    history within ENG_TOL, identical haplotypes, responsibilities within SPEC_TOL."""
+    from viloca_b200 import synthetic
+    engine = _engine()
+    g = _fullshape(golden_dir, "hiv5k_w96")
+    win = synthetic.make_window(synthetic.WORKLOADS["hiv5k_uqs"], int(g["index"]))
+    assert win.n_reads == int(g["n_reads"])
+    out = engine.run_windows([win])[0]
+    r = out.restarts[0]
+    assert (r.n_iterations, r.exit_message, r.converged) == (int(g["n_iterations"]), str(g["exit_message"]), bool(g["converged"]))
+    assert r.n_updates == len(g["history"]) > 1000
+    assert br.rel_err(r.history_elbo, g["history"]) < ENG_TOL
+    assert orc.haplotype_strings(out.state["mean_haplo"]) == orc.haplotype_strings(g["mean_haplo"])
+    assert np.array_equal(out.state["mean_cluster"] == 0, g["mean_cluster"] == 0)
+    assert br.rel_err(out.state["mean_cluster"], g["mean_cluster"]) < SPEC_TOL
+    assert br.rel_err(out.state["alpha"], g["alpha"]) < ENG_TOL
+
+
+@pytest.mark.parametrize("name", ["amplicon_full", "ont_full"])
+def test_full_shape_windows_against_reference_updates(golden_dir, name):
+    """configs[3] (N_raw = 20 000 -> ~2 500 unique reads, L ~ 400) and configs[4] shape (N = 20 000 unique
+    ONT-like reads, L = 1 000, K = 100, 2 restarts: the widest kernel class with 8-way split haplotype tiles):
+    the first iterations of every restart against the unmodified update_eqs.update / elbo_eqs.compute_elbo."""
+    from oracle import make_golden_fullshape as mg
+    engine = _engine()
+    g = _fullshape(golden_dir, name)
+    win, n_iter = mg.full_shape_windows()[name]
+    assert (win.n_reads, win.length, win.n_starts, n_iter) == (int(g["n_reads"]), int(g["length"]), int(g["n_starts"]), int(g["n_iter"]))
+    with engine.CaviBatch([win]) as batch:
+        batch.upload()
+        batch.run()
+        for r in range(win.n_starts):
+            out = batch.fetch(state=r)[0]
+            res, st = out.restarts[r], out.state
+            assert res.n_updates == n_iter and res.status == 4                     # stopped by the iteration cap
+            assert br.rel_err(res.history_elbo, g[f"r{r}_history"]) < ENG_TOL
+            z, h = st["mean_cluster"], st["mean_haplo"]
+            assert int((z == 0).sum()) == int(g[f"r{r}_z_zeros"])
+            assert br.rel_err(z[mg.sample_index(z.shape[0])], g[f"r{r}_z_rows"]) < SPEC_TOL
+            assert br.rel_err(h[:, mg.sample_index(h.shape[1])], g[f"r{r}_h_positions"]) < SPEC_TOL
+            assert br.rel_err(z.sum(axis=0), g[f"r{r}_z_colsum"], floor=1e-200) < SPEC_TOL
+            assert br.rel_err(st["alpha"], g[f"r{r}_alpha"]) < ENG_TOL
+            assert br.rel_err(st["mean_log_pi"], g[f"r{r}_mean_log_pi"]) < ENG_TOL
+            assert br.rel_err(np.array([st["gamma_a"], st["gamma_b"]]), g[f"r{r}_gamma_ab"]) < ENG_TOL
+
+
+def test_batched_hook_on_two_devices(golden_dir, tmp_path, monkeypatch):
+    """shotgun_hook.run_dpm_batch with the windows sharded over two GPUs (one host thread per device):
+    the same files and states as on one device."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    from oracle import bam_windows
+    from viloca_b200 import shotgun_hook
+    meta = _json_file(os.path.join(golden_dir, "bam_windows", "expected.json"))
+    runs = {}
+    for tag, devices in (("one", [0]), ("two", [0, 1])):
+        d = tmp_path / tag
+        d.mkdir()
+        monkeypatch.chdir(d)
+        runlist = []
+        for name in BAM_WINDOWS:
+            m = meta[name]
+            _, f_reads, _, _ = bam_windows.materialize(os.path.join(golden_dir, "bam_windows", name, "window.npz"), str(d))
+            runlist.append((f_reads, 0, 0.0001, np.array([m["seed"]]), "use_quality_scores", m["K"], m["n_starts"], True, 1e-3, False))
+        jobs, finished = shotgun_hook.run_dpm_batch(runlist, devices=devices, collect=True)
+        runs[tag] = (d, [meta[n]["stem"] for n in BAM_WINDOWS], finished)
+    (d1, stems, fin1), (d2, _, fin2) = runs["one"], runs["two"]
+    for stem, (s1, r1), (s2, r2) in zip(stems, fin1, fin2):
+        for suffix in (".reads-support.fas", ".reads-cor.fas"):
+            assert _text(os.path.join(d1, stem + suffix)) == _text(os.path.join(d2, stem + suffix))
+        assert r1["n_iterations"] == r2["n_iterations"] and r1["elbo"] == r2["elbo"]

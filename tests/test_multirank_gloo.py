@@ -23,16 +23,19 @@ def _worker(rank, world, port, out):
     sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
     import bench
     from viloca_b200 import synthetic
-    spec = synthetic.WORKLOADS["hiv5k_uqs"]
-    items, parts = bench.shard_items(spec, 7, world)
-    mine = [items[i] for i in parts[rank]]
+    # strong scaling: the windows of ONE genome over the ranks, longest first; the cost uses the
+    # committed iteration table (amplicon: the counts vary 10..17178 between windows)
+    spec = synthetic.WORKLOADS["sars_amplicon"]
+    parts, how = bench.shard_windows(spec, spec.n_windows, world)
+    costs, _ = bench.predicted_costs(spec, spec.n_windows)
+    mine = [(w, costs[w]) for w in parts[rank]]
     gathered = [None] * world
     dist.all_gather_object(gathered, mine)
     t = torch.tensor([float(rank + 1), float(len(mine))], dtype=torch.float64)
     tmax = t.clone(); dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
     tsum = t.clone(); dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
     if rank == 0:
-        out.put((gathered, tmax.tolist(), tsum.tolist(), len(items)))
+        out.put((gathered, tmax.tolist(), tsum.tolist(), spec.n_windows, how))
     dist.barrier()
     dist.destroy_process_group()
 
@@ -45,11 +48,15 @@ def test_two_rank_sharding_is_consistent():
     procs = [ctx.Process(target=_worker, args=(r, world, port, out)) for r in range(world)]
     for p in procs:
         p.start()
-    gathered, tmax, tsum, n_items = out.get(timeout=120)
+    gathered, tmax, tsum, n_items, how = out.get(timeout=120)
     for p in procs:
         p.join(timeout=120)
         assert p.exitcode == 0
-    flat = [tuple(x) for shard in gathered for x in shard]
-    assert len(flat) == n_items == 14 and len(set(flat)) == n_items       # disjoint cover
-    assert abs(len(gathered[0]) - len(gathered[1])) <= 1                   # balanced
-    assert tmax[0] == 2.0 and tsum[1] == 14.0
+    flat = [x[0] for shard in gathered for x in shard]
+    assert len(flat) == n_items == 98 and len(set(flat)) == n_items        # disjoint cover of the genome
+    assert how.startswith("profile-guided")
+    loads = [sum(c for _, c in shard) for shard in gathered]
+    # longest-first: no rank carries more than the mean load plus the largest single window
+    biggest = max(c for shard in gathered for _, c in shard)
+    assert max(loads) <= sum(loads) / world + biggest
+    assert tmax[0] == 2.0 and tsum[1] == 98.0

@@ -62,7 +62,7 @@ EXPORTS = (
     "vl_batch_create", "vl_batch_destroy", "vl_batch_upload", "vl_batch_run", "vl_batch_step",
     "vl_batch_fetch", "vl_batch_set_state", "vl_batch_merge_haplo", "vl_batch_profile_step",
     "vl_batch_last_device_ms", "vl_batch_set_option", "vl_batch_problem_stats",
-    "vl_window_plan", "vl_window_plan_capacity", "vl_debug_counters", "vl_debug_exp", "vl_debug_occupancy",
+    "vl_window_plan", "vl_window_plan_capacity", "vl_debug_counters", "vl_debug_exp", "vl_debug_occupancy", "vl_debug_fp64_peak",
     "vl_reads_parse", "vl_reads_fill", "vl_reads_free",
 )
 
@@ -107,6 +107,8 @@ def _load():
     lib.vl_reads_free.restype = None
     lib.vl_debug_occupancy.argtypes = [C.c_int32] * 4 + [_i32p] * 3
     lib.vl_debug_exp.argtypes = [C.c_int32, _f64p, _f64p, C.c_int32]
+    if hasattr(lib, "vl_debug_fp64_peak"):      # (absent from older development builds selected with VILOCA_B200_LIB)
+        lib.vl_debug_fp64_peak.argtypes = [C.c_int32, _f64p]
     lib.vl_debug_counters.argtypes = [C.POINTER(C.c_uint64), C.c_int32]
     lib.vl_batch_set_option.argtypes = [C.c_void_p, C.c_int32, C.c_int32]
     lib.vl_batch_problem_stats.argtypes = [C.c_void_p, _i32p, C.c_int32]

@@ -313,8 +313,10 @@ struct vl_batch {
   int skip_dead = 1, fused = 1;
   cudaStream_t class_stream[VL_N_CLASSES * 4] = {};   // chunk launches of different classes run side by side
   cudaEvent_t ev_fork = nullptr, ev_join[VL_N_CLASSES * 4] = {};
-  int occ[VL_N_CLASSES][4][2] = {};    // resident CTAs per SM of the chunk kernel (class, variant, deep), 0 = not asked yet
+  int occ[VL_N_CLASSES][4][3] = {};    // resident CTAs per SM of the persistent chunk kernel (class, variant, deep), 0 = not asked yet
+  int persistent = -1;                 // chunk launches: 1 = persistent workers, 0 = one block per tile, -1 = by the number of launches
   int n_sms = 148;
+  int deep2_max = 148;                 // most tiles in flight for which a launch gives every CTA a whole SM's shared memory
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   double last_ms = 0.0;
   bool uploaded = false;
@@ -388,10 +390,12 @@ int launch_phase(vl_batch* b, int phase, int64_t* launches) {
   return 0;
 }
 
-// n_iter updates of every scheduled restart: one launch of persistent workers per kernel class and
-// variant (vl_sched_kernel), the launches side by side on their own streams.  A launch gets as many
-// workers as its restarts can have tiles in flight, at most what fits the GPU; when several launches
-// together want more SMs than there are, each gets its share.
+// n_iter updates of every scheduled restart: one launch per kernel class and variant (vl_sched_kernel),
+// the launches side by side on their own streams.  One launch alone: one block per tile the chunk can
+// have.  Several launches: persistent workers, each launch as many as its restarts can have tiles in
+// flight, at most what fits the GPU; when the launches together want more SMs than there are, each gets
+// its share (blocks of a huge one-tile-per-block grid would fill every SM slot and keep the other
+// launches out).
 int run_chunk_fused(vl_batch* b, int n_iter, int64_t* launches) {
   const Layout& L = b->lay;
   const int np = L.n_problems;
@@ -400,37 +404,41 @@ int run_chunk_fused(vl_batch* b, int n_iter, int64_t* launches) {
   VL_CUDA(cudaMemsetAsync(b->dev<VlCtl>(L.ctl), 0, (size_t)np * sizeof(VlCtl), b->stream));
   struct Launch { int c, m, deep, occ, workers; double sms; };
   std::vector<Launch> todo;
-  double sm_demand = 0.0;
   for (int c = 0; c < VL_N_CLASSES; ++c)
     for (int m = 0; m < 4; ++m) {
       b->h_nlive[c * 4 + m] = b->n_rs[c][m];
-      if (b->n_rs[c][m] == 0) continue;
-      Launch l{c, m, b->want_workers[c][m] <= 2 * b->n_sms ? 1 : 0, 0, 0, 0.0};
-      int& occ = b->occ[c][m][l.deep];
-      if (occ == 0) {
-        int smem = 0, regs = 0;
-        VL_CUDA(vl_sched_occupancy(c, (m & 1) ? VL_MODE_LEP : VL_MODE_UQS, m >> 1, l.deep, &occ, &smem, &regs));
-        if (occ <= 0) return fail("the chunk kernel does not fit an SM");
-      }
-      l.occ = occ;
-      l.workers = std::min(b->want_workers[c][m], occ * b->n_sms);
-      l.sms = (double)l.workers / occ;
-      sm_demand += l.sms;
-      todo.push_back(l);
+      // few tiles in flight: the SMs are mostly idle and a restart's update is a chain of latencies
+      if (b->n_rs[c][m] > 0) todo.push_back(Launch{c, m, b->want_workers[c][m] <= b->deep2_max ? 2 : (b->want_workers[c][m] <= 2 * b->n_sms ? 1 : 0), 0, 0, 0.0});
     }
   if (todo.empty()) return 0;
   VL_CUDA(cudaMemcpyAsync(b->dev<int>(L.nlive), b->h_nlive, VL_N_CLASSES * 4 * sizeof(int), cudaMemcpyHostToDevice, b->stream));
-  const double scale = sm_demand > b->n_sms ? b->n_sms / sm_demand : 1.0;
   const bool fork = todo.size() > 1;
+  const int persistent = b->persistent >= 0 ? b->persistent : (fork ? 1 : 0);
+  double sm_demand = 0.0;
+  if (persistent)
+    for (Launch& l : todo) {
+      int& occ = b->occ[l.c][l.m][l.deep];
+      if (occ == 0) {
+        int smem = 0, regs = 0;
+        VL_CUDA(vl_sched_occupancy(l.c, (l.m & 1) ? VL_MODE_LEP : VL_MODE_UQS, l.m >> 1, l.deep, 1, &occ, &smem, &regs));
+        if (occ <= 0) return fail("the chunk kernel does not fit an SM");
+      }
+      l.occ = occ;
+      l.workers = std::min(b->want_workers[l.c][l.m], occ * b->n_sms);
+      l.sms = (double)l.workers / occ;
+      sm_demand += l.sms;
+    }
+  const double scale = sm_demand > b->n_sms ? b->n_sms / sm_demand : 1.0;
   if (fork) VL_CUDA(cudaEventRecord(b->ev_fork, b->stream));
   for (const Launch& l : todo) {
     const int i = l.c * 4 + l.m;
     cudaStream_t s = fork ? b->class_stream[i] : b->stream;
     if (fork) VL_CUDA(cudaStreamWaitEvent(s, b->ev_fork, 0));
-    const int workers = std::max(1, std::min(l.workers, (int)(l.sms * scale * l.occ + 0.5)));
+    const long long blocks = persistent ? std::max(1, std::min(l.workers, (int)(l.sms * scale * l.occ + 0.5)))
+                                        : (long long)n_iter * (b->n_ht[l.c][l.m] + b->n_zt[l.c][l.m]);
     VL_CUDA(vl_launch_sched(l.c, (l.m & 1) ? VL_MODE_LEP : VL_MODE_UQS, l.m >> 1, b->d_probs(), b->dev<int>(L.rlist) + b->off_rs[l.c][l.m],
                             b->n_rs[l.c][l.m], n_iter, b->dev<int>(L.cbase), b->dev<VlCtl>(L.ctl), b->dev<int>(L.nlive) + i,
-                            b->d_done(), b->d_pstat(), workers, l.deep, s));
+                            b->d_done(), b->d_pstat(), blocks, l.deep, persistent, s));
     *launches += 1;
     if (fork) {
       VL_CUDA(cudaEventRecord(b->ev_join[i], s));
@@ -530,6 +538,8 @@ int vl_batch_create(vl_batch** out, int32_t device, const vl_window_desc* window
   b->stream = reinterpret_cast<cudaStream_t>(stream);
   b->ws = static_cast<unsigned char*>(dev_workspace);
   b->ws_bytes = dev_bytes;
+  if (const char* env = std::getenv("VL_PERSISTENT")) b->persistent = std::atoi(env);      // development aid
+  if (const char* env = std::getenv("VL_DEEP2_MAX")) b->deep2_max = std::atoi(env);        // development aid
   cudaError_t e = cudaSetDevice(device);
   if (e != cudaSuccess) { delete b; return fail(std::string("cudaSetDevice: ") + cudaGetErrorString(e)); }
 
@@ -1034,7 +1044,7 @@ int vl_debug_occupancy(int32_t device, int32_t kernel_class, int32_t mode, int32
   if (kernel_class < 0 || kernel_class >= VL_N_CLASSES) return fail("kernel_class out of range");
   VL_CUDA(cudaSetDevice(device));
   int c = 0, sm = 0, r = 0;
-  VL_CUDA(vl_sched_occupancy(kernel_class, mode, 0, deep, &c, &sm, &r));
+  VL_CUDA(vl_sched_occupancy(kernel_class, mode, 0, deep, 0, &c, &sm, &r));
   *ctas_per_sm = c; *smem_bytes = sm; *registers = r;
   return 0;
 }
@@ -1049,6 +1059,36 @@ int vl_debug_exp(int32_t device, const double* x, double* out, int32_t n) {
   if (e == cudaSuccess) e = cudaMemcpy(out, d + n, (size_t)n * 8, cudaMemcpyDeviceToHost);
   cudaFree(d);
   VL_CUDA(e);
+  return 0;
+}
+
+int vl_debug_fp64_peak(int32_t device, double* tflops) {
+  if (!tflops) return fail("bad argument");
+  VL_CUDA(cudaSetDevice(device));
+  int sms = 0;
+  VL_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
+  const int blocks = 2 * sms, iters = 4096;
+  double* d = nullptr;
+  VL_CUDA(cudaMalloc(reinterpret_cast<void**>(&d), (size_t)blocks * 256 * sizeof(double)));
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  cudaError_t e = cudaEventCreate(&e0);
+  if (e == cudaSuccess) e = cudaEventCreate(&e1);
+  float best = 1e30f;
+  for (int r = 0; r < 5 && e == cudaSuccess; ++r) {        // (the first repetitions warm the clocks up)
+    e = cudaEventRecord(e0, nullptr);
+    if (e == cudaSuccess) e = vl_launch_dmma_peak(d, blocks, iters, nullptr);
+    if (e == cudaSuccess) e = cudaEventRecord(e1, nullptr);
+    if (e == cudaSuccess) e = cudaEventSynchronize(e1);
+    float ms = 0.f;
+    if (e == cudaSuccess) e = cudaEventElapsedTime(&ms, e0, e1);
+    if (e == cudaSuccess && r >= 2 && ms < best) best = ms;
+  }
+  if (e0) cudaEventDestroy(e0);
+  if (e1) cudaEventDestroy(e1);
+  cudaFree(d);
+  VL_CUDA(e);
+  const double flops = 2.0 * 8 * 8 * 4 * 8.0 * iters * (256 / 32) * (double)blocks;
+  *tflops = flops / ((double)best * 1e-3) * 1e-12;
   return 0;
 }
 

@@ -73,16 +73,19 @@ __device__ __forceinline__ void vl_load_state(VlState* dst, const VlState* src, 
     reinterpret_cast<unsigned long long*>(dst)[tid] = __ldcg(reinterpret_cast<const unsigned long long*>(src) + tid);
 }
 
-// sum_{t<n} p[t * stride] in index order, eight loads in flight (adding the 0.0 of a padded slot
+// sum_{t<n} p[t * stride] in index order, sixteen loads in flight (adding the 0.0 of a padded slot
 // changes nothing, so the value equals the plain sequential loop)
 __device__ __forceinline__ double vl_ordered_sum(const double* p, size_t stride, int n) {
   double v = 0.0;
-  for (int t = 0; t < n; t += 8) {
-    double x[8];
+#ifndef VL_SUM_WIDTH
+#define VL_SUM_WIDTH 16
+#endif
+  for (int t = 0; t < n; t += VL_SUM_WIDTH) {
+    double x[VL_SUM_WIDTH];
 #pragma unroll
-    for (int u = 0; u < 8; ++u) x[u] = (t + u < n) ? __ldcg(p + (size_t)(t + u) * stride) : 0.0;
+    for (int u = 0; u < VL_SUM_WIDTH; ++u) x[u] = (t + u < n) ? __ldcg(p + (size_t)(t + u) * stride) : 0.0;
 #pragma unroll
-    for (int u = 0; u < 8; ++u) v += x[u];
+    for (int u = 0; u < VL_SUM_WIDTH; ++u) v += x[u];
   }
   return v;
 }

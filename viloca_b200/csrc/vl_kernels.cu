@@ -21,8 +21,12 @@ __device__ unsigned long long vl_su_cycles[8];     // vl_scalar_update phases of
 #endif
 #include "vl_cavi.cuh"
 #include <cstdio>
+#include <cstdlib>
 
 #include "vl_launch.h"
+#ifndef VL_ATTR_KB
+#define VL_ATTR_KB 220
+#endif
 #include "../../include/viloca_b200.h"
 
 // Per-phase cycle counters of restart 0's tile 0 (development aid, -DVL_RS_PROFILE):
@@ -139,7 +143,7 @@ __device__ __forceinline__ bool vl_haplo_body(const VlProblem* __restrict__ prob
   __shared__ uint64_t bars[VL_MAX_STAGES];
   __shared__ double red[VL_THREADS / 32][4];
 
-  GK_DECL(tm.x == 0 && (tm.y & 0xFFFFFF) == 0);
+  GK_DECL(tm.x == 0 && (tm.y & 0xFFFFF) == 0);     // (all read parts of column tile 0: the loop phases are summed over them)
   const VlProblem& P = probs[tm.x];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, q = lane & 3;
   // Large windows: n_hsplit CTAs share the reads of a column tile;
@@ -173,23 +177,32 @@ __device__ __forceinline__ bool vl_haplo_body(const VlProblem* __restrict__ prob
   const int ktz = s_kt_old;                // tiles of the layout w z is stored in
   if (ktz < 0 || ktz > KTM) return false;
   if (early) asm volatile("fence.proxy.async;\n" ::: "memory");   // bulk copies below read what other CTAs wrote
-  // a narrow layout has small stages: use the same shared memory for a deeper pipeline
-  const int st_stride = DM_STAGE + VL_H_NC * vl_ks(ktz);
-  constexpr int OWN_DOUBLES = vl_haplo_doubles(KTM);
-  const int nstg = min(VL_MAX_STAGES, max(stage_doubles, OWN_DOUBLES) / st_stride);
-
   const int Npad = P.Npad;
   const int KSz = vl_ks(ktz), K8z = 8 * ktz;
   const int nchunks_all = Npad / VL_H_NC;
   const int per_split = (nchunks_all + n_split - 1) / n_split;
-  const int c_first = min(nchunks_all, split * per_split);            // this CTA's stages of 32 reads
+  const int c_first = min(nchunks_all, split * per_split);            // this CTA's chunks of 32 reads
   const int nchunks = min(nchunks_all, c_first + per_split) - c_first;
+  // A stage = `grp` consecutive chunks (contiguous in dm and in w z: two bulk copies, one barrier phase).
+  // With shared memory to spare (narrow layout, or the deep launch of a chunk with few tiles in flight)
+  // the stages grow: an update of a lone restart is a chain of latencies, and every stage costs one
+  // issue by one thread and one CTA-wide barrier.  The rows are visited in the same order whatever grp.
+  const int chunk_doubles = DM_STAGE + VL_H_NC * vl_ks(ktz);
+  constexpr int OWN_DOUBLES = vl_haplo_doubles(KTM);
+  const int fit = max(stage_doubles, OWN_DOUBLES) / chunk_doubles;     // chunks the shared memory holds
+#ifdef VL_NO_GROUP
+  const int grp = 1;
+#else
+  const int grp = (fit >= nchunks) ? max(1, (nchunks + 2) / 3) : max(1, min(8, fit / 3));
+#endif
+  const int st_stride = grp * chunk_doubles;
+  const int nstg = max(1, min(VL_MAX_STAGES, fit / grp));
+  const int nstages = (nchunks + grp - 1) / grp;
   const double* __restrict__ dmg = P.dm + (size_t)ty * Npad * VL_PT + (size_t)c_first * VL_H_NC * VL_PT;
   const double* wzg = P.wz;     // (mutable state: no __restrict__, these must stay coherent loads)
   const double* wzs = wzg + (size_t)c_first * VL_H_NC * vl_ks(ktz);   // first read of this CTA's range
   const int* gat = P.gat;
-  const uint32_t z_bytes = (uint32_t)(VL_H_NC * KSz * sizeof(double));
-  const uint32_t stage_bytes = (uint32_t)(DM_STAGE * sizeof(double)) + z_bytes;
+  const uint32_t z_bytes = (uint32_t)(VL_H_NC * KSz * sizeof(double));       // per chunk
 
   if (tid == 0) {
     for (int s = 0; s < nstg; ++s) vl_mbar_init(&bars[s], 1);
@@ -203,15 +216,17 @@ __device__ __forceinline__ bool vl_haplo_body(const VlProblem* __restrict__ prob
     if (j == VL_B) s_refb[pos] = (l >= 0) ? P.ref[l] : 255u;
   }
   __syncthreads();
+  // stage c: chunks [c grp, c grp + n); shared memory: n dm chunks, then (at grp * DM_STAGE) their w z rows
   auto issue = [&](int c) {
     const int sn = c % nstg;
+    const int n = min(grp, nchunks - c * grp);
     double* dst = stg + (size_t)sn * st_stride;
-    vl_mbar_expect_tx(&bars[sn], stage_bytes);
-    vl_tma_load_1d(dst, dmg + (size_t)c * DM_STAGE, DM_STAGE * sizeof(double), &bars[sn]);
-    vl_tma_load_1d(dst + DM_STAGE, wzs + (size_t)c * VL_H_NC * KSz, z_bytes, &bars[sn]);
+    vl_mbar_expect_tx(&bars[sn], (uint32_t)n * ((uint32_t)(DM_STAGE * sizeof(double)) + z_bytes));
+    vl_tma_load_1d(dst, dmg + (size_t)c * grp * DM_STAGE, (uint32_t)n * DM_STAGE * sizeof(double), &bars[sn]);
+    vl_tma_load_1d(dst + grp * DM_STAGE, wzs + (size_t)c * grp * VL_H_NC * KSz, (uint32_t)n * z_bytes, &bars[sn]);
   };
   if (tid == 0)
-    for (int c = 0; c < nstg - 1 && c < nchunks; ++c) issue(c);
+    for (int c = 0; c < nstg - 1 && c < nstages; ++c) issue(c);
 
   // warp = all 16 columns (two m-tiles) x 8 of the 32 reads of every stage: one w z fragment
   // feeds two DMMAs
@@ -225,12 +240,7 @@ __device__ __forceinline__ bool vl_haplo_body(const VlProblem* __restrict__ prob
   GK_TICK(0);
   vl_dispatch_tiles<KTM>(ktz, [&](auto ktc) {
     constexpr int KT = decltype(ktc)::value;
-    for (int c = 0; c < nchunks; ++c) {
-      const int st = c % nstg;
-      if (tid == 0 && c + nstg - 1 < nchunks) issue(c + nstg - 1);
-      vl_mbar_wait(&bars[st], (c / nstg) & 1);
-      const double* dt = stg + (size_t)st * st_stride;
-      const double* zt = dt + DM_STAGE;
+    auto chunk = [&](const double* dt, const double* zt) {     // 32 reads: rows warp * 8 + 4 s + q
 #pragma unroll
       for (int s = 0; s < VL_H_NC / 16; ++s) {
         const int row = warp * (VL_H_NC / 4) + 4 * s + q;
@@ -244,7 +254,27 @@ __device__ __forceinline__ bool vl_haplo_body(const VlProblem* __restrict__ prob
           vl_dmma(acc[1][i], a1, bf);
         }
       }
-      __syncthreads();
+    };
+    if (grp == 1) {                    // (the loop of the busy phases, kept free of the grouping arithmetic)
+      for (int c = 0; c < nchunks; ++c) {
+        const int st = c % nstg;
+        if (tid == 0 && c + nstg - 1 < nchunks) issue(c + nstg - 1);
+        vl_mbar_wait(&bars[st], (c / nstg) & 1);
+        const double* dt = stg + (size_t)st * st_stride;
+        chunk(dt, dt + DM_STAGE);
+        __syncthreads();
+      }
+    } else {
+      for (int c = 0; c < nstages; ++c) {
+        const int st = c % nstg;
+        if (tid == 0 && c + nstg - 1 < nstages) issue(c + nstg - 1);
+        vl_mbar_wait(&bars[st], (c / nstg) & 1);
+        const int n = min(grp, nchunks - c * grp);
+        const double* dt = stg + (size_t)st * st_stride;
+        const double* zt = dt + grp * DM_STAGE;
+        for (int u = 0; u < n; ++u) chunk(dt + u * DM_STAGE, zt + u * VL_H_NC * KSz);
+        __syncthreads();
+      }
     }
   });
 
@@ -278,12 +308,14 @@ __device__ __forceinline__ bool vl_haplo_body(const VlProblem* __restrict__ prob
     combine_warps();
     if (n_split > 1 && !vl_split_combine(P, T, ty, split, n_split, VL_PT * K8z)) return false;
   }
+  GK_TICK(2);
   // the state of this update: published by the scalar update of the previous one
   if (early) {
     if (!vl_wait_published(P.st, pub_want)) return false;
     vl_load_state(&sS, P.st, tid);
     __syncthreads();
   }
+  GK_TICK(6);
   const VlState* S = &sS;
   const int ktl = S->ktl;
   if (S->active == 0 || ktl > KTM || S->ktl_z != ktz) return false;
@@ -456,26 +488,37 @@ __device__ __forceinline__ bool vl_cluster_tile(const VlProblem* __restrict__ pr
   const int n0 = tm.y * VL_ZT_READS;
   const double* __restrict__ dmg = P.dm + (size_t)n0 * VL_PT;
   const double* gmg = P.gm;
-  const uint32_t gm_bytes = (uint32_t)(VL_PT * KS * sizeof(double));
-  const uint32_t stage_bytes = (uint32_t)(DM_STAGE * sizeof(double)) + gm_bytes;
-  // narrow layouts: deeper pipeline in the same shared memory (see vl_haplo_kernel)
-  const int st_stride = DM_STAGE + VL_PT * KS;
-  const int nstg = min(VL_MAX_STAGES, max(stage_doubles, vl_zstages(KTM) * ST_STRIDE) / st_stride);
+  const uint32_t gm_bytes = (uint32_t)(VL_PT * KS * sizeof(double));          // per column tile
+  // a stage = `grp` consecutive column tiles (their gm rows are contiguous: one copy; one dm copy per
+  // tile; one barrier phase): larger stages when shared memory is to spare, see vl_haplo_body
+  const int tile_doubles = DM_STAGE + VL_PT * KS;
+  const int fit = max(stage_doubles, vl_zstages(KTM) * ST_STRIDE) / tile_doubles;
+#ifdef VL_NO_GROUP
+  const int grp = 1;
+#else
+  const int grp = (fit >= nst) ? max(1, (nst + 2) / 3) : max(1, min(8, fit / 3));
+#endif
+  const int st_stride = grp * tile_doubles;
+  const int nstg = max(1, min(VL_MAX_STAGES, fit / grp));
+  const int nstages = (nst + grp - 1) / grp;
 
   if (tid == 0) {
     for (int s = 0; s < nstg; ++s) vl_mbar_init(&bars[s], 1);
     vl_fence_mbar_init();
   }
   __syncthreads();
+  // stage c: column tiles [c grp, c grp + n); shared memory: n dm tiles, then (at grp * DM_STAGE) their gm rows
   auto issue = [&](int c) {
     const int sn = c % nstg;
+    const int n = min(grp, nst - c * grp);
     double* dst = stg + (size_t)sn * st_stride;
-    vl_mbar_expect_tx(&bars[sn], stage_bytes);
-    vl_tma_load_1d(dst, dmg + (size_t)c * Npad * VL_PT, DM_STAGE * sizeof(double), &bars[sn]);
-    vl_tma_load_1d(dst + DM_STAGE, gmg + (size_t)c * VL_PT * KS, gm_bytes, &bars[sn]);
+    vl_mbar_expect_tx(&bars[sn], (uint32_t)n * ((uint32_t)(DM_STAGE * sizeof(double)) + gm_bytes));
+    for (int u = 0; u < n; ++u)
+      vl_tma_load_1d(dst + u * DM_STAGE, dmg + (size_t)(c * grp + u) * Npad * VL_PT, DM_STAGE * sizeof(double), &bars[sn]);
+    vl_tma_load_1d(dst + grp * DM_STAGE, gmg + (size_t)c * grp * VL_PT * KS, (uint32_t)n * gm_bytes, &bars[sn]);
   };
   if (tid == 0)
-    for (int c = 0; c < nstg - 1 && c < nst; ++c) issue(c);
+    for (int c = 0; c < nstg - 1 && c < nstages; ++c) issue(c);
 
   double acc[2][KTM][2];
 #pragma unroll
@@ -499,12 +542,7 @@ __device__ __forceinline__ bool vl_cluster_tile(const VlProblem* __restrict__ pr
   GK_TICK(8);
   vl_dispatch_tiles<KTM>(ktl, [&](auto ktc) {
     constexpr int KT = decltype(ktc)::value;
-    for (int c = 0; c < nst; ++c) {
-      const int st = c % nstg;
-      if (tid == 0 && c + nstg - 1 < nst) issue(c + nstg - 1);
-      vl_mbar_wait(&bars[st], (c / nstg) & 1);
-      const double* dt = stg + (size_t)st * st_stride;
-      const double* gt = dt + DM_STAGE + g;
+    auto tile = [&](const double* dt, const double* gt) {      // one column tile: 16 columns x this warp's 16 reads
 #pragma unroll
       for (int s = 0; s < 4; ++s) {
         const int col = (4 * s + q + 4 * (g & 3)) & 15;
@@ -518,7 +556,27 @@ __device__ __forceinline__ bool vl_cluster_tile(const VlProblem* __restrict__ pr
           vl_dmma(acc[1][i], a1, bf);
         }
       }
-      __syncthreads();
+    };
+    if (grp == 1) {                    // (the loop of the busy phases, kept free of the grouping arithmetic)
+      for (int c = 0; c < nst; ++c) {
+        const int st = c % nstg;
+        if (tid == 0 && c + nstg - 1 < nst) issue(c + nstg - 1);
+        vl_mbar_wait(&bars[st], (c / nstg) & 1);
+        const double* dt = stg + (size_t)st * st_stride;
+        tile(dt, dt + DM_STAGE + g);
+        __syncthreads();
+      }
+    } else {
+      for (int c = 0; c < nstages; ++c) {
+        const int st = c % nstg;
+        if (tid == 0 && c + nstg - 1 < nstages) issue(c + nstg - 1);
+        vl_mbar_wait(&bars[st], (c / nstg) & 1);
+        const int n = min(grp, nst - c * grp);
+        const double* dt = stg + (size_t)st * st_stride;
+        const double* gt = dt + grp * DM_STAGE + g;
+        for (int u = 0; u < n; ++u) tile(dt + u * DM_STAGE, gt + u * VL_PT * KS);
+        __syncthreads();
+      }
     }
   });
 
@@ -712,28 +770,33 @@ vl_cluster_kernel(const VlProblem* __restrict__ probs, const int2* __restrict__ 
 }
 
 // =========================================================================================
-// A whole chunk of updates of one kernel class in ONE launch of persistent worker CTAs.  Every
-// scheduled restart has a scheduling word (VlCtl) that names its current phase -- the haplotype
-// tiles of update k of the chunk, then its read tiles -- and the next tile of it to hand out.  A
-// worker claims a tile with one atomicAdd on that word, runs it, counts it done; the worker that
-// finishes the last tile of a phase opens the next one.  No worker ever waits for a tile that
-// nobody runs: a phase is opened only when everything it reads has been written, with one
-// exception, the haplotype tiles of update k + 1, which are opened when the last read tile of
-// update k has arrived and wait (after their operand loop) for the scalar update that this very
-// tile's CTA is running.  Restarts advance independently of each other; a restart that leaves its
-// loop, finishes the chunk, or whose layout outgrows the kernel class is marked VL_PHASE_LEFT.
-// Nothing depends on the order in which the hardware dispatches blocks.
+// A whole chunk of updates of one kernel class in ONE launch.  Every scheduled restart has a
+// scheduling word (VlCtl) that names its current phase -- the haplotype tiles of update k of the
+// chunk, then its read tiles -- and the next tile of it to hand out.  A block is a worker for ONE
+// tile: it claims whichever tile is open with one atomicAdd on that word (polling while none is),
+// runs it, counts it done and exits; the block that finishes the last tile of a phase opens the
+// next one.  The launch has as many blocks as the chunk can have tiles; blocks that find every
+// restart gone exit at once.  No block ever waits for a tile that nobody runs: a phase is opened
+// only when everything it reads has been written, with one exception, the haplotype tiles of
+// update k + 1, which are opened when the last read tile of update k has arrived and wait (after
+// their operand loop) for the scalar update that this very tile's CTA is running.  Restarts
+// advance independently of each other; a restart that leaves its loop, finishes the chunk, or
+// whose layout outgrows the kernel class is marked VL_PHASE_LEFT.  Nothing depends on the order in
+// which the hardware dispatches blocks.  (One tile per block rather than a loop of tiles per
+// block: inside a loop the compiler keeps the constants of both tile kinds in registers across
+// iterations and spills in the DMMA loops.)
 // =========================================================================================
 __device__ __forceinline__ int vl_phase_tiles(const VlProblem& P, unsigned phase) {
   return (phase & 1u) ? P.n_ztiles : P.n_htiles * P.n_hsplit;
 }
 
-// Warp 0 of a worker: find a restart with a tile to hand out and claim it.  task = (problem, phase,
+// Warp 0 of a block: find a restart with a tile to hand out and claim it.  task = (problem, phase,
 // tile index); problem < 0 when every restart of the launch has left the chunk.
 __device__ __forceinline__ void vl_sched_claim(const VlProblem* __restrict__ probs, const int* __restrict__ rlist,
-                                               const int n_r, VlCtl* ctl, const int* n_live, int& cursor, int* task) {
+                                               const int n_r, VlCtl* ctl, const int* n_live, int* task) {
   const int lane = threadIdx.x & 31;
   unsigned idle = 0;
+  const int cursor = (int)(blockIdx.x % (unsigned)n_r);     // blocks start their search at different restarts
   for (;;) {
     int got_p = -1;
     unsigned got_phase = 0, got_idx = 0;
@@ -760,9 +823,6 @@ __device__ __forceinline__ void vl_sched_claim(const VlProblem* __restrict__ pro
         const unsigned phase = (unsigned)(old >> 32), idx = (unsigned)old;
         if (phase != VL_PHASE_LEFT && idx < (unsigned)vl_phase_tiles(probs[pp], phase)) {
           got_p = pp; got_phase = phase; got_idx = idx;
-          int at = cursor + base + src;          // the next search starts at this restart: its next tile is likely open
-          if (at >= n_r) at -= n_r;
-          cursor = at;
         }
       }
     }
@@ -774,8 +834,8 @@ __device__ __forceinline__ void vl_sched_claim(const VlProblem* __restrict__ pro
       if (lane == 0) task[0] = -1;
       return;
     }
-    if (++idle > (1u << 26)) __trap();           // minutes without any tile to run although restarts are live: an error, not a hang
-    __nanosleep(idle < 64 ? 20 : 200);
+    if (++idle > (1u << 26)) __trap();           // a long time without any tile to run although restarts are live: an error, not a hang
+    __nanosleep(idle < 4096 ? 40 : 1000);
   }
 }
 
@@ -786,43 +846,141 @@ vl_sched_kernel(const VlProblem* __restrict__ probs, const int* __restrict__ rli
                 int4* __restrict__ pstat, const int stage_doubles) {
   __shared__ int s_task[4];
   __shared__ int s_flag;
-  __shared__ VlState sZ;                     // a read tile's copy of the state before the update
-  const int tid = threadIdx.x;
-  int cursor = (int)(blockIdx.x % (unsigned)n_r);
-  for (;;) {
-    if (tid < 32) vl_sched_claim(probs, rlist, n_r, ctl, n_live, cursor, s_task);
-    __syncthreads();
-    const int p = s_task[0];
-    const unsigned phase = (unsigned)s_task[1];
-    const int idx = s_task[2];
-    __syncthreads();                         // s_task is rewritten by the next claim
-    if (p < 0) return;
-    const VlProblem& P = probs[p];
-    VlCtl* C = ctl + p;
-    const int k = (int)(phase >> 1);
-    __threadfence();                         // what the claim word promised is visible to every thread of the CTA
-    if ((phase & 1u) == 0) {
-      // ---- haplotype tile of update k ----
+  if (threadIdx.x < 32) vl_sched_claim(probs, rlist, n_r, ctl, n_live, s_task);
+  __syncthreads();
+  if (s_task[0] < 0) return;
+  GK_DECL(s_task[0] == 0 && s_task[2] == 0);
+  // (the task is read again from shared memory after the tile, so that nothing of the scheduler is live in it)
+  if ((s_task[1] & 1) == 0) {
+    // ---- haplotype tile of update k ----
+    {
+      const int p = s_task[0], idx = s_task[2], k = s_task[1] >> 1;
+      const VlProblem& P = probs[p];
       const int t = idx % P.n_htiles, sp = idx / P.n_htiles;
       const int2 tm = make_int2(p, P.n_hsplit > 1 ? (t | (sp << 20) | (P.n_hsplit << 24)) : t);
-      GK_DECL(p == 0 && idx == 0);
-      asm volatile("fence.proxy.async;\n" ::: "memory");      // its bulk copies read what other CTAs wrote
       vl_haplo_body<KTM, MODE, SPLIT>(probs, tm, stage_doubles, true, chunk_base[p] + k);
+    }
 #ifdef VL_RS_PROFILE
-      gk_t_ = clock64();
+    gk_t_ = clock64();
 #endif
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      const int p = s_task[0];
+      const unsigned phase = (unsigned)s_task[1];
+      const int k = (int)(phase >> 1);
+      const VlProblem& P = probs[p];
+      VlCtl* C = ctl + p;
+      // C->done counts the tiles of the whole chunk: this phase is complete when it reaches (k + 1) nh + k nz
+      if (atomicAdd(&C->done, 1) + 1 == (k + 1) * P.n_htiles * P.n_hsplit + k * P.n_ztiles) {
+        // last tile of the phase: the tiles that ran have seen the published state of this update, so it is final here
+        __threadfence();
+        const bool live = *reinterpret_cast<const volatile int*>(&P.st->active) != 0 &&
+                          *reinterpret_cast<const volatile int*>(&P.st->ktl) <= KTM;
+        if (!live) {                       // left its loop, or the layout grew past this kernel class: the host reschedules it
+          atomicExch(&C->claim, (unsigned long long)VL_PHASE_LEFT << 32);
+          __threadfence();
+          atomicSub(n_live, 1);
+        } else {
+          atomicExch(&C->claim, (unsigned long long)(phase + 1u) << 32);
+        }
+      }
+    }
+    GK_TICK(7);
+    return;
+  }
+  // ---- read tile of update k ----
+  __shared__ VlState sZ;                     // the state before the update
+  asm volatile("fence.proxy.async;\n" ::: "memory");     // its bulk copies read what other CTAs wrote
+  const bool ran = vl_cluster_tile<KTM, MODE>(probs, make_int2(s_task[0], s_task[2]), stage_doubles, sZ);
+  __threadfence();
+  __syncthreads();
+  const int p = s_task[0];
+  const unsigned phase = (unsigned)s_task[1];
+  const int k = (int)(phase >> 1);
+  const VlProblem& P = probs[p];
+  VlCtl* C = ctl + p;
+  if (threadIdx.x == 0) s_flag = (atomicAdd(&C->done, 1) + 1 == (k + 1) * (P.n_htiles * P.n_hsplit + P.n_ztiles)) ? 1 : 0;
+  __syncthreads();
+  if (!s_flag) return;
+  __threadfence();
+  const bool more = k + 1 < n_iter;
+  // the haplotype tiles of the next update may start their operand loops while this CTA does the
+  // scalar update (they read w z, which is complete, and wait for the published state afterwards)
+  if (threadIdx.x == 0 && ran && more) atomicExch(&C->claim, (unsigned long long)(phase + 1u) << 32);
+#ifdef VL_RS_PROFILE
+  const bool gk_last_ = p == 0 && threadIdx.x == 0;
+  long long gk_t2_ = clock64();
+#endif
+  if (ran) vl_cluster_close<MODE>(P, sZ, done_count, pstat + p);
+#ifdef VL_RS_PROFILE
+  if (gk_last_) { atomicAdd(&vl_gk_cycles[13], (unsigned long long)(clock64() - gk_t2_)); atomicAdd(&vl_gk_cycles[17], 1ull); }
+#endif
+  if (!ran || !more) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      __threadfence();
+      atomicExch(&C->claim, (unsigned long long)VL_PHASE_LEFT << 32);
+      __threadfence();
+      atomicSub(n_live, 1);
+    }
+  }
+}
+
+// The same scheduler with persistent workers: a block runs tile after tile until every restart of
+// the launch has left the chunk, so a launch occupies only as many SM slots as it is given and
+// launches of different kernel classes share the GPU side by side.  The tiles are functions of their
+// own here: inlined into the loop, the compiler allocates the registers of both tile kinds and of the
+// loop together and spills in the DMMA loops.
+template <int KTM, int MODE, bool SPLIT>
+__device__ __noinline__ void vl_haplo_task(const VlProblem* __restrict__ probs, const int2 tm, const int stage_doubles,
+                                           const int pub_want) {
+  vl_haplo_body<KTM, MODE, SPLIT>(probs, tm, stage_doubles, true, pub_want);
+}
+template <int KTM, int MODE>
+__device__ __noinline__ bool vl_cluster_task(const VlProblem* __restrict__ probs, const int2 tm, const int stage_doubles,
+                                             VlState* sS) {
+  return vl_cluster_tile<KTM, MODE>(probs, tm, stage_doubles, *sS);
+}
+template <int MODE>
+__device__ __noinline__ void vl_close_task(const VlProblem* P, const VlState* R, int* done_count, int4* pstat_entry) {
+  vl_cluster_close<MODE>(*P, *R, done_count, pstat_entry);
+}
+
+template <int KTM, int MODE, bool SPLIT>
+__global__ void __launch_bounds__(VL_THREADS, vl_min_ctas(KTM))
+vl_sched_persistent_kernel(const VlProblem* __restrict__ probs, const int* __restrict__ rlist, const int n_r, const int n_iter,
+                           const int* __restrict__ chunk_base, VlCtl* ctl, int* n_live, int* __restrict__ done_count,
+                           int4* __restrict__ pstat, const int stage_doubles) {
+  __shared__ int s_task[4];
+  __shared__ int s_flag;
+  __shared__ VlState sZ;
+  for (;;) {
+    if (threadIdx.x < 32) vl_sched_claim(probs, rlist, n_r, ctl, n_live, s_task);
+    __syncthreads();
+    if (s_task[0] < 0) return;
+    if ((s_task[1] & 1) == 0) {
+      {
+        const int p = s_task[0], idx = s_task[2], k = s_task[1] >> 1;
+        const VlProblem& P = probs[p];
+        const int t = idx % P.n_htiles, sp = idx / P.n_htiles;
+        vl_haplo_task<KTM, MODE, SPLIT>(probs, make_int2(p, P.n_hsplit > 1 ? (t | (sp << 20) | (P.n_hsplit << 24)) : t),
+                                        stage_doubles, chunk_base[p] + k);
+      }
       __threadfence();
       __syncthreads();
-      if (tid == 0) {
-        if (atomicAdd(&C->done, 1) == P.n_htiles * P.n_hsplit - 1) {
-          // last tile of the phase.  Every tile has seen the published state, so it is final here.
+      if (threadIdx.x == 0) {
+        const int p = s_task[0];
+        const unsigned phase = (unsigned)s_task[1];
+        const int k = (int)(phase >> 1);
+        const VlProblem& P = probs[p];
+        VlCtl* C = ctl + p;
+        const int nh = P.n_htiles * P.n_hsplit, nz = P.n_ztiles;
+        if (atomicAdd(&C->done, 1) + 1 == (k + 1) * nh + k * nz) {
           __threadfence();
-          const VlState* S = P.st;
-          const int active = *reinterpret_cast<const volatile int*>(&S->active);
-          const int ktl = *reinterpret_cast<const volatile int*>(&S->ktl);
-          C->done = 0;
-          __threadfence();
-          if (active == 0 || ktl > KTM) {    // left its loop, or the layout grew past this kernel class: the host reschedules it
+          const bool live = *reinterpret_cast<const volatile int*>(&P.st->active) != 0 &&
+                            *reinterpret_cast<const volatile int*>(&P.st->ktl) <= KTM;
+          if (!live) {
             atomicExch(&C->claim, (unsigned long long)VL_PHASE_LEFT << 32);
             __threadfence();
             atomicSub(n_live, 1);
@@ -831,37 +989,27 @@ vl_sched_kernel(const VlProblem* __restrict__ probs, const int* __restrict__ rli
           }
         }
       }
-      GK_TICK(7);
+      __syncthreads();                       // every thread has read the task before the next claim rewrites it
     } else {
-      // ---- read tile of update k ----
-      GK_DECL(p == 0 && idx == 0);
       asm volatile("fence.proxy.async;\n" ::: "memory");
-      const bool ran = vl_cluster_tile<KTM, MODE>(probs, make_int2(p, idx), stage_doubles, sZ);
+      const bool ran = vl_cluster_task<KTM, MODE>(probs, make_int2(s_task[0], s_task[2]), stage_doubles, &sZ);
       __threadfence();
       __syncthreads();
-      if (tid == 0) s_flag = (atomicAdd(&C->done, 1) == P.n_ztiles - 1) ? 1 : 0;
+      const int p = s_task[0];
+      const unsigned phase = (unsigned)s_task[1];
+      const int k = (int)(phase >> 1);
+      const VlProblem& P = probs[p];
+      VlCtl* C = ctl + p;
+      if (threadIdx.x == 0) s_flag = (atomicAdd(&C->done, 1) + 1 == (k + 1) * (P.n_htiles * P.n_hsplit + P.n_ztiles)) ? 1 : 0;
       __syncthreads();
       if (s_flag) {
         __threadfence();
         const bool more = k + 1 < n_iter;
-        if (tid == 0) {
-          C->done = 0;
-          __threadfence();
-          // the haplotype tiles of the next update may start their operand loops while this CTA does the
-          // scalar update (they read w z, which is complete, and wait for the published state afterwards)
-          if (ran && more) atomicExch(&C->claim, (unsigned long long)(phase + 1u) << 32);
-        }
-#ifdef VL_RS_PROFILE
-        const bool gk_last_ = p == 0 && tid == 0;
-        long long gk_t2_ = clock64();
-#endif
-        if (ran) vl_cluster_close<MODE>(P, sZ, done_count, pstat + p);
-#ifdef VL_RS_PROFILE
-        if (gk_last_) atomicAdd(&vl_gk_cycles[13], (unsigned long long)(clock64() - gk_t2_));
-#endif
+        if (threadIdx.x == 0 && ran && more) atomicExch(&C->claim, (unsigned long long)(phase + 1u) << 32);
+        if (ran) vl_close_task<MODE>(&P, &sZ, done_count, pstat + p);
         if (!ran || !more) {
           __syncthreads();
-          if (tid == 0) {
+          if (threadIdx.x == 0) {
             __threadfence();
             atomicExch(&C->claim, (unsigned long long)VL_PHASE_LEFT << 32);
             __threadfence();
@@ -869,8 +1017,8 @@ vl_sched_kernel(const VlProblem* __restrict__ probs, const int* __restrict__ rli
           }
         }
       }
+      __syncthreads();
     }
-    __syncthreads();
   }
 }
 
@@ -1045,6 +1193,23 @@ __global__ void vl_exp_test_kernel(const double* __restrict__ x, double* __restr
   if (i + 1 < n) out[i + 1] = ev[1];
 }
 
+// roofline denominator: the FP64 tensor instruction of the contraction kernels (DMMA m8n8k4) in a
+// register-resident loop with eight independent accumulators per warp
+__global__ void __launch_bounds__(256) vl_dmma_peak_kernel(double* __restrict__ out, int iters, double a0, double b0) {
+  double acc[8][2];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { acc[i][0] = 0.0; acc[i][1] = 0.0; }
+  const double a = a0 + threadIdx.x * 1e-9, b = b0;
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) vl_dmma(acc[i], a, b);
+  }
+  double s = 0.0;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) s += acc[i][0] + acc[i][1];
+  out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
 template <int KTM>
 constexpr size_t smem_haplo() {
   return (size_t)vl_haplo_doubles(KTM) * sizeof(double);
@@ -1078,11 +1243,13 @@ cudaError_t launch_cluster(const VlProblem* probs, const int2* tiles, int n, int
 // are mostly idle and one restart's update is a chain of latencies -- enough to have (nearly) all
 // operand stages of a tile in flight at once.  Same arithmetic either way.
 template <int KTM>
-size_t sched_smem(bool deep, int* stage_doubles) {
+size_t sched_smem(int deep, int* stage_doubles) {
   size_t smem = std::max(smem_haplo<KTM>(), smem_cluster<KTM>());
   *stage_doubles = 0;
-  const size_t big = (size_t)104 * 1024;        // two CTAs per SM
-  if (deep && big > smem) {
+  // deep = 1: two CTAs per SM; deep = 2: the launch has at most one tile per SM in flight, every CTA gets an SM's shared memory
+  static const size_t dev_kb = std::getenv("VL_DEEP_KB") ? (size_t)std::atoi(std::getenv("VL_DEEP_KB")) : 0;   // development aid
+  const size_t big = (deep ? (dev_kb ? dev_kb : (deep >= 2 ? (size_t)200 : (size_t)104)) : (size_t)0) * 1024;
+  if (big > smem) {
     *stage_doubles = (int)((big - (VL_THREADS / 32) * 8 * KTM * sizeof(double)) / sizeof(double));
     smem = big;
   }
@@ -1090,28 +1257,39 @@ size_t sched_smem(bool deep, int* stage_doubles) {
 }
 
 template <int KTM, int MODE, bool SPLIT>
-cudaError_t sched_occupancy(int deep, int* ctas_per_sm, int* smem_bytes, int* regs) {
+cudaError_t sched_occupancy(int deep, int persistent, int* ctas_per_sm, int* smem_bytes, int* regs) {
   int sd = 0;
-  const size_t smem = sched_smem<KTM>(deep != 0, &sd);
-  cudaError_t e = cudaFuncSetAttribute(vl_sched_kernel<KTM, MODE, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(160 * 1024));
+  const size_t smem = sched_smem<KTM>(deep, &sd);
+  const void* fn = persistent ? (const void*)vl_sched_persistent_kernel<KTM, MODE, SPLIT> : (const void*)vl_sched_kernel<KTM, MODE, SPLIT>;
+  cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(VL_ATTR_KB * 1024));
   if (e != cudaSuccess) return e;
   cudaFuncAttributes at;
-  e = cudaFuncGetAttributes(&at, vl_sched_kernel<KTM, MODE, SPLIT>);
+  e = cudaFuncGetAttributes(&at, fn);
   if (e != cudaSuccess) return e;
   *regs = at.numRegs;
   *smem_bytes = (int)(smem + at.sharedSizeBytes);
+  if (persistent) return cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas_per_sm, vl_sched_persistent_kernel<KTM, MODE, SPLIT>, VL_THREADS, smem);
   return cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas_per_sm, vl_sched_kernel<KTM, MODE, SPLIT>, VL_THREADS, smem);
 }
 
 template <int KTM, int MODE, bool SPLIT>
 cudaError_t launch_sched(const VlProblem* probs, const int* rlist, int n_r, int n_updates, const int* chunk_base,
-                         VlCtl* ctl, int* n_live, int* done_count, int4* pstat, int n_workers, int deep, cudaStream_t stream) {
+                         VlCtl* ctl, int* n_live, int* done_count, int4* pstat, long long n_blocks, int deep, int persistent,
+                         cudaStream_t stream) {
   int stage_doubles = 0;
-  const size_t smem = sched_smem<KTM>(deep != 0, &stage_doubles);
-  cudaError_t e = cudaFuncSetAttribute(vl_sched_kernel<KTM, MODE, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(160 * 1024));
+  const size_t smem = sched_smem<KTM>(deep, &stage_doubles);
+  if (n_blocks > 0x7fffffffLL) return cudaErrorInvalidValue;
+  if (persistent) {
+    cudaError_t e = cudaFuncSetAttribute(vl_sched_persistent_kernel<KTM, MODE, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(VL_ATTR_KB * 1024));
+    if (e != cudaSuccess) return e;
+    vl_sched_persistent_kernel<KTM, MODE, SPLIT><<<(unsigned)n_blocks, VL_THREADS, smem, stream>>>(probs, rlist, n_r, n_updates, chunk_base,
+                                                                                            ctl, n_live, done_count, pstat, stage_doubles);
+    return cudaGetLastError();
+  }
+  cudaError_t e = cudaFuncSetAttribute(vl_sched_kernel<KTM, MODE, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(VL_ATTR_KB * 1024));
   if (e != cudaSuccess) return e;
-  vl_sched_kernel<KTM, MODE, SPLIT><<<(unsigned)n_workers, VL_THREADS, smem, stream>>>(probs, rlist, n_r, n_updates, chunk_base, ctl,
-                                                                                  n_live, done_count, pstat, stage_doubles);
+  vl_sched_kernel<KTM, MODE, SPLIT><<<(unsigned)n_blocks, VL_THREADS, smem, stream>>>(probs, rlist, n_r, n_updates, chunk_base, ctl,
+                                                                                 n_live, done_count, pstat, stage_doubles);
   return cudaGetLastError();
 }
 
@@ -1141,8 +1319,8 @@ int vl_class_capacity(int cls) { return 2 << cls; }
     default: return cudaErrorInvalidValue;                                               \
   }
 
-cudaError_t vl_sched_occupancy(int cls, int mode, int split, int deep, int* ctas_per_sm, int* smem_bytes, int* regs) {
-  VL_DISPATCH(sched_occupancy, deep, ctas_per_sm, smem_bytes, regs)
+cudaError_t vl_sched_occupancy(int cls, int mode, int split, int deep, int persistent, int* ctas_per_sm, int* smem_bytes, int* regs) {
+  VL_DISPATCH(sched_occupancy, deep, persistent, ctas_per_sm, smem_bytes, regs)
 }
 
 cudaError_t vl_launch_haplo(int cls, int mode, int split, const VlProblem* probs, const int2* tiles, int n_tiles,
@@ -1159,10 +1337,10 @@ cudaError_t vl_launch_cluster(int cls, int mode, const VlProblem* probs, const i
 }
 
 cudaError_t vl_launch_sched(int cls, int mode, int split, const VlProblem* probs, const int* rlist, int n_r, int n_updates,
-                            const int* chunk_base, VlCtl* ctl, int* n_live, int* done_count, int4* pstat, int n_workers,
-                            int deep, cudaStream_t stream) {
-  if (n_r <= 0 || n_updates <= 0 || n_workers <= 0) return cudaSuccess;
-  VL_DISPATCH(launch_sched, probs, rlist, n_r, n_updates, chunk_base, ctl, n_live, done_count, pstat, n_workers, deep, stream)
+                            const int* chunk_base, VlCtl* ctl, int* n_live, int* done_count, int4* pstat, long long n_blocks,
+                            int deep, int persistent, cudaStream_t stream) {
+  if (n_r <= 0 || n_updates <= 0 || n_blocks <= 0) return cudaSuccess;
+  VL_DISPATCH(launch_sched, probs, rlist, n_r, n_updates, chunk_base, ctl, n_live, done_count, pstat, n_blocks, deep, persistent, stream)
 }
 
 cudaError_t vl_launch_init(const VlProblem* probs, int n_probs, int4* pstat, cudaStream_t stream) {
@@ -1210,6 +1388,11 @@ cudaError_t vl_launch_init_rows(const double* raw, const double* w, double* z, d
                                 cudaStream_t stream) {
   const size_t total = (size_t)Npad * KS;
   vl_init_rows_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(raw, w, z, wz, N, K, Npad, KS);
+  return cudaGetLastError();
+}
+
+cudaError_t vl_launch_dmma_peak(double* out, int n_blocks, int iters, cudaStream_t stream) {
+  vl_dmma_peak_kernel<<<n_blocks, 256, 0, stream>>>(out, iters, 1.0, 1e-3);
   return cudaGetLastError();
 }
 

@@ -140,9 +140,21 @@ def make_window(spec: WorkloadSpec, index: int, master_seed: int = 0, n_reads: i
     return win
 
 
-def make_workload(name: str, n_windows: int | None = None, master_seed: int = 0, indices=None, **kw) -> list:
-    """The first ``n_windows`` windows of a workload (default: all), or the windows ``indices``."""
+def _make_one(arg):
+    name, index, master_seed, kw = arg
+    return make_window(WORKLOADS[name], index, master_seed, **kw)
+
+
+def make_workload(name: str, n_windows: int | None = None, master_seed: int = 0, indices=None, procs: int = 1, **kw) -> list:
+    """The first ``n_windows`` windows of a workload (default: all), or the windows ``indices``.
+    ``procs`` > 1 generates them in a process pool (host-only work; call it before the process
+    touches CUDA -- the pool forks)."""
     spec = WORKLOADS[name]
     if indices is None:
         indices = range(spec.n_windows if n_windows is None else n_windows)
+    indices = list(indices)
+    if procs > 1 and len(indices) > 1:
+        import multiprocessing as mp
+        with mp.get_context("fork").Pool(min(procs, len(indices))) as pool:
+            return pool.map(_make_one, [(name, i, master_seed, kw) for i in indices], chunksize=1)
     return [make_window(spec, i, master_seed, **kw) for i in indices]

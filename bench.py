@@ -575,7 +575,7 @@ def run_b200_arm(args):
 
 # other BASELINE configs measured after the headline workload (N = 1 only): configs[1] whole, and a
 # bounded shard of configs[4] (2 of its 120 windows x 20 restarts: one window's workspace is 10 GB)
-EXTRA_WORKLOADS = (("hiv5k_uqs", {}), ("sars_ont", {"indices": [0, 1]}))
+EXTRA_WORKLOADS = (("hiv5k_uqs", {}), ("sars_ont", {"indices": [0, 1], "steps": 1}))
 
 
 def C_double():

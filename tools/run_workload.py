@@ -21,7 +21,7 @@ if os.environ.get("VL_N_READS"):
 if os.environ.get("VL_MAX_ITER"):
     kw["max_iter"] = int(os.environ["VL_MAX_ITER"])
 idx = [int(x) for x in os.environ["VL_WINDOWS"].split(",")] if os.environ.get("VL_WINDOWS") else None   # e.g. VL_WINDOWS=80,83
-wins = [w.pin() for w in synthetic.make_workload(name, nw, indices=idx, **kw)]
+wins = [w.pin() for w in synthetic.make_workload(name, nw, indices=idx, procs=min(32, os.cpu_count() or 1), **kw)]
 print(f"{name}: {len(wins)} windows, N_unique {[w.n_reads for w in wins[:4]]}, L {wins[0].length}, restarts {wins[0].n_starts}",
       flush=True)
 fused = os.environ.get("VL_FUSED", "1") != "0"

@@ -407,10 +407,17 @@ int run_chunk_fused(vl_batch* b, int n_iter, int64_t* launches) {
   for (int c = 0; c < VL_N_CLASSES; ++c)
     for (int m = 0; m < 4; ++m) {
       b->h_nlive[c * 4 + m] = b->n_rs[c][m];
-      // few tiles in flight: the SMs are mostly idle and a restart's update is a chain of latencies
-      if (b->n_rs[c][m] > 0) todo.push_back(Launch{c, m, b->want_workers[c][m] <= b->deep2_max ? 2 : (b->want_workers[c][m] <= 2 * b->n_sms ? 1 : 0), 0, 0, 0.0});
+      if (b->n_rs[c][m] > 0) todo.push_back(Launch{c, m, 0, 0, 0, 0.0});
     }
   if (todo.empty()) return 0;
+  // Few tiles in flight: the SMs are mostly idle and a restart's update is a chain of latencies, so a
+  // CTA gets more shared memory (larger pipeline stages): a whole SM's when all launches together have
+  // at most one tile per SM in flight, half an SM's when the launch has at most two per SM.
+  {
+    long long want_all = 0;
+    for (const Launch& l : todo) want_all += b->want_workers[l.c][l.m];
+    for (Launch& l : todo) l.deep = want_all <= b->deep2_max ? 2 : (b->want_workers[l.c][l.m] <= 2 * b->n_sms ? 1 : 0);
+  }
   VL_CUDA(cudaMemcpyAsync(b->dev<int>(L.nlive), b->h_nlive, VL_N_CLASSES * 4 * sizeof(int), cudaMemcpyHostToDevice, b->stream));
   const bool fork = todo.size() > 1;
   const int persistent = b->persistent >= 0 ? b->persistent : (fork ? 1 : 0);

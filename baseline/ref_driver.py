@@ -113,6 +113,18 @@ def _port_loop(win, n_iter: int, restart: int):
     return time.perf_counter() - t0, traj.n_updates, float(traj.history_elbo[-1])
 
 
+def first_reads(win, n: int):
+    """The window restricted to its first ``n`` unique reads (a bounded sample of a window whose single
+    iteration would take minutes on one core; the cost of an iteration is linear in the reads)."""
+    import dataclasses
+    if n >= win.n_reads:
+        return win
+    kw = {"codes": win.codes[:n], "weights": win.weights[:n], "init_cluster": win.init_cluster[:, :n]}
+    if win.mode == "uqs":
+        kw.update({"log_hit": win.log_hit[:n], "log_off": win.log_off[:n]})
+    return dataclasses.replace(win, **kw)
+
+
 def time_iterations(win, n_iter: int, restart: int = 0):
     """(seconds, iterations done, last ELBO) of ``n_iter`` CAVI iterations on one window, one thread."""
     if install_ref.available():

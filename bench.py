@@ -62,6 +62,7 @@ def parse_args():
     ap.add_argument("--no-extra", action="store_true", help="skip the hiv5k_uqs / sars_ont lines reported under 'extra'")
     ap.add_argument("--windows", type=int, default=None, help="windows per synthetic genome (default: all)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--waves", type=float, default=0.0, help="run in HBM-bounded waves of at most this many GiB each (default: only when the shard does not fit the GPU)")
     ap.add_argument("--record-iterations", action="store_true", help="write profiles/bench_iterations.json")
     return ap.parse_args()
 
@@ -246,10 +247,15 @@ def cpu_baseline_single_core(spec, windows, n_updates_per_window, n_genome_windo
     spent, work, sample = 0.0, 0.0, []
     n_iter = 6 if windows[0].n_reads * windows[0].length > 400000 else 24
     for i, win in enumerate(windows[:8]):
+        tag = ""
+        if win.n_reads * win.length > 20_000_000:          # one iteration of the full window would take minutes
+            n_iter = 2
+            win = ref_driver.first_reads(win, 20_000_000 // win.length)
+            tag = f"(first {win.n_reads} reads)"
         dt, n, _ = ref_driver.time_iterations(win, n_iter)
         spent += dt
-        work += n * win.n_reads * win.length * win.n_starts ** 0
-        sample.append(f"w{i}:{n}it")
+        work += n * win.n_reads * win.length
+        sample.append(f"w{i}{tag}:{n}it")
         if spent > budget_s:
             break
     sec_per_unit = spent / work
@@ -272,7 +278,10 @@ def _reference_worker(name, index, n_iter, n_rounds, barrier, queue):
         pass
     from baseline import ref_driver
     from viloca_b200 import synthetic
-    win = synthetic.make_window(synthetic.WORKLOADS[name], index)
+    import dataclasses
+    win = synthetic.make_window(dataclasses.replace(synthetic.WORKLOADS[name], n_starts=1), index)   # (restart 0 is what is timed)
+    if win.n_reads * win.length > 20_000_000:              # one iteration of the full window would take minutes: bounded sample
+        win = ref_driver.first_reads(win, 20_000_000 // win.length)
     for r in range(n_rounds):
         barrier.wait()
         dt, n, elbo = ref_driver.time_iterations(win, n_iter)
@@ -290,7 +299,7 @@ def run_reference_arm(args):
     n_windows = args.windows or spec.n_windows
     procs = max((os.cpu_count() or 2) - 1, 1)          # shotgun.py:527
     heavy = spec.coverage * spec.window_length > 2_000_000
-    n_iter = 4 if heavy else 10
+    n_iter = 2 if spec.coverage * spec.window_length > 20_000_000 else (4 if heavy else 10)
     rounds = args.warmup + args.steps
     ctx = mp.get_context("fork")
     barrier, queue = ctx.Barrier(procs + 1), ctx.Queue()
@@ -367,6 +376,31 @@ def timed_steps(batch, windows, steps, warmup, barrier, device):
     return run_ms, ev0.elapsed_time(ev1), launches, launches_run, outcomes, sampler.stop()
 
 
+def timed_steps_waves(windows, steps, warmup, barrier, device, budget=None):
+    """The same for a shard that does not fit the GPU at once: HBM-bounded waves, the next wave
+    uploaded on its own stream while this one runs (engine.run_in_waves).  run_ms is the sum of the
+    waves' loop times (CUDA events on each wave's stream); e2e is the wall clock between device-wide
+    synchronisations (several streams are in flight, one event pair cannot bracket them)."""
+    from viloca_b200 import engine
+    outcomes, st = None, {}
+    for _ in range(warmup):
+        outcomes = engine.run_in_waves(windows, device=device, budget_bytes=budget, stats=st)
+    sampler = ClockSampler(device)
+    sampler.start()
+    barrier()
+    run_ms, launches, launches_run = 0.0, 0, 0
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        st = {}
+        outcomes = engine.run_in_waves(windows, device=device, budget_bytes=budget, stats=st)
+        run_ms += st["device_ms"]
+        launches_run += st["launches"]
+        launches += st["launches"] + 4 * len(windows) + st["waves"]
+    barrier()
+    e2e_ms = 1e3 * (time.perf_counter() - t0)
+    return run_ms, e2e_ms, launches, launches_run, outcomes, sampler.stop(), st
+
+
 def d2h_bytes(outcomes, windows):
     n = 0
     for o, w in zip(outcomes, windows):
@@ -391,8 +425,9 @@ def extra_line(name, device, indices=None, steps=2, warmup=1, gen_procs=1, **kw)
         ex = sum(2.0 * o["Npad"] * o["NCs"] for o, w in zip(ops, windows) for _ in range(w.n_starts))
         out = {"workload": name, "windows": len(windows), "of_windows": spec.n_windows, "n_starts": spec.n_starts,
                "n_unique_mean": float(np.mean([w.n_reads for w in windows])), "length_mean": float(np.mean([w.length for w in windows])),
-               "value": n_problems * steps / (run_ms * 1e-3), "unit": "windows x restarts / s", "ms_per_step": run_ms / steps,
-               "e2e": {"value": n_problems * steps / (e2e_ms * 1e-3), "ms_per_step": e2e_ms / steps,
+               "value": len(windows) * steps / (run_ms * 1e-3), "unit": UNIT, "ms_per_step": run_ms / steps,
+               "window_restarts_per_sec": n_problems * steps / (run_ms * 1e-3),
+               "e2e": {"value": len(windows) * steps / (e2e_ms * 1e-3), "ms_per_step": e2e_ms / steps,
                        "h2d_bytes_per_step": batch.input_bytes(), "d2h_bytes_per_step": d2h_bytes(outcomes, windows)},
                "steps": steps, "warmup": warmup, "loop_launches_per_step": launches_run / steps,
                "iterations": {"mean": float(np.mean(updates)), "max": int(max(updates)), "min": int(min(updates))},
@@ -431,21 +466,44 @@ def run_b200_arm(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    batch = engine.CaviBatch(windows, device=device)
-    h2d = batch.input_bytes()
-    run_ms, e2e_ms, launches, launches_run, outcomes, clocks = timed_steps(batch, windows, args.steps, args.warmup, barrier, device)
-    d2h = d2h_bytes(outcomes, windows)
-
-    # per-kernel roofline numbers: a separate pass with every launch bracketed by CUDA events
+    # does the rank's shard fit the GPU at once?  Otherwise it runs in HBM-bounded waves
+    sizes = [engine.window_workspace_bytes(w) for w in windows]
+    free_hbm, _ = torch.cuda.mem_get_info(torch.device("cuda", device))
+    wave_info = None
     ops = operand_stats(windows)
-    ops_per_problem = [o for o, w in zip(ops, windows) for _ in range(w.n_starts)]     # problem = (window, restart)
-    prof_tot, prof_first = profiled_run(batch, ops_per_problem)
+    if sum(sizes) + (1 << 30) <= free_hbm and not args.waves:
+        batch = engine.CaviBatch(windows, device=device)
+        workspace_bytes = batch.workspace_bytes
+        h2d = batch.input_bytes()
+        run_ms, e2e_ms, launches, launches_run, outcomes, clocks = timed_steps(batch, windows, args.steps, args.warmup, barrier, device)
+        # per-kernel roofline numbers: a separate pass with every launch bracketed by CUDA events
+        ops_per_problem = [o for o, w in zip(ops, windows) for _ in range(w.n_starts)]     # problem = (window, restart)
+        prof_tot, prof_first = profiled_run(batch, ops_per_problem)
+        prof_scale = 1.0
+    else:
+        budget = int(args.waves * (1 << 30)) if args.waves else None
+        h2d = sum(w.input_bytes() for w in windows)
+        workspace_bytes = sum(sizes)
+        run_ms, e2e_ms, launches, launches_run, outcomes, clocks, wave_info = timed_steps_waves(
+            windows, args.steps, args.warmup, barrier, device, budget)
+        # roofline pass on the first wave only (its work scaled to the shard by the iteration counts)
+        first = engine.plan_waves(sizes, wave_info["budget_bytes"])[0]
+        batch = engine.CaviBatch([windows[i] for i in first], device=device)
+        ops_first = [ops[i] for i in first]
+        prof_tot, prof_first = profiled_run(batch, [o for o, i in zip(ops_first, first) for _ in range(windows[i].n_starts)])
+        work = lambda idx: float(sum(r.n_updates * windows[i].n_reads * windows[i].length for i in idx for r in outcomes[i].restarts))
+        prof_scale = work(range(len(windows))) / max(work(first), 1.0)
+        for k in prof_tot:
+            for key in ("bytes", "executed", "algorithmic", "dense_equivalent", "ms"):
+                prof_tot[k][key] *= prof_scale
+    d2h = d2h_bytes(outcomes, windows)
     n_updates_window = [sum(r.n_updates for r in o.restarts) for o in outcomes]
     all_updates = [r.n_updates for o in outcomes for r in o.restarts]
     read_iters = sum(r.n_updates * w.n_reads for o, w in zip(outcomes, windows) for r in o.restarts)
     raw_read_iters = sum(r.n_updates * getattr(w, "n_raw", w.n_reads) for o, w in zip(outcomes, windows) for r in o.restarts)
 
-    t = torch.tensor([run_ms, e2e_ms, float(n_problems), float(read_iters), float(raw_read_iters), float(launches),
+    # (a window counts once, whatever the number of its restarts: the reference's unit of work)
+    t = torch.tensor([run_ms, e2e_ms, float(len(windows)), float(read_iters), float(raw_read_iters), float(launches),
                       float(h2d), float(d2h)], dtype=torch.float64, device="cuda")
     if world > 1:
         tmax = t.clone(); dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
@@ -539,12 +597,13 @@ def run_b200_arm(args):
             "workload_stats": {"windows_rank0": len(windows), "n_unique_mean": float(np.mean([w.n_reads for w in windows])),
                                "dense_columns_mean": float(np.mean([o["NC"] for o in ops])),
                                "sparse_entries_mean": float(np.mean([o["nnz"] for o in ops])),
-                               "workspace_mb_rank0": batch.workspace_bytes / 1e6, "host_generation_s": t_gen,
+                               "workspace_mb_rank0": workspace_bytes / 1e6, "waves": wave_info, "host_generation_s": t_gen,
                                "rank_ms_per_step": {"max": run_ms_max / args.steps, "min": float(tmin[0]) / args.steps}},
             "e2e": {"value": total_problems * args.steps / (e2e_ms_max * 1e-3), "unit": UNIT,
                     "h2d_bytes_per_step": int(float(tsum[6])), "d2h_bytes_per_step": int(float(tsum[7])),
                     "ms_per_step": e2e_ms_max / args.steps},
             "gpu_launches": int(float(tsum[5])),
+            "window_restarts_per_sec": total_problems * spec.n_starts * args.steps / (run_ms_max * 1e-3),
             "read_iterations_per_sec": float(tsum[3]) * args.steps / (run_ms_max * 1e-3),
             "raw_read_iterations_per_sec": float(tsum[4]) * args.steps / (run_ms_max * 1e-3),
             "iterations": {"mean": float(np.mean(all_updates)), "max": int(max(all_updates)), "min": int(min(all_updates))},

@@ -698,3 +698,28 @@ def test_batched_hook_on_two_devices(golden_dir, tmp_path, monkeypatch):
         for suffix in (".reads-support.fas", ".reads-cor.fas"):
             assert _text(os.path.join(d1, stem + suffix)) == _text(os.path.join(d2, stem + suffix))
         assert r1["n_iterations"] == r2["n_iterations"] and r1["elbo"] == r2["elbo"]
+
+
+def test_waves_equal_one_batch():
+    """HBM-bounded waves (next wave uploaded on its own stream while this one runs) give bit for bit what
+    one batch of all windows gives; a window larger than the budget is a wave of its own."""
+    from viloca_b200 import synthetic
+    engine = _engine()
+    wins = [synthetic.make_window(_spec("uqs", 24, 60), i, n_reads=150 + 40 * i, length=80) for i in range(5)]
+    wins.append(synthetic.make_window(_spec("lep", 16, 50), 7, n_reads=200, length=64))
+    one = engine.run_windows(wins)
+    sizes = [engine.window_workspace_bytes(w) for w in wins]
+    stats = {}
+    seen = []
+    waves = engine.run_in_waves(wins, budget_bytes=int(1.5 * max(sizes)), stats=stats,
+                                consume=lambda batch, idx, outs: seen.append((list(idx), len(batch.windows))))
+    assert stats["waves"] >= 3 and [i for idx, _ in seen for i in idx] == list(range(len(wins)))
+    assert all(n == len(idx) for idx, n in seen)
+    for a, b in zip(one, waves):
+        assert a.best_restart == b.best_restart
+        assert [r.n_updates for r in a.restarts] == [r.n_updates for r in b.restarts]
+        assert np.array_equal(a.restarts[0].history_elbo, b.restarts[0].history_elbo)
+        assert np.array_equal(a.state["mean_cluster"], b.state["mean_cluster"])
+        assert np.array_equal(a.state["mean_haplo"], b.state["mean_haplo"])
+    tiny = engine.run_in_waves(wins[:2], budget_bytes=1)          # every window exceeds the budget: one wave each
+    assert np.array_equal(tiny[1].state["mean_cluster"], one[1].state["mean_cluster"])

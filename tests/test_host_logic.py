@@ -330,3 +330,19 @@ def test_corrected_reads_writer_equals_generic_fasta_writer(tmp_path):
     fasta.write(records, str(tmp_path / "a.fas"))
     _common.correct_reads(state, str(tmp_path / "b.fas"))
     assert (tmp_path / "a.fas").read_text() == (tmp_path / "b.fas").read_text()
+
+
+def test_plan_waves_keeps_order_and_respects_budget():
+    import ast
+    # plan_waves is pure host logic; engine.py itself imports the CUDA binding, so take the function's source
+    src = open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "viloca_b200", "engine.py")).read()
+    fn = next(n for n in ast.parse(src).body if isinstance(n, ast.FunctionDef) and n.name == "plan_waves")
+    ns = {}
+    exec("from typing import Sequence\n" + ast.get_source_segment(src, fn), ns)
+    plan = ns["plan_waves"]
+    assert plan([5, 5, 5, 20, 1, 1], 10) == [[0, 1], [2], [3], [4, 5]]
+    assert plan([], 10) == [] and plan([3], 1) == [[0]]
+    sizes = [7, 3, 9, 2, 2, 8, 1]
+    waves = plan(sizes, 12)
+    assert [i for w in waves for i in w] == list(range(len(sizes)))
+    assert all(sum(sizes[i] for i in w) <= 12 or len(w) == 1 for w in waves)

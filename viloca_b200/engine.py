@@ -254,3 +254,92 @@ def run_windows(windows: Sequence[Window], device: int = 0, **options) -> list:
         batch.upload()
         batch.run()
         return batch.fetch()
+
+
+# ------------------------------------------------------------------------------------------
+# Waves: batches bounded by the HBM that is free, the next one uploaded while this one runs
+# ------------------------------------------------------------------------------------------
+
+def window_workspace_bytes(window: Window) -> int:
+    """Device workspace one window needs (all its restarts), from the library's own layout."""
+    desc = (capi.WindowDesc * 1)(window.desc())
+    nbytes = C.c_size_t(0)
+    capi.check(capi.lib.vl_batch_workspace_bytes(desc, 1, C.byref(nbytes)))
+    return int(nbytes.value)
+
+
+def plan_waves(sizes: Sequence[int], budget: int) -> list:
+    """Consecutive groups of windows (the caller's order is kept) whose workspaces fit ``budget``
+    bytes together; a window larger than the budget is a wave of its own.  The reference never
+    holds more than ``max_proc`` windows at a time (shotgun.py:527-538); here the bound is HBM."""
+    waves, cur, used = [], [], 0
+    for i, s in enumerate(sizes):
+        if cur and used + s > budget:
+            waves.append(cur)
+            cur, used = [], 0
+        cur.append(i)
+        used += int(s)
+    if cur:
+        waves.append(cur)
+    return waves
+
+
+def run_in_waves(windows: Sequence[Window], device: int = 0, budget_bytes: Optional[int] = None, consume=None,
+                 fetch_options: Optional[dict] = None, stats: Optional[dict] = None, **options) -> list:
+    """upload + run + fetch of ``windows`` in HBM-bounded waves on one GPU.  While wave i runs its
+    loops, wave i + 1 is created and uploaded by a helper thread on its own stream (host planning,
+    H2D copies and the operand kernels overlap the run), so two waves are resident at a time and each
+    may take up to ``budget_bytes`` (default: 45 % of the HBM that is free now).  ``consume(batch,
+    indices, outcomes)`` is called while a wave's batch is still alive (the finishing contraction
+    needs it); the outcomes are returned in the order of ``windows``."""
+    from concurrent.futures import ThreadPoolExecutor
+    windows = list(windows)
+    if not windows:
+        return []
+    if not torch.cuda.is_available():
+        raise capi.EngineError("no CUDA device: the CAVI engine has no CPU fallback")
+    dev = torch.device("cuda", int(device))
+    if budget_bytes is None:
+        free, _total = torch.cuda.mem_get_info(dev)
+        budget_bytes = int(0.45 * free)
+    sizes = [window_workspace_bytes(w) for w in windows]
+    waves = plan_waves(sizes, budget_bytes)
+    if stats is not None:
+        stats.update({"waves": len(waves), "budget_bytes": int(budget_bytes), "workspace_bytes": int(sum(sizes)),
+                      "largest_wave_bytes": max(sum(sizes[i] for i in w) for w in waves),
+                      "device_ms": 0.0, "launches": 0, "upload_s": 0.0, "run_s": 0.0, "fetch_s": 0.0})
+
+    def prepare(idx):
+        import time as _t
+        t0 = _t.perf_counter()
+        with torch.cuda.device(dev):
+            stream = torch.cuda.Stream(device=dev)
+            batch = CaviBatch([windows[i] for i in idx], device=device, stream=stream.cuda_stream, **options)
+            batch._stream_keepalive = stream
+            batch.upload()
+            stream.synchronize()
+        return batch, _t.perf_counter() - t0
+
+    import time
+    results = [None] * len(windows)
+    with ThreadPoolExecutor(max_workers=1) as pool:
+        pending = pool.submit(prepare, waves[0])
+        for k, idx in enumerate(waves):
+            batch, up_s = pending.result()
+            pending = pool.submit(prepare, waves[k + 1]) if k + 1 < len(waves) else None
+            try:
+                t0 = time.perf_counter()
+                n = batch.run()
+                t1 = time.perf_counter()
+                outcomes = batch.fetch(**(fetch_options or {}))
+                t2 = time.perf_counter()
+                if stats is not None:
+                    stats["device_ms"] += batch.last_device_ms(); stats["launches"] += n
+                    stats["upload_s"] += up_s; stats["run_s"] += t1 - t0; stats["fetch_s"] += t2 - t1
+                if consume is not None:
+                    consume(batch, idx, outcomes)
+                for i, o in zip(idx, outcomes):
+                    results[i] = o
+            finally:
+                batch.close()
+    return results

@@ -365,6 +365,8 @@ def _record_history_run(job: WindowJob, batch, window_index: int):
     for r in range(job.n_starts):
         sc = w.init_scalars[r]
         hist[r]["history_alpha"].append(w.alpha0 * np.ones(w.n_clusters))
+        from scipy.special import digamma          # the initial entry of cavi.py:108: psi(alpha0) - psi(K alpha0)
+        hist[r]["history_mean_log_pi"].append(digamma(w.alpha0 * np.ones(w.n_clusters)) - digamma(w.n_clusters * w.alpha0))
         hist[r]["history_mean_log_gamma"].append((sc[2], sc[3]))
         hist[r]["history_mean_cluster"].append(w.init_cluster[r].copy())
     active = set(range(job.n_starts))
@@ -373,7 +375,7 @@ def _record_history_run(job: WindowJob, batch, window_index: int):
         batch.step(1)
         for r in sorted(active):
             sel = [r if i == window_index else "none" for i in range(len(batch.windows))]
-            out = batch.fetch(state=sel, want_haplo=False)[window_index]
+            out = batch.fetch(state=sel, want_haplo=False, want_history=False)[window_index]
             if it % 2 == 0:
                 hist[r]["history_mean_log_pi"].append(out.state["mean_log_pi"].copy())
                 hist[r]["history_mean_log_gamma"].append(out.state["mean_log_gamma"])
@@ -384,45 +386,57 @@ def _record_history_run(job: WindowJob, batch, window_index: int):
     return hist
 
 
-def run_jobs(jobs: Sequence[WindowJob], device: int = 0) -> list:
+def _finish_job(job: WindowJob, batch, i: int, out, histories=None):
+    """Best restart of one finished window -> state / result dicts, summary, the two output files."""
+    best = out.best_restart
+    logging.info("reference " + job.fref_in)
+    logging.info("reads " + job.freads_in)
+    logging.info("Maximal ELBO " + str(out.restarts[best].elbo) + "in run " + str(best))
+    logging.info("CAVI termination " + str(out.restarts[best].exit_message))
+    state, result = _result_dicts(job, out, best, out.state)
+    if job.record_history:
+        order = sorted(range(job.n_starts), key=lambda r: out.restarts[r].elbo, reverse=True)
+        per = []
+        for r in order:
+            o_r = batch.fetch(state=[r if x == i else "none" for x in range(len(batch.windows))])[i]
+            s_r, d_r = _result_dicts(job, o_r, r, o_r.state)
+            d_r.update((histories or {}).get(i, {}).get(r, {}))
+            per.append((s_r, d_r))
+        with open(job.output_name + "all_results.pkl", "wb") as fh:
+            pickle.dump(per, fh)
+        logging.info("Results dicts of all runs written to " + job.output_name + "all_results.pkl")
+    state.update(summarize(job, batch, i, best, state))
+    haplotypes_to_fasta(state, job.output_name + "support.fas")
+    correct_reads(state, job.output_name + "cor.fas")
+    return state, result
+
+
+def run_jobs(jobs: Sequence[WindowJob], device: int = 0, budget_bytes: Optional[int] = None) -> list:
     """Load, run and finish a list of windows on one GPU; writes ``<output_name>support.fas``
     and ``<output_name>cor.fas`` per window (run_dpm_mfa.py:119-120).  Returns the best
-    restart's state dict (with the summary merged in) per job."""
-    from ..engine import CaviBatch
+    restart's state dict (with the summary merged in) per job.  The windows go through the GPU in
+    waves bounded by the free HBM (``engine.run_in_waves``: the next wave is uploaded while this
+    one runs), the way the reference bounds its pool by ``max_proc`` (shotgun.py:527-538)."""
+    from ..engine import CaviBatch, run_in_waves
     for job in jobs:
         os.makedirs(job.output_dir, exist_ok=True)
     jobs = load_jobs(jobs)
-    finished = []
-    with CaviBatch([j.window for j in jobs], device=device) as batch:
-        batch.upload()
-        histories = {}
-        if any(j.record_history for j in jobs):
-            # slow path: single-step so that per-iteration states can be copied out
-            for i, job in enumerate(jobs):
-                if job.record_history:
-                    histories[i] = _record_history_run(job, batch, i)
-        batch.run()
-        outcomes = batch.fetch(state="best")
-        for i, (job, out) in enumerate(zip(jobs, outcomes)):
-            best = out.best_restart
-            logging.info("reference " + job.fref_in)
-            logging.info("reads " + job.freads_in)
-            logging.info("Maximal ELBO " + str(out.restarts[best].elbo) + "in run " + str(best))
-            logging.info("CAVI termination " + str(out.restarts[best].exit_message))
-            state, result = _result_dicts(job, out, best, out.state)
-            if job.record_history:
-                order = sorted(range(job.n_starts), key=lambda r: out.restarts[r].elbo, reverse=True)
-                per = []
-                for r in order:
-                    o_r = batch.fetch(state=[r if x == i else "none" for x in range(len(jobs))])[i]
-                    s_r, d_r = _result_dicts(job, o_r, r, o_r.state)
-                    d_r.update(histories.get(i, {}).get(r, {}))
-                    per.append((s_r, d_r))
-                with open(job.output_name + "all_results.pkl", "wb") as fh:
-                    pickle.dump(per, fh)
-                logging.info("Results dicts of all runs written to " + job.output_name + "all_results.pkl")
-            state.update(summarize(job, batch, i, best, state))
-            haplotypes_to_fasta(state, job.output_name + "support.fas")
-            correct_reads(state, job.output_name + "cor.fas")
-            finished.append((state, result))
+    finished = [None] * len(jobs)
+    plain = [i for i, j in enumerate(jobs) if not j.record_history]
+    if plain:
+        def consume(batch, idx, outcomes):
+            for local, (k, out) in enumerate(zip(idx, outcomes)):
+                finished[plain[k]] = _finish_job(jobs[plain[k]], batch, local, out)
+        run_in_waves([jobs[i].window for i in plain], device=device, budget_bytes=budget_bytes, consume=consume,
+                     fetch_options={"state": "best"})
+    slow = [i for i, j in enumerate(jobs) if j.record_history]
+    if slow:
+        # record_history: single-step so that per-iteration states can be copied out
+        with CaviBatch([jobs[i].window for i in slow], device=device) as batch:
+            batch.upload()
+            histories = {local: _record_history_run(jobs[i], batch, local) for local, i in enumerate(slow)}
+            batch.run()
+            outcomes = batch.fetch(state="best")
+            for local, (i, out) in enumerate(zip(slow, outcomes)):
+                finished[i] = _finish_job(jobs[i], batch, local, out, histories)
     return finished

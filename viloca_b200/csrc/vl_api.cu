@@ -42,7 +42,7 @@ struct RestartLayout {
 
 struct WindowLayout {
   int mode, N, L, K, R, max_iter;
-  int Npad, Ls, KT, KS, K8, n_ztiles, n_htiles, n_hsplit;
+  int Npad, Ls, KT, KS, K8, n_ztiles, n_htiles, n_hsplit, zt_reads;
   double alpha0, conv_thres;
   size_t nnz_cap;
   int NCs;
@@ -190,13 +190,17 @@ int build_layout(const vl_window_desc* w, int n, Layout& lay, std::string& err) 
     W.Npad = round_up(W.N, VL_ZT_READS);
     W.Ls = round_up(W.L, VL_PT);
     W.KT = (W.K + 7) / 8; W.KS = vl_ks(W.KT); W.K8 = 8 * W.KT;
-    W.n_ztiles = W.Npad / VL_ZT_READS;
+    W.n_ztiles = W.Npad / VL_ZT_READS;          // (re-derived below once the split of the haplotype tiles is known)
     plan_columns(d, W.Ls, plan);
     W.NCs = plan.NCs;
     W.n_htiles = W.NCs / VL_PT;
     // Large windows: the reads of a haplotype tile are shared by several CTAs (a property of the
     // window alone, so the sums a restart computes never depend on the rest of the batch)
     W.n_hsplit = std::max(1, std::min(VL_MAX_HSPLIT, W.Npad / VL_HSPLIT_READS));
+    // Mid-sized windows (amplicon: 2 500 reads -> 39 tiles of 64 reads on 148 SMs): read tiles of 32 reads, so
+    // that a lone restart's responsibility update spreads over twice the SMs.  A function of the window alone.
+    W.zt_reads = (W.n_hsplit > 1 && W.Npad <= VL_FINE_ZT_MAX_READS) ? 32 : VL_ZT_READS;
+    W.n_ztiles = W.Npad / W.zt_reads;
     W.nnz_cap = std::max<size_t>(plan.nnz, 1);
     W.dm = take((size_t)W.Npad * W.NCs * 8);
     W.w = take((size_t)W.Npad * 8);
@@ -307,6 +311,7 @@ struct vl_batch {
   // v = mode (bit 0: lep) + 2 * (window with split haplotype tiles)
   int n_ht[VL_N_CLASSES][4] = {}, n_zt[VL_N_CLASSES][4] = {}, n_rs[VL_N_CLASSES][4] = {};
   size_t off_ht[VL_N_CLASSES][4] = {}, off_zt[VL_N_CLASSES][4] = {}, off_rs[VL_N_CLASSES][4] = {};
+  int kt_max[VL_N_CLASSES][4] = {};         // widest layout among the restarts of a list (cluster tiles)
   int want_workers[VL_N_CLASSES][4] = {};   // tiles the restarts of a list can have in flight at once
   int n_sched = 0;
   bool sched_dirty = true;
@@ -316,7 +321,9 @@ struct vl_batch {
   int occ[VL_N_CLASSES][4][3] = {};    // resident CTAs per SM of the persistent chunk kernel (class, variant, deep), 0 = not asked yet
   int persistent = -1;                 // chunk launches: 1 = persistent workers, 0 = one block per tile, -1 = by the number of launches
   int n_sms = 148;
-  int deep2_max = 148;                 // most tiles in flight for which a launch gives every CTA a whole SM's shared memory
+  int sm_priority = 1;                 // SM shares of side-by-side launches: widest class first (see run_chunk_fused)
+  int merge_classes = 1;               // few tiles in flight: one launch of the widest class needed (see schedule)
+  int deep2_max = 296;                 // most tiles in flight for which a launch gives every CTA a whole SM's shared memory
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   double last_ms = 0.0;
   bool uploaded = false;
@@ -339,18 +346,39 @@ int schedule(vl_batch* b) {
   std::vector<int> rs[VL_N_CLASSES][4];
   b->n_sched = 0;
   for (int c = 0; c < VL_N_CLASSES; ++c)
-    for (int m = 0; m < 4; ++m) b->want_workers[c][m] = 0;
+    for (int m = 0; m < 4; ++m) { b->want_workers[c][m] = 0; b->kt_max[c][m] = 0; }
+  // Few tiles in flight (the tail of a run): the restarts of a variant all go to the widest class any of
+  // them needs, so that the chunk is ONE launch of one-tile blocks instead of persistent workers of several
+  // classes side by side (a lone wide window next to a lone narrow one ran 20 % slower that way).  The
+  // arithmetic of a restart is the same in every class that holds its layout.
+  int top_class[4] = {-1, -1, -1, -1};
+  if (b->merge_classes) {
+    long long want_all = 0;
+    int tc[4] = {-1, -1, -1, -1};
+    for (int p : b->order) {
+      const int4 st = b->pstat[p];
+      if (st.x == 0) continue;
+      const VlProblem& P = b->probs[p];
+      const int v = (P.mode == VL_MODE_LEP ? 1 : 0) + (P.n_hsplit > 1 ? 2 : 0);
+      tc[v] = std::max(tc[v], vl_class_of_tiles(st.y));
+      want_all += std::max(P.n_htiles * P.n_hsplit, P.n_ztiles);
+    }
+    if (want_all <= 2 * b->n_sms)
+      for (int v = 0; v < 4; ++v) top_class[v] = tc[v];
+  }
   for (int p : b->order) {
     const int4 st = b->pstat[p];
     if (st.x == 0) continue;
     const VlProblem& P = b->probs[p];
-    const int cls = vl_class_of_tiles(st.y), m = P.mode == VL_MODE_LEP ? 1 : 0;
+    const int m = P.mode == VL_MODE_LEP ? 1 : 0;
     const int v = m + (P.n_hsplit > 1 ? 2 : 0);
+    const int cls = top_class[v] >= 0 ? top_class[v] : vl_class_of_tiles(st.y);
     for (int sp = 0; sp < P.n_hsplit; ++sp)
       for (int t = 0; t < P.n_htiles; ++t) ht[cls][v].push_back(make_int2(p, vl_htile_id(t, sp, P.n_hsplit)));
     for (int t = 0; t < P.n_ztiles; ++t) zt[cls][v].push_back(make_int2(p, t));
     rs[cls][v].push_back(p);
     b->want_workers[cls][v] += std::max(P.n_htiles * P.n_hsplit, P.n_ztiles);
+    b->kt_max[cls][v] = std::max(b->kt_max[cls][v], st.y);
     ++b->n_sched;
   }
   size_t ho = 0, zo = 0, ro = 0;
@@ -435,8 +463,31 @@ int run_chunk_fused(vl_batch* b, int n_iter, int64_t* launches) {
       l.sms = (double)l.workers / occ;
       sm_demand += l.sms;
     }
-  const double scale = sm_demand > b->n_sms ? b->n_sms / sm_demand : 1.0;
+  // More demand than SMs: a chunk ends when its slowest launch has done its updates, and a launch needs
+  // (tiles in flight / workers) rounds of its restarts' update time per update -- about 32 + 8 kt us for
+  // a layout of kt cluster tiles (measured on lone restarts).  Equal finishing times: SM shares in
+  // proportion to demand x update time (demand alone halves the workers of the wide restarts a run ends
+  // up waiting for); what a launch cannot use goes to the others.
+  double scale = sm_demand > b->n_sms ? b->n_sms / sm_demand : 1.0;
+  if (persistent && sm_demand > b->n_sms && b->sm_priority) {
+    double wsum = 0.0;
+    std::vector<double> w(todo.size());
+    for (size_t k = 0; k < todo.size(); ++k) { w[k] = todo[k].sms * (32.0 + 8.0 * b->kt_max[todo[k].c][todo[k].m]); wsum += w[k]; }
+    double left = b->n_sms, wleft = wsum;
+    std::vector<char> fixed(todo.size(), 0);
+    for (int pass = 0; pass < 2; ++pass)                 // launches whose share exceeds their demand keep the demand
+      for (size_t k = 0; k < todo.size(); ++k)
+        if (!fixed[k] && left * w[k] / wleft >= todo[k].sms) { fixed[k] = 1; left -= todo[k].sms; wleft -= w[k]; }
+    for (size_t k = 0; k < todo.size(); ++k) {
+      Launch& l = todo[k];
+      const double grant = fixed[k] ? l.sms : std::max(1.0, left * w[k] / wleft);
+      l.workers = std::max(1, std::min(l.workers, (int)(grant * l.occ + 0.5)));
+      l.sms = grant;
+    }
+    scale = 1.0;
+  }
   if (fork) VL_CUDA(cudaEventRecord(b->ev_fork, b->stream));
+  if (b->sm_priority) std::reverse(todo.begin(), todo.end());      // widest class first: its blocks are placed before the small ones fill the SMs
   for (const Launch& l : todo) {
     const int i = l.c * 4 + l.m;
     cudaStream_t s = fork ? b->class_stream[i] : b->stream;
@@ -547,6 +598,8 @@ int vl_batch_create(vl_batch** out, int32_t device, const vl_window_desc* window
   b->ws_bytes = dev_bytes;
   if (const char* env = std::getenv("VL_PERSISTENT")) b->persistent = std::atoi(env);      // development aid
   if (const char* env = std::getenv("VL_DEEP2_MAX")) b->deep2_max = std::atoi(env);        // development aid
+  if (const char* env = std::getenv("VL_MERGE_CLASSES")) b->merge_classes = std::atoi(env); // development aid
+  if (const char* env = std::getenv("VL_SM_PRIORITY")) b->sm_priority = std::atoi(env);     // development aid
   cudaError_t e = cudaSetDevice(device);
   if (e != cudaSuccess) { delete b; return fail(std::string("cudaSetDevice: ") + cudaGetErrorString(e)); }
 
@@ -568,7 +621,7 @@ int vl_batch_create(vl_batch** out, int32_t device, const vl_window_desc* window
       P.mode = W.mode; P.N = W.N; P.L = W.L; P.K = W.K;
       P.Npad = W.Npad; P.Ls = W.Ls; P.KT = W.KT; P.NCs = W.NCs;
       P.n_ztiles = W.n_ztiles; P.n_htiles = W.n_htiles; P.window = (int)i; P.restart = r;
-      P.n_hsplit = W.n_hsplit; P.pad0_ = 0;
+      P.n_hsplit = W.n_hsplit; P.zt_reads = W.zt_reads;
       P.dm = b->dev<double>(W.dm);
       P.w = b->dev<double>(W.w);
       P.ltsum = b->dev<double>(W.ltsum);

@@ -42,6 +42,7 @@
 #define VL_MAX_KT 16     // 8-slot tiles of a layout (VL_MAX_CLUSTERS / 8)
 #define VL_HSPLIT_READS 512   // a haplotype tile's reads are shared by Npad / 512 CTAs ...
 #define VL_MAX_HSPLIT 8       // ... at most 8 (windows of fewer than 1024 padded reads: one CTA, as before)
+#define VL_FINE_ZT_MAX_READS 16384   // windows with split haplotype tiles and at most this many padded reads use read tiles of 32 reads
 #define VL_ZP_EXTRA 8    // scalars appended to each per-tile column-sum record: data, ent, c, d
 #define VL_HP_STRIDE 4
 
@@ -131,7 +132,7 @@ struct VlProblem {
   // large windows only (kept behind the fields every tile reads, whose cache lines stay as they were)
   double* tsplit;          // [n_htiles][n_hsplit][16 * 8*KT]  partial sums over reads of a split tile (n_hsplit > 1)
   int* hsplit_count;       // [n_htiles]  arrivals at a split tile in the current update
-  int n_hsplit, pad0_;     // CTAs that share the reads of one haplotype tile (1 unless the window is large)
+  int n_hsplit, zt_reads;  // CTAs that share the reads of one haplotype tile (1 unless the window is large); reads per read tile (64 or 32)
 };
 
 // ---------------------------------------------------------------------------------------

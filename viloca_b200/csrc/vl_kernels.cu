@@ -344,7 +344,7 @@ __device__ __forceinline__ bool vl_haplo_body(const VlProblem* __restrict__ prob
         double av[NB];
 #pragma unroll
         for (int j = 0; j < NB; ++j) av[j] = 0.0;
-#pragma unroll 4
+#pragma unroll 8
         for (int e = e0; e < e1; ++e) {
           const double wd = sp_d[e];
           const double* zr = wzg + (size_t)sp_n[e] * KSz;
@@ -458,12 +458,15 @@ vl_haplo_kernel(const VlProblem* __restrict__ probs, const int2* __restrict__ ti
 // vl_cluster_tile: one tile up to its per-tile record; returns false if the restart is not running in this
 // kernel class.  vl_cluster_close: what the tile that finishes last does for its restart.  sS receives the
 // restart's state as it was before the update.
-template <int KTM, int MODE>
-__device__ __forceinline__ bool vl_cluster_tile(const VlProblem* __restrict__ probs, const int2 tm,
-                                                const int stage_doubles, VlState& sS) {
+// MT = m-tiles of 8 reads per warp: 2 (CTA = 64 reads), or 1 (CTA = 32 reads) for the windows whose read
+// tiles would otherwise occupy a fraction of the SMs (VlProblem::zt_reads, a function of the window alone).
+template <int KTM, int MODE, int MT>
+__device__ __forceinline__ bool vl_cluster_tile_mt(const VlProblem* __restrict__ probs, const int2 tm,
+                                                   const int stage_doubles, VlState& sS) {
   constexpr int KSM = vl_ks(KTM), K8M = 8 * KTM;
-  constexpr int DM_STAGE = VL_ZT_READS * VL_PT;        // doubles
-  constexpr int ST_STRIDE = DM_STAGE + VL_PT * KSM;    // dm | gm
+  constexpr int ZT = 32 * MT;                           // reads of this tile
+  constexpr int DM_STAGE = ZT * VL_PT;                  // doubles
+  constexpr int ST_STRIDE = VL_ZT_READS * VL_PT + VL_PT * KSM;    // dm | gm as the shared memory is sized (64 reads)
   extern __shared__ __align__(128) unsigned char vl_smem[];
   double* stg = reinterpret_cast<double*>(vl_smem);
   double* red_cs = stg + max(stage_doubles, vl_zstages(KTM) * ST_STRIDE);   // [4][K8M], after the stages
@@ -485,7 +488,7 @@ __device__ __forceinline__ bool vl_cluster_tile(const VlProblem* __restrict__ pr
   const int Npad = P.Npad;
   const int KS = vl_ks(ktl), K8 = 8 * ktl;
   const int nst = P.NCs / VL_PT;
-  const int n0 = tm.y * VL_ZT_READS;
+  const int n0 = tm.y * ZT;
   const double* __restrict__ dmg = P.dm + (size_t)n0 * VL_PT;
   const double* gmg = P.gm;
   const uint32_t gm_bytes = (uint32_t)(VL_PT * KS * sizeof(double));          // per column tile
@@ -520,18 +523,18 @@ __device__ __forceinline__ bool vl_cluster_tile(const VlProblem* __restrict__ pr
   if (tid == 0)
     for (int c = 0; c < nstg - 1 && c < nstages; ++c) issue(c);
 
-  double acc[2][KTM][2];
+  double acc[MT][KTM][2];
 #pragma unroll
-  for (int mt = 0; mt < 2; ++mt)
+  for (int mt = 0; mt < MT; ++mt)
 #pragma unroll
     for (int i = 0; i < KTM; ++i) { acc[mt][i][0] = 0.0; acc[mt][i][1] = 0.0; }
 
-  const int r0 = warp * 16 + g;                    // rows r0 and r0 + 8 of the tile; r0 % 4 == g % 4
+  const int r0 = warp * (8 * MT) + g;              // rows r0 (and r0 + 8) of the tile; r0 % 4 == g % 4
   // per-read scalars: requested now, needed after the operand loop
-  double wn_r[2], mc_r[2], lt_r[2];
-  int se0[2], se1[2];
+  double wn_r[MT], mc_r[MT], lt_r[MT];
+  int se0[MT], se1[MT];
 #pragma unroll
-  for (int mt = 0; mt < 2; ++mt) {
+  for (int mt = 0; mt < MT; ++mt) {
     const int n = n0 + r0 + 8 * mt;
     wn_r[mt] = P.w[n];
     mc_r[mt] = P.mcount[n];
@@ -547,13 +550,13 @@ __device__ __forceinline__ bool vl_cluster_tile(const VlProblem* __restrict__ pr
       for (int s = 0; s < 4; ++s) {
         const int col = (4 * s + q + 4 * (g & 3)) & 15;
         const double a0 = dt[r0 * VL_PT + col];
-        const double a1 = dt[(r0 + 8) * VL_PT + col];
+        const double a1 = (MT > 1) ? dt[(r0 + 8) * VL_PT + col] : 0.0;
         const double* gr = gt + (4 * s + q) * KS;
 #pragma unroll
         for (int i = 0; i < KT; ++i) {
           const double bf = gr[8 * i];
           vl_dmma(acc[0][i], a0, bf);
-          vl_dmma(acc[1][i], a1, bf);
+          if (MT > 1) vl_dmma(acc[MT - 1][i], a1, bf);
         }
       }
     };
@@ -589,7 +592,7 @@ __device__ __forceinline__ bool vl_cluster_tile(const VlProblem* __restrict__ pr
     const double* __restrict__ sr_d = P.sr_d;
     const double* gtab = P.g;
 #pragma unroll
-    for (int mt = 0; mt < 2; ++mt) {
+    for (int mt = 0; mt < MT; ++mt) {
       for (int e = se0[mt]; e < se1[mt]; ++e) {
         const double d = sr_d[e];
         const double* gp = gtab + (size_t)sr_idx[e] * KS + 2 * q;
@@ -615,7 +618,7 @@ __device__ __forceinline__ bool vl_cluster_tile(const VlProblem* __restrict__ pr
   double s_data = 0.0, s_ent = 0.0, s_c = 0.0, s_d = 0.0;
   double cs[KTM][2];
 #pragma unroll
-  for (int mt = 0; mt < 2; ++mt) {
+  for (int mt = 0; mt < MT; ++mt) {
     const int n = n0 + r0 + 8 * mt;
     const bool valid = n < N;
     const double wn = wn_r[mt];
@@ -724,6 +727,16 @@ __device__ __forceinline__ bool vl_cluster_tile(const VlProblem* __restrict__ pr
 
   GK_TICK(12);
   return true;
+}
+
+// one read tile of the height the window is laid out for
+template <int KTM, int MODE, bool FINE_OK = true>
+__device__ __forceinline__ bool vl_cluster_tile(const VlProblem* __restrict__ probs, const int2 tm,
+                                                const int stage_doubles, VlState& sS) {
+  if constexpr (FINE_OK) {
+    if (probs[tm.x].zt_reads == 32) return vl_cluster_tile_mt<KTM, MODE, 1>(probs, tm, stage_doubles, sS);
+  }
+  return vl_cluster_tile_mt<KTM, MODE, 2>(probs, tm, stage_doubles, sS);
 }
 
 // The read tile of a restart that finishes last closes the update: fixed-order sums of the per-tile
@@ -892,7 +905,7 @@ vl_sched_kernel(const VlProblem* __restrict__ probs, const int* __restrict__ rli
   // ---- read tile of update k ----
   __shared__ VlState sZ;                     // the state before the update
   asm volatile("fence.proxy.async;\n" ::: "memory");     // its bulk copies read what other CTAs wrote
-  const bool ran = vl_cluster_tile<KTM, MODE>(probs, make_int2(s_task[0], s_task[2]), stage_doubles, sZ);
+  const bool ran = vl_cluster_tile<KTM, MODE, SPLIT>(probs, make_int2(s_task[0], s_task[2]), stage_doubles, sZ);
   __threadfence();
   __syncthreads();
   const int p = s_task[0];
@@ -937,10 +950,10 @@ __device__ __noinline__ void vl_haplo_task(const VlProblem* __restrict__ probs, 
                                            const int pub_want) {
   vl_haplo_body<KTM, MODE, SPLIT>(probs, tm, stage_doubles, true, pub_want);
 }
-template <int KTM, int MODE>
+template <int KTM, int MODE, bool SPLIT>
 __device__ __noinline__ bool vl_cluster_task(const VlProblem* __restrict__ probs, const int2 tm, const int stage_doubles,
                                              VlState* sS) {
-  return vl_cluster_tile<KTM, MODE>(probs, tm, stage_doubles, *sS);
+  return vl_cluster_tile<KTM, MODE, SPLIT>(probs, tm, stage_doubles, *sS);
 }
 template <int MODE>
 __device__ __noinline__ void vl_close_task(const VlProblem* P, const VlState* R, int* done_count, int4* pstat_entry) {
@@ -992,7 +1005,7 @@ vl_sched_persistent_kernel(const VlProblem* __restrict__ probs, const int* __res
       __syncthreads();                       // every thread has read the task before the next claim rewrites it
     } else {
       asm volatile("fence.proxy.async;\n" ::: "memory");
-      const bool ran = vl_cluster_task<KTM, MODE>(probs, make_int2(s_task[0], s_task[2]), stage_doubles, &sZ);
+      const bool ran = vl_cluster_task<KTM, MODE, SPLIT>(probs, make_int2(s_task[0], s_task[2]), stage_doubles, &sZ);
       __threadfence();
       __syncthreads();
       const int p = s_task[0];

@@ -723,3 +723,39 @@ def test_waves_equal_one_batch():
         assert np.array_equal(a.state["mean_haplo"], b.state["mean_haplo"])
     tiny = engine.run_in_waves(wins[:2], budget_bytes=1)          # every window exceeds the budget: one wave each
     assert np.array_equal(tiny[1].state["mean_cluster"], one[1].state["mean_cluster"])
+
+
+def test_in_memory_windows_through_the_batched_hook(golden_dir, tmp_path, monkeypatch):
+    """the fixture windows handed to run_dpm_batch as arrays (no w-*.reads.fas / .qualities.npy
+    round trip, results kept in memory) give the same states and the same SNV tables as the file-based path."""
+    from oracle import bam_windows
+    from viloca_b200 import shotgun_hook
+    meta = _json_file(os.path.join(golden_dir, "bam_windows", "expected.json"))
+    monkeypatch.chdir(tmp_path)
+    names = [n for n in BAM_WINDOWS if meta[n]["n_starts"] == 1 and meta[n]["K"] == meta[BAM_WINDOWS[0]]["K"]] or BAM_WINDOWS[:1]
+    K, seed = meta[names[0]]["K"], meta[names[0]]["seed"]
+    names = [n for n in names if meta[n]["seed"] == seed]
+    runlist, arrays = [], []
+    for name in names:
+        npz = os.path.join(golden_dir, "bam_windows", name, "window.npz")
+        stem, f_reads, _, _ = bam_windows.materialize(npz, str(tmp_path))
+        runlist.append((f_reads, 0, 0.0001, np.array([seed]), "use_quality_scores", K, 1, True, 1e-3, False))
+        z = np.load(npz)
+        start, ref_seq = int(z["start"]), str(z["ref_seq"])
+        arrays.append({"name": stem, "read_ids": [str(i) for i in z["ids"]], "read_seqs": [str(r) for r in z["rows"]],
+                       "qualities": z["quals"].astype(np.int64), "ref": (str(z["ref_name"]), ref_seq)})
+    jobs_f, fin_f = shotgun_hook.run_dpm_batch(runlist, devices=[0], collect=True)
+    before = set(os.listdir(tmp_path))
+    jobs_m = shotgun_hook.jobs_from_arrays(arrays, "use_quality_scores", K, 1, 0.0001, seed=seed)
+    jobs_m, fin_m = shotgun_hook.run_dpm_batch(jobs_m, devices=[0], collect=True)
+    assert set(os.listdir(tmp_path)) == before                        # nothing written
+    for (sf, rf), (sm, rm) in zip(fin_f, fin_m):
+        assert rf["n_iterations"] == rm["n_iterations"] and rf["elbo"] == rm["elbo"]
+        assert np.array_equal(sf["mean_cluster"], sm["mean_cluster"])
+        assert [sf[k] for k in sorted(sf) if k.startswith("haplotype")] == [sm[k] for k in sorted(sm) if k.startswith("haplotype")]
+    tf, tm = shotgun_hook.snv_tables(jobs_f, fin_f), shotgun_hook.snv_tables(jobs_m, fin_m)
+    assert [t["window"] for t in tf] == [t["window"] for t in tm]
+    for a, b in zip(tf, tm):
+        assert sorted((k.pos, k.var, v.freq, v.support) for k, v in a["snvs"].items()) == \
+               sorted((k.pos, k.var, v.freq, v.support) for k, v in b["snvs"].items())
+        assert a["cooccurring"] == b["cooccurring"]

@@ -346,3 +346,42 @@ def test_plan_waves_keeps_order_and_respects_budget():
     waves = plan(sizes, 12)
     assert [i for w in waves for i in w] == list(range(len(sizes)))
     assert all(sum(sizes[i] for i in w) <= 12 or len(w) == 1 for w in waves)
+
+
+def test_in_memory_window_preparation_equals_file_preparation(tmp_path):
+    """A window handed over as arrays (shotgun_hook.jobs_from_arrays) is prepared exactly like the same window
+    read back from the files b2w would have written (b2w.py:604-616, 670-672)."""
+    from viloca_b200 import shotgun_hook
+    rng = np.random.default_rng(5)
+    L, n_raw = 40, 60
+    base = "".join(rng.choice(list("ACGT"), size=L))
+    seqs = []
+    for i in range(n_raw):
+        s = list(base)
+        for p in rng.choice(L, size=rng.integers(0, 3), replace=False):
+            s[p] = rng.choice(list("ACGT-N"))
+        seqs.append("".join(s))
+    ids = [f"read{i} {100 + i}" for i in range(n_raw)]
+    quals = rng.integers(0, 42, size=(n_raw, L)).astype(np.int64)
+    name = "w-chr1-101-140"
+    stem = str(tmp_path / name)
+    with open(stem + ".reads.fas", "w") as fh:
+        for i, s in zip(ids, seqs):
+            fh.write(f">{i}\n{s}\n")
+    with open(stem + ".ref.fas", "w") as fh:
+        fh.write(f">chr1 101\n{base.lower()}\n")
+    np.save(stem + ".qualities.npy", quals, allow_pickle=True)
+    for inference, mode in (("use_quality_scores", "uqs"), ("learn_error_params", "lep")):
+        run = (stem + ".reads.fas", 0, 1e-4, np.array([27]), inference, 12, 2, True, 1e-3, False)
+        from_files = shotgun_hook.jobs_from_runlist([run])[0].load()
+        mem = shotgun_hook.jobs_from_arrays([{"name": name, "read_ids": ids, "read_seqs": seqs, "qualities": quals,
+                                              "ref": ("chr1", base.lower())}], inference, 12, 2, 1e-4, seed=27)[0].load()
+        a, b = from_files.window, mem.window
+        assert a.mode == b.mode == mode
+        for field in ("codes", "weights", "ref_codes", "init_cluster", "init_scalars", "log_hit", "log_off"):
+            x, y = getattr(a, field), getattr(b, field)
+            assert (x is None and y is None) or np.array_equal(x, y), field
+        assert from_files.prepared.read_ids == mem.prepared.read_ids
+        assert from_files.ref_seq == mem.ref_seq
+        assert shotgun_hook.window_coordinates(mem) == ("chr1", "101", "140")
+        assert mem.write_files is False

@@ -15,9 +15,11 @@ class Record:
     seq: str
 
 
-def parse(path: str) -> Iterator[Record]:
+def parse(path) -> Iterator[Record]:
+    """Records of a FASTA file (``path``: a file name, or an open text stream)."""
+    import contextlib
     title, chunks = None, []
-    with open(path) as fh:
+    with (open(path) if isinstance(path, (str, bytes)) or hasattr(path, "__fspath__") else contextlib.nullcontext(path)) as fh:
         for line in fh:
             line = line.rstrip("\r\n")
             if line.startswith(">"):

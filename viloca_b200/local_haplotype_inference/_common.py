@@ -101,10 +101,22 @@ def prepare_reads_file(path: str, qualities: Optional[np.ndarray], alphabet: str
     PreparedWindow as ``prepare_reads(*read_window_fasta(path), ...)`` bit for bit, without the per-record
     Python loops.  Files the native reader does not take (multi-line sequences, qualities that are not
     a dense (n_raw, length) int64 / float64 array, non-ASCII alphabets) go through the generic path."""
-    import ctypes as C
-    from .. import _capi as capi
     with open(path, "rb") as fh:
         text = fh.read()
+    return prepare_reads_text(text, qualities, alphabet, unique_modus, path)
+
+
+def fasta_text(ids: Sequence[str], seqs: Sequence[str]) -> bytes:
+    """The window's reads as b2w writes them (b2w.py:613-616: one ``>id`` line and one sequence line per
+    read), in memory."""
+    return "".join(f">{i}\n{s}\n" for i, s in zip(ids, seqs)).encode("ascii")
+
+
+def prepare_reads_text(text: bytes, qualities: Optional[np.ndarray], alphabet: str, unique_modus: bool,
+                       path: Optional[str] = None) -> PreparedWindow:
+    """prepare_reads_file on the FASTA text itself (a file's bytes, or a window handed over in memory)."""
+    import ctypes as C
+    from .. import _capi as capi
     q_kind, q = 0, None
     if qualities is not None:
         q = np.asarray(qualities)
@@ -125,6 +137,10 @@ def prepare_reads_file(path: str, qualities: Optional[np.ndarray], alphabet: str
         capi.lib.vl_reads_free(handle)
         ok = False
     if not ok:
+        if path is None:
+            import io
+            recs = list(fasta.parse(io.StringIO(text.decode("ascii", "replace"))))
+            return prepare_reads([r.id for r in recs], [r.seq for r in recs], qualities, alphabet, unique_modus)
         return prepare_reads(*read_window_fasta(path), qualities, alphabet, unique_modus)
     try:
         nr, nu, ln = n_raw.value, n_rows.value, length.value
@@ -181,6 +197,12 @@ class WindowJob:
     record_history: bool = False
     seed: int = 27
     max_iter: int = 50000
+    # in-memory hand-over from the window builder (instead of the three files of b2w.py:613-616, 670-672):
+    # reads as FASTA text or as (ids, sequences), the (n_raw, L) quality array, the reference window
+    reads_text: Optional[bytes] = None
+    qualities: Optional[np.ndarray] = None
+    ref_record: Optional[tuple] = None          # (id, sequence)
+    write_files: bool = True                    # False: results stay in memory (shotgun_hook.snv_tables)
     # filled by load()
     prepared: Optional[PreparedWindow] = None
     ref_codes: Optional[np.ndarray] = None
@@ -197,11 +219,18 @@ class WindowJob:
         if self.alphabet != ALPHABET:
             raise ValueError("the engine is built for the alphabet 'ACGT-' (B = 5)")
         quals = None
-        if self.mode == "uqs":
-            with open(self.fname_qualities, "rb") as fh:
-                quals = np.load(fh, allow_pickle=True)
-        self.prepared = prepare_reads_file(self.freads_in, quals, self.alphabet, self.unique_modus)
-        self.ref_codes, _, self.ref_seq = load_reference(self.fref_in, self.alphabet, upper=(self.mode == "uqs"))
+        if self.reads_text is not None:
+            quals = self.qualities if self.mode == "uqs" else None
+            self.prepared = prepare_reads_text(self.reads_text, quals, self.alphabet, self.unique_modus)
+            _rid, rseq = self.ref_record
+            seq = rseq.upper() if self.mode == "uqs" else rseq          # as load_reference
+            self.ref_codes, self.ref_seq = tensors.encode(seq, self.alphabet), rseq
+        else:
+            if self.mode == "uqs":
+                with open(self.fname_qualities, "rb") as fh:
+                    quals = np.load(fh, allow_pickle=True)
+            self.prepared = prepare_reads_file(self.freads_in, quals, self.alphabet, self.unique_modus)
+            self.ref_codes, _, self.ref_seq = load_reference(self.fref_in, self.alphabet, upper=(self.mode == "uqs"))
         p = self.prepared
         n = p.codes.shape[0]
         zs, scs = init_state.draw_restarts(self.mode, self.K, self.alpha0, n, self.n_starts, self.seed)
@@ -223,7 +252,7 @@ def _load_cost_seconds(job: WindowJob) -> float:
     """Rough host time of WindowJob.load: parsing / dedup ~ 12 ns per byte of the read file, the seeded
     Dirichlet draws ~ 120 ns per (read, cluster, restart)."""
     try:
-        size = os.path.getsize(job.freads_in)
+        size = len(job.reads_text) if job.reads_text is not None else os.path.getsize(job.freads_in)
     except OSError:
         return 0.0
     return 12e-9 * size + 1.2e-7 * (size / 200.0) * job.K * job.n_starts
@@ -406,8 +435,9 @@ def _finish_job(job: WindowJob, batch, i: int, out, histories=None):
             pickle.dump(per, fh)
         logging.info("Results dicts of all runs written to " + job.output_name + "all_results.pkl")
     state.update(summarize(job, batch, i, best, state))
-    haplotypes_to_fasta(state, job.output_name + "support.fas")
-    correct_reads(state, job.output_name + "cor.fas")
+    if job.write_files:
+        haplotypes_to_fasta(state, job.output_name + "support.fas")
+        correct_reads(state, job.output_name + "cor.fas")
     return state, result
 
 
@@ -419,7 +449,8 @@ def run_jobs(jobs: Sequence[WindowJob], device: int = 0, budget_bytes: Optional[
     one runs), the way the reference bounds its pool by ``max_proc`` (shotgun.py:527-538)."""
     from ..engine import CaviBatch, run_in_waves
     for job in jobs:
-        os.makedirs(job.output_dir, exist_ok=True)
+        if job.write_files:
+            os.makedirs(job.output_dir, exist_ok=True)
     jobs = load_jobs(jobs)
     finished = [None] * len(jobs)
     plain = [i for i, j in enumerate(jobs) if not j.record_history]

@@ -15,6 +15,8 @@ from __future__ import annotations
 
 import logging
 import threading
+
+import numpy as np
 from typing import Optional, Sequence
 
 from . import scheduler
@@ -63,10 +65,54 @@ def snv_tables(jobs, finished, threshold: float = 0.9) -> list:
     return out
 
 
+def jobs_from_arrays(windows, inference_type: str, n_max_haplotypes: int, n_mfa_starts: int, alpha0: float, seed: int = 27,
+                     unique_modus: bool = True, conv_thres: float = 1e-3, write_files: bool = False,
+                     output_dir: str = "./") -> list:
+    """In-memory hand-over from the window builder: what b2w.py:604-616, 670-672 writes per window and
+    shotgun.py:312-333 reads back, passed as arrays instead.  Each window is a dict (or object) with
+    ``name`` (``w-<chrom>-<beg>-<end>``, the stem of the files the reference would write), ``read_ids`` and
+    ``read_seqs`` (equal-length strings over ACGT-N, in b2w's order; or ``reads_text``, the FASTA text b2w would
+    have written, as bytes), ``qualities`` ((n_raw, L) integer
+    array; ignored for learn_error_params) and ``ref`` ((id, sequence) of the reference window).  The other
+    arguments are the fields of the reference's run-setting tuple (shotgun.py:326).  ``write_files=False``
+    keeps the results in memory (``run_dpm_batch(..., collect=True)`` + ``snv_tables``)."""
+    if inference_type not in MODES:
+        raise ValueError(f"inference_type {inference_type!r} is not served by the CUDA engine")
+    mode = MODES[inference_type]
+    jobs = []
+    for w in windows:
+        get = (lambda k: w[k]) if isinstance(w, dict) else (lambda k: getattr(w, k))
+        name = get("name")
+        q = None
+        if mode == "uqs":
+            q = np.ascontiguousarray(get("qualities"))
+            if q.dtype not in (np.float64, np.int64):
+                q = q.astype(np.int64)                                   # b2w saves int64 (b2w.py:508)
+        try:
+            text = get("reads_text")                                     # the FASTA text b2w would write, if the caller has it
+        except (KeyError, AttributeError):
+            text = None
+        if text is None:
+            text = _common.fasta_text(get("read_ids"), get("read_seqs"))
+        jobs.append(_common.WindowJob(
+            mode=mode, freads_in=name + ".reads.fas", fref_in=name + ".ref.fas",
+            fname_qualities=(name + ".qualities.npy") if mode == "uqs" else None,
+            output_dir=output_dir, n_starts=int(n_mfa_starts), K=int(n_max_haplotypes), alpha0=float(alpha0),
+            unique_modus=unique_modus, record_history=False, seed=int(seed),
+            convergence_threshold=conv_thres if mode == "uqs" else 1e-3,
+            reads_text=text, qualities=q,
+            ref_record=tuple(get("ref")), write_files=write_files))
+    return jobs
+
+
 def run_dpm_batch(runlist, devices: Optional[Sequence[int]] = None, collect: bool = False,
                   load_workers: Optional[int] = None):
+    """``runlist``: the reference's run-setting tuples (files on disk), or WindowJobs from
+    :func:`jobs_from_arrays` (windows in memory)."""
     import torch
-    jobs = _common.load_jobs(jobs_from_runlist(runlist), workers=load_workers)    # a process pool, like the reference's
+    runlist = list(runlist)
+    todo = runlist if runlist and isinstance(runlist[0], _common.WindowJob) else jobs_from_runlist(runlist)
+    jobs = _common.load_jobs(todo, workers=load_workers)    # a process pool, like the reference's
     if not jobs:
         return ([], []) if collect else None
     if devices is None:

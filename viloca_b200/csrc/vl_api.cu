@@ -264,7 +264,7 @@ int build_layout(const vl_window_desc* w, int n, Layout& lay, std::string& err) 
   lay.htiles = take(lay.n_htiles_total * sizeof(int2));
   lay.ztiles = take(lay.n_ztiles_total * sizeof(int2));
   lay.rlist = take((size_t)lay.n_problems * sizeof(int));
-  lay.cbase = take((size_t)lay.n_problems * sizeof(int));
+  lay.cbase = take((size_t)lay.n_problems * sizeof(int4));
   lay.ctl = take((size_t)lay.n_problems * sizeof(VlCtl));
   lay.nlive = take(VL_N_CLASSES * 4 * sizeof(int));
   lay.raw_codes = take(max_nl);
@@ -304,7 +304,7 @@ struct vl_batch {
   // pinned staging of the per-chunk schedule
   int2* h_htiles = nullptr; int2* h_ztiles = nullptr; int4* h_pstat = nullptr;
   int* h_rlist = nullptr;
-  int* h_cbase = nullptr;
+  int4* h_cbase = nullptr;            // per problem: updates done when the chunk was scheduled, haplotype tiles (x parts), read tiles
   int* h_nlive = nullptr;
   unsigned char* h_arena = nullptr;    // pinned image of every window's small arrays (maps, sparse lists)
   // tile lists (per-phase launches) and restart lists (chunk launches) per kernel class and variant
@@ -322,7 +322,7 @@ struct vl_batch {
   int persistent = -1;                 // chunk launches: 1 = persistent workers, 0 = one block per tile, -1 = by the number of launches
   int n_sms = 148;
   int sm_priority = 1;                 // SM shares of side-by-side launches: widest class first (see run_chunk_fused)
-  int merge_classes = 1;               // few tiles in flight: one launch of the widest class needed (see schedule)
+  int merge_classes = 1;               // one launch of the widest class needed per variant (see schedule)
   int deep2_max = 296;                 // most tiles in flight for which a launch gives every CTA a whole SM's shared memory
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   double last_ms = 0.0;
@@ -347,25 +347,22 @@ int schedule(vl_batch* b) {
   b->n_sched = 0;
   for (int c = 0; c < VL_N_CLASSES; ++c)
     for (int m = 0; m < 4; ++m) { b->want_workers[c][m] = 0; b->kt_max[c][m] = 0; }
-  // Few tiles in flight (the tail of a run): the restarts of a variant all go to the widest class any of
-  // them needs, so that the chunk is ONE launch of one-tile blocks instead of persistent workers of several
-  // classes side by side (a lone wide window next to a lone narrow one ran 20 % slower that way).  The
-  // arithmetic of a restart is the same in every class that holds its layout.
+  // The restarts of a variant (mode, split haplotype tiles) all go to the widest kernel class any of them
+  // needs, so that a chunk is ONE launch of one-tile blocks per variant.  Launching every class on its own
+  // -- persistent workers side by side, each with a static share of the SMs -- was measured slower on every
+  // workload (hiv5k 647 -> 592 ms, amplicon 2.92 -> 2.67 s): a wide straggler kept only its share of the
+  // SMs, and narrow tiles lose little in the wider class's kernel.  The arithmetic of a restart is the
+  // same in every class that holds its layout (test: ragged batch == single-window runs, bitwise).
+  // merge_classes = 0 keeps every class apart (development aid).
   int top_class[4] = {-1, -1, -1, -1};
-  if (b->merge_classes) {
-    long long want_all = 0;
-    int tc[4] = {-1, -1, -1, -1};
+  if (b->merge_classes)
     for (int p : b->order) {
       const int4 st = b->pstat[p];
       if (st.x == 0) continue;
       const VlProblem& P = b->probs[p];
       const int v = (P.mode == VL_MODE_LEP ? 1 : 0) + (P.n_hsplit > 1 ? 2 : 0);
-      tc[v] = std::max(tc[v], vl_class_of_tiles(st.y));
-      want_all += std::max(P.n_htiles * P.n_hsplit, P.n_ztiles);
+      top_class[v] = std::max(top_class[v], vl_class_of_tiles(st.y));
     }
-    if (want_all <= 2 * b->n_sms)
-      for (int v = 0; v < 4; ++v) top_class[v] = tc[v];
-  }
   for (int p : b->order) {
     const int4 st = b->pstat[p];
     if (st.x == 0) continue;
@@ -427,8 +424,9 @@ int launch_phase(vl_batch* b, int phase, int64_t* launches) {
 int run_chunk_fused(vl_batch* b, int n_iter, int64_t* launches) {
   const Layout& L = b->lay;
   const int np = L.n_problems;
-  for (int p = 0; p < np; ++p) b->h_cbase[p] = b->pstat[p].w;
-  VL_CUDA(cudaMemcpyAsync(b->dev<int>(L.cbase), b->h_cbase, (size_t)np * sizeof(int), cudaMemcpyHostToDevice, b->stream));
+  for (int p = 0; p < np; ++p)
+    b->h_cbase[p] = make_int4(b->pstat[p].w, b->probs[p].n_htiles * b->probs[p].n_hsplit, b->probs[p].n_ztiles, 0);
+  VL_CUDA(cudaMemcpyAsync(b->dev<int4>(L.cbase), b->h_cbase, (size_t)np * sizeof(int4), cudaMemcpyHostToDevice, b->stream));
   VL_CUDA(cudaMemsetAsync(b->dev<VlCtl>(L.ctl), 0, (size_t)np * sizeof(VlCtl), b->stream));
   struct Launch { int c, m, deep, occ, workers; double sms; };
   std::vector<Launch> todo;
@@ -495,7 +493,7 @@ int run_chunk_fused(vl_batch* b, int n_iter, int64_t* launches) {
     const long long blocks = persistent ? std::max(1, std::min(l.workers, (int)(l.sms * scale * l.occ + 0.5)))
                                         : (long long)n_iter * (b->n_ht[l.c][l.m] + b->n_zt[l.c][l.m]);
     VL_CUDA(vl_launch_sched(l.c, (l.m & 1) ? VL_MODE_LEP : VL_MODE_UQS, l.m >> 1, b->d_probs(), b->dev<int>(L.rlist) + b->off_rs[l.c][l.m],
-                            b->n_rs[l.c][l.m], n_iter, b->dev<int>(L.cbase), b->dev<VlCtl>(L.ctl), b->dev<int>(L.nlive) + i,
+                            b->n_rs[l.c][l.m], n_iter, b->dev<int4>(L.cbase), b->dev<VlCtl>(L.ctl), b->dev<int>(L.nlive) + i,
                             b->d_done(), b->d_pstat(), blocks, l.deep, persistent, s));
     *launches += 1;
     if (fork) {
@@ -659,7 +657,7 @@ int vl_batch_create(vl_batch** out, int32_t device, const vl_window_desc* window
   VL_CREATE_CUDA(cudaMallocHost(reinterpret_cast<void**>(&b->h_ztiles), std::max<size_t>(L.n_ztiles_total, 1) * sizeof(int2)));
   VL_CREATE_CUDA(cudaMallocHost(reinterpret_cast<void**>(&b->h_pstat), (size_t)L.n_problems * sizeof(int4)));
   VL_CREATE_CUDA(cudaMallocHost(reinterpret_cast<void**>(&b->h_rlist), (size_t)L.n_problems * sizeof(int)));
-  VL_CREATE_CUDA(cudaMallocHost(reinterpret_cast<void**>(&b->h_cbase), (size_t)L.n_problems * sizeof(int)));
+  VL_CREATE_CUDA(cudaMallocHost(reinterpret_cast<void**>(&b->h_cbase), (size_t)L.n_problems * sizeof(int4)));
   VL_CREATE_CUDA(cudaMallocHost(reinterpret_cast<void**>(&b->h_nlive), VL_N_CLASSES * 4 * sizeof(int)));
   for (int i = 0; i < VL_N_CLASSES * 4; ++i) {
     VL_CREATE_CUDA(cudaStreamCreateWithFlags(&b->class_stream[i], cudaStreamNonBlocking));

@@ -799,13 +799,9 @@ vl_cluster_kernel(const VlProblem* __restrict__ probs, const int2* __restrict__ 
 // block: inside a loop the compiler keeps the constants of both tile kinds in registers across
 // iterations and spills in the DMMA loops.)
 // =========================================================================================
-__device__ __forceinline__ int vl_phase_tiles(const VlProblem& P, unsigned phase) {
-  return (phase & 1u) ? P.n_ztiles : P.n_htiles * P.n_hsplit;
-}
-
 // Warp 0 of a block: find a restart with a tile to hand out and claim it.  task = (problem, phase,
 // tile index); problem < 0 when every restart of the launch has left the chunk.
-__device__ __forceinline__ void vl_sched_claim(const VlProblem* __restrict__ probs, const int* __restrict__ rlist,
+__device__ __forceinline__ void vl_sched_claim(const int4* __restrict__ chunk_base, const int* __restrict__ rlist,
                                                const int n_r, VlCtl* ctl, const int* n_live, int* task) {
   const int lane = threadIdx.x & 31;
   unsigned idle = 0;
@@ -817,13 +813,15 @@ __device__ __forceinline__ void vl_sched_claim(const VlProblem* __restrict__ pro
       const int slot = base + lane;
       int p = -1;
       bool open = false;
+      int4 cnt = make_int4(0, 0, 0, 0);          // the restart's tile counts travel with the scheduling data: one latency
       if (slot < n_r) {
         int at = cursor + slot;
         if (at >= n_r) at -= n_r;
         p = rlist[at];
+        cnt = __ldg(chunk_base + p);
         const unsigned long long w = *reinterpret_cast<const volatile unsigned long long*>(&ctl[p].claim);
         const unsigned phase = (unsigned)(w >> 32), idx = (unsigned)w;
-        open = phase != VL_PHASE_LEFT && idx < (unsigned)vl_phase_tiles(probs[p], phase);
+        open = phase != VL_PHASE_LEFT && idx < (unsigned)((phase & 1u) ? cnt.z : cnt.y);
       }
       unsigned cand = __ballot_sync(0xffffffffu, open);
       while (cand && got_p < 0) {
@@ -833,8 +831,9 @@ __device__ __forceinline__ void vl_sched_claim(const VlProblem* __restrict__ pro
         if (lane == src) old = atomicAdd(&ctl[p].claim, 1ull);
         old = __shfl_sync(0xffffffffu, old, src);
         const int pp = __shfl_sync(0xffffffffu, p, src);
+        const int nh = __shfl_sync(0xffffffffu, cnt.y, src), nz = __shfl_sync(0xffffffffu, cnt.z, src);
         const unsigned phase = (unsigned)(old >> 32), idx = (unsigned)old;
-        if (phase != VL_PHASE_LEFT && idx < (unsigned)vl_phase_tiles(probs[pp], phase)) {
+        if (phase != VL_PHASE_LEFT && idx < (unsigned)((phase & 1u) ? nz : nh)) {
           got_p = pp; got_phase = phase; got_idx = idx;
         }
       }
@@ -855,11 +854,11 @@ __device__ __forceinline__ void vl_sched_claim(const VlProblem* __restrict__ pro
 template <int KTM, int MODE, bool SPLIT>
 __global__ void __launch_bounds__(VL_THREADS, vl_min_ctas(KTM))
 vl_sched_kernel(const VlProblem* __restrict__ probs, const int* __restrict__ rlist, const int n_r, const int n_iter,
-                const int* __restrict__ chunk_base, VlCtl* ctl, int* n_live, int* __restrict__ done_count,
+                const int4* __restrict__ chunk_base, VlCtl* ctl, int* n_live, int* __restrict__ done_count,
                 int4* __restrict__ pstat, const int stage_doubles) {
   __shared__ int s_task[4];
   __shared__ int s_flag;
-  if (threadIdx.x < 32) vl_sched_claim(probs, rlist, n_r, ctl, n_live, s_task);
+  if (threadIdx.x < 32) vl_sched_claim(chunk_base, rlist, n_r, ctl, n_live, s_task);
   __syncthreads();
   if (s_task[0] < 0) return;
   GK_DECL(s_task[0] == 0 && s_task[2] == 0);
@@ -871,7 +870,7 @@ vl_sched_kernel(const VlProblem* __restrict__ probs, const int* __restrict__ rli
       const VlProblem& P = probs[p];
       const int t = idx % P.n_htiles, sp = idx / P.n_htiles;
       const int2 tm = make_int2(p, P.n_hsplit > 1 ? (t | (sp << 20) | (P.n_hsplit << 24)) : t);
-      vl_haplo_body<KTM, MODE, SPLIT>(probs, tm, stage_doubles, true, chunk_base[p] + k);
+      vl_haplo_body<KTM, MODE, SPLIT>(probs, tm, stage_doubles, true, chunk_base[p].x + k);
     }
 #ifdef VL_RS_PROFILE
     gk_t_ = clock64();
@@ -963,13 +962,13 @@ __device__ __noinline__ void vl_close_task(const VlProblem* P, const VlState* R,
 template <int KTM, int MODE, bool SPLIT>
 __global__ void __launch_bounds__(VL_THREADS, vl_min_ctas(KTM))
 vl_sched_persistent_kernel(const VlProblem* __restrict__ probs, const int* __restrict__ rlist, const int n_r, const int n_iter,
-                           const int* __restrict__ chunk_base, VlCtl* ctl, int* n_live, int* __restrict__ done_count,
+                           const int4* __restrict__ chunk_base, VlCtl* ctl, int* n_live, int* __restrict__ done_count,
                            int4* __restrict__ pstat, const int stage_doubles) {
   __shared__ int s_task[4];
   __shared__ int s_flag;
   __shared__ VlState sZ;
   for (;;) {
-    if (threadIdx.x < 32) vl_sched_claim(probs, rlist, n_r, ctl, n_live, s_task);
+    if (threadIdx.x < 32) vl_sched_claim(chunk_base, rlist, n_r, ctl, n_live, s_task);
     __syncthreads();
     if (s_task[0] < 0) return;
     if ((s_task[1] & 1) == 0) {
@@ -978,7 +977,7 @@ vl_sched_persistent_kernel(const VlProblem* __restrict__ probs, const int* __res
         const VlProblem& P = probs[p];
         const int t = idx % P.n_htiles, sp = idx / P.n_htiles;
         vl_haplo_task<KTM, MODE, SPLIT>(probs, make_int2(p, P.n_hsplit > 1 ? (t | (sp << 20) | (P.n_hsplit << 24)) : t),
-                                        stage_doubles, chunk_base[p] + k);
+                                        stage_doubles, chunk_base[p].x + k);
       }
       __threadfence();
       __syncthreads();
@@ -1286,7 +1285,7 @@ cudaError_t sched_occupancy(int deep, int persistent, int* ctas_per_sm, int* sme
 }
 
 template <int KTM, int MODE, bool SPLIT>
-cudaError_t launch_sched(const VlProblem* probs, const int* rlist, int n_r, int n_updates, const int* chunk_base,
+cudaError_t launch_sched(const VlProblem* probs, const int* rlist, int n_r, int n_updates, const int4* chunk_base,
                          VlCtl* ctl, int* n_live, int* done_count, int4* pstat, long long n_blocks, int deep, int persistent,
                          cudaStream_t stream) {
   int stage_doubles = 0;
@@ -1350,7 +1349,7 @@ cudaError_t vl_launch_cluster(int cls, int mode, const VlProblem* probs, const i
 }
 
 cudaError_t vl_launch_sched(int cls, int mode, int split, const VlProblem* probs, const int* rlist, int n_r, int n_updates,
-                            const int* chunk_base, VlCtl* ctl, int* n_live, int* done_count, int4* pstat, long long n_blocks,
+                            const int4* chunk_base, VlCtl* ctl, int* n_live, int* done_count, int4* pstat, long long n_blocks,
                             int deep, int persistent, cudaStream_t stream) {
   if (n_r <= 0 || n_updates <= 0 || n_blocks <= 0) return cudaSuccess;
   VL_DISPATCH(launch_sched, probs, rlist, n_r, n_updates, chunk_base, ctl, n_live, done_count, pstat, n_blocks, deep, persistent, stream)

@@ -16,11 +16,11 @@ cudaError_t vl_launch_haplo(int cls, int mode, int split, const VlProblem* probs
 cudaError_t vl_launch_cluster(int cls, int mode, const VlProblem* probs, const int2* tiles, int n_tiles,
                               int* done_count, int4* pstat, cudaStream_t stream);
 // n_updates updates of the restarts rlist[0..n_r) of one kernel class in one launch of n_blocks one-tile
-// workers (vl_sched_kernel; n_blocks = tiles the chunk can have): chunk_base[p] = updates restart p had
-// completed when the chunk was scheduled, ctl[p] zeroed and *n_live = n_r set by the caller; deep = large
+// workers (vl_sched_kernel; n_blocks = tiles the chunk can have): chunk_base[p] = (updates restart p had
+// completed when the chunk was scheduled, its haplotype tiles x read parts, its read tiles, 0), ctl[p] zeroed and *n_live = n_r set by the caller; deep = large
 // shared memory per block (few tiles in flight)
 cudaError_t vl_launch_sched(int cls, int mode, int split, const VlProblem* probs, const int* rlist, int n_r, int n_updates,
-                            const int* chunk_base, VlCtl* ctl, int* n_live, int* done_count, int4* pstat, long long n_blocks,
+                            const int4* chunk_base, VlCtl* ctl, int* n_live, int* done_count, int4* pstat, long long n_blocks,
                             int deep, int persistent, cudaStream_t stream);
 cudaError_t vl_launch_init(const VlProblem* probs, int n_probs, int4* pstat, cudaStream_t stream);
 cudaError_t vl_launch_prepare(const uint8_t* codes, const double* lt, const double* lo, const int* col_lb,

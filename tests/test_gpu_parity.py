@@ -293,6 +293,7 @@ def test_free_running_against_oracle(mode, n_raw, L, K):
     assert (r.n_iterations, r.n_updates, r.exit_message) == (traj.n_iterations, traj.n_updates, traj.exit_message)
     assert br.rel_err(r.history_elbo, np.array(traj.history_elbo)) < ENG_TOL
     assert orc.haplotype_strings(out.state["mean_haplo"]) == orc.haplotype_strings(traj.state["mean_haplo"])
+    assert np.array_equal(out.state["mean_cluster"] == 0, traj.state["mean_cluster"] == 0), "zero pattern of mean_cluster"
     assert br.rel_err(out.state["mean_cluster"], traj.state["mean_cluster"]) < SPEC_TOL
 
 

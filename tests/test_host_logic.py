@@ -385,3 +385,12 @@ def test_in_memory_window_preparation_equals_file_preparation(tmp_path):
         assert from_files.ref_seq == mem.ref_seq
         assert shotgun_hook.window_coordinates(mem) == ("chr1", "101", "140")
         assert mem.write_files is False
+
+
+def test_cluster_limit_is_reported_before_any_work():
+    from viloca_b200 import shotgun_hook
+    run = ("w-x-1-10.reads.fas", 0, 1e-4, np.array([27]), "use_quality_scores", 129, 1, True, 1e-3, False)
+    with pytest.raises(ValueError, match="128"):
+        shotgun_hook.jobs_from_runlist([run])
+    with pytest.raises(ValueError, match="128"):
+        shotgun_hook.jobs_from_arrays([], "use_quality_scores", 200, 1, 1e-4)

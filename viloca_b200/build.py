@@ -19,9 +19,10 @@ HEADERS = ["vl_device.cuh", "vl_cavi.cuh", "vl_launch.h", os.path.join("..", "..
 # vl_kernels.cu: vl_chunk_kernel runs many dependent updates in one launch, so state written by
 # one CTA is read by later CTAs of the same launch, possibly on an SM whose L1 still holds the old
 # line: global loads of that file are cached in L2 only (the operand streams through TMA anyway).
-# (--split-compile 0: the 64 kernel instantiations of that file are compiled by ptxas on all host cores,
-# 6 min -> 1.5 min; same code per kernel)
-EXTRA_FLAGS = {"vl_kernels.cu": ["-Xptxas", "-dlcm=cg", "--split-compile", "0"],
+# (not --split-compile: it compiles the 64 kernel instantiations of that file on all host cores, 6 min ->
+# 1.5 min, but the code it produces ran 13 % slower -- hiv5k 590 -> 669 ms, amplicon 2.64 -> 2.87 s, same box;
+# VL_SPLIT_COMPILE=1 turns it on for development builds)
+EXTRA_FLAGS = {"vl_kernels.cu": ["-Xptxas", "-dlcm=cg"] + (["--split-compile", "0"] if os.environ.get("VL_SPLIT_COMPILE") else []),
                # host arithmetic that must match NumPy bit for bit (running mean of the qualities): no FMA contraction
                "vl_prepare.cu": ["-Xcompiler", "-ffp-contract=off"]}
 NVCC_FLAGS = [
@@ -61,8 +62,7 @@ def build(force: bool = False, verbose: bool = False, profile: bool = False, def
         obj = os.path.join(LIB_DIR, src.replace(".cu", suffix + ".o"))
         objs.append(obj)
         if force or _stale(obj, [src_path] + headers):
-            extra = [f for f in EXTRA_FLAGS.get(src, []) if not (os.environ.get("VL_NO_SPLIT_COMPILE") and f in ("--split-compile", "0"))]
-            cmd = [_nvcc()] + NVCC_FLAGS + (["-DVL_RS_PROFILE"] if profile else []) + extra_defs + extra + \
+            cmd = [_nvcc()] + NVCC_FLAGS + (["-DVL_RS_PROFILE"] if profile else []) + extra_defs + EXTRA_FLAGS.get(src, []) + \
                 ["-c", src_path, "-o", obj]
             if verbose:
                 cmd.insert(1, "-Xptxas=-v")

@@ -25,6 +25,15 @@ from .local_haplotype_inference import _common
 MODES = {"use_quality_scores": "uqs", "learn_error_params": "lep"}
 
 
+MAX_CLUSTERS = 128     # VL_MAX_CLUSTERS of include/viloca_b200.h (the reference's CLI allows any K, cli.py:179-181)
+
+
+def _check_clusters(k: int, what: str) -> None:
+    if int(k) > MAX_CLUSTERS:
+        raise ValueError(f"{what}: n_max_haplotypes = {k} exceeds the engine's limit of {MAX_CLUSTERS} clusters "
+                         f"(VL_MAX_CLUSTERS); run this window with the reference, or with K <= {MAX_CLUSTERS}")
+
+
 def jobs_from_runlist(runlist) -> list:
     jobs = []
     for run_setting in runlist:
@@ -32,6 +41,7 @@ def jobs_from_runlist(runlist) -> list:
          conv_thres, record_history) = run_setting
         if inference_type not in MODES:
             raise ValueError(f"inference_type {inference_type!r} is not served by the CUDA engine")
+        _check_clusters(n_max_haplotypes, filein)
         mode = MODES[inference_type]
         stem = filein.split(".reads.")[0]                       # shotgun.py:151-152
         seed = int(seed[0]) if hasattr(seed, "__len__") else int(seed)   # shotgun.py:442-443 passes an array
@@ -79,6 +89,7 @@ def jobs_from_arrays(windows, inference_type: str, n_max_haplotypes: int, n_mfa_
     if inference_type not in MODES:
         raise ValueError(f"inference_type {inference_type!r} is not served by the CUDA engine")
     mode = MODES[inference_type]
+    _check_clusters(n_max_haplotypes, "jobs_from_arrays")
     jobs = []
     for w in windows:
         get = (lambda k: w[k]) if isinstance(w, dict) else (lambda k: getattr(w, k))

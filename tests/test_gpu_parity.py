@@ -760,3 +760,32 @@ def test_in_memory_windows_through_the_batched_hook(golden_dir, tmp_path, monkey
         assert sorted((k.pos, k.var, v.freq, v.support) for k, v in a["snvs"].items()) == \
                sorted((k.pos, k.var, v.freq, v.support) for k, v in b["snvs"].items())
         assert a["cooccurring"] == b["cooccurring"]
+
+
+def test_run_jobs_in_host_bounded_groups(golden_dir, tmp_path, monkeypatch):
+    """A run whose windows do not fit host memory together is loaded, run and released group by group
+    (forced here with a 1-byte budget): the same files and states as the all-at-once path."""
+    from oracle import bam_windows
+    from viloca_b200 import shotgun_hook
+    from viloca_b200.local_haplotype_inference import _common
+    meta = _json_file(os.path.join(golden_dir, "bam_windows", "expected.json"))
+    out = {}
+    for tag, budget in (("all", None), ("groups", 1)):
+        d = tmp_path / tag
+        d.mkdir()
+        monkeypatch.chdir(d)
+        runlist = []
+        for name in BAM_WINDOWS[:3]:
+            m = meta[name]
+            _, f_reads, _, _ = bam_windows.materialize(os.path.join(golden_dir, "bam_windows", name, "window.npz"), str(d))
+            runlist.append((f_reads, 0, 0.0001, np.array([m["seed"]]), "use_quality_scores", m["K"], m["n_starts"], True, 1e-3, False))
+        jobs = shotgun_hook.jobs_from_runlist(runlist)
+        fin = _common.run_jobs(jobs, device=0, host_budget=budget)
+        out[tag] = (d, [meta[n]["stem"] for n in BAM_WINDOWS[:3]], fin, jobs)
+    (d1, stems, f1, _), (d2, _, f2, jobs2) = out["all"], out["groups"]
+    assert all(j.window is None and j.ref_seq for j in jobs2)                    # released, but still usable for snv_tables
+    for stem, (s1, r1), (s2, r2) in zip(stems, f1, f2):
+        for suffix in (".reads-support.fas", ".reads-cor.fas"):
+            assert _text(os.path.join(d1, stem + suffix)) == _text(os.path.join(d2, stem + suffix))
+        assert r1["elbo"] == r2["elbo"] and np.array_equal(s1["mean_cluster"], s2["mean_cluster"])
+    assert len(shotgun_hook.snv_tables(jobs2, f2)) == 3

@@ -394,3 +394,28 @@ def test_cluster_limit_is_reported_before_any_work():
         shotgun_hook.jobs_from_runlist([run])
     with pytest.raises(ValueError, match="128"):
         shotgun_hook.jobs_from_arrays([], "use_quality_scores", 200, 1, 1e-4)
+
+
+def test_host_memory_estimate_of_an_unloaded_window(tmp_path):
+    """run_jobs decides from the read file's size alone whether the windows of a run fit host memory
+    together; the estimate must bound what the loaded window really takes."""
+    from viloca_b200 import shotgun_hook
+    rng = np.random.default_rng(3)
+    L, n_raw = 50, 400
+    seqs = ["".join(rng.choice(list("ACGT"), size=L)) for _ in range(n_raw)]
+    stem = str(tmp_path / "w-c-1-50")
+    with open(stem + ".reads.fas", "w") as fh:
+        for i, s in enumerate(seqs):
+            fh.write(f">read{i} {i}\n{s}\n")
+    with open(stem + ".ref.fas", "w") as fh:
+        fh.write(f">c 1\n{seqs[0]}\n")
+    np.save(stem + ".qualities.npy", rng.integers(2, 41, size=(n_raw, L)).astype(np.int64), allow_pickle=True)
+    job = shotgun_hook.jobs_from_runlist([(stem + ".reads.fas", 0, 1e-4, np.array([27]), "use_quality_scores", 20, 3, True, 1e-3, False)])[0]
+    est = _common.host_bytes_estimate(job)
+    job.load()
+    real = job.window.input_bytes() + job.prepared.qualities.nbytes
+    assert real <= est <= 3 * real
+    assert _common.host_bytes_estimate(job) >= job.window.input_bytes()       # loaded: the real figure
+    _common.release_job(job)
+    assert job.window is None and job.prepared.qualities is None and job.ref_seq
+    assert _common.host_budget_bytes() > (1 << 28)

@@ -258,6 +258,49 @@ def _load_cost_seconds(job: WindowJob) -> float:
     return 12e-9 * size + 1.2e-7 * (size / 200.0) * job.K * job.n_starts
 
 
+def host_bytes_estimate(job: WindowJob) -> int:
+    """Host memory a loaded window takes, from the size of its read file alone (nothing is parsed):
+    codes + qualities + the two log tables of the unique reads (<= raw reads) and the seeded initial
+    responsibilities (reads x K x restarts doubles) -- the term that makes a 100 000-read, 20-restart
+    window 1.6 GB."""
+    if job.window is not None:
+        w = job.window
+        return int(w.input_bytes()) + (0 if job.prepared is None or job.prepared.qualities is None else job.prepared.qualities.nbytes)
+    try:
+        if job.reads_text is not None:
+            size, head = len(job.reads_text), job.reads_text[:65536]
+        else:
+            size = os.path.getsize(job.freads_in)
+            with open(job.freads_in, "rb") as fh:
+                head = fh.read(65536)
+    except OSError:
+        return 0
+    lines = head.split(b"\n")
+    rec = (len(lines[0]) + len(lines[1]) + 2) if len(lines) > 1 else 1
+    length = len(lines[1]) if len(lines) > 1 else 1
+    n_raw = max(1, size // max(rec, 1))
+    return int(n_raw * (length * (1 + 8 + 16) + 8.0 * job.K * job.n_starts))
+
+
+def host_budget_bytes() -> int:
+    """Host memory the loaded windows of one run_jobs call may take together: 40 % of what is available."""
+    try:
+        import psutil
+        return int(0.4 * psutil.virtual_memory().available)
+    except Exception:                      # noqa: BLE001
+        return 64 << 30
+
+
+def release_job(job: WindowJob) -> None:
+    """Drop the large host arrays of a finished window (inputs, initial states); what the caller and
+    ``snv_tables`` need afterwards -- names, the reference window, the finished state -- stays."""
+    job.window = None
+    job.qualities = None
+    job.reads_text = None
+    if job.prepared is not None:
+        job.prepared.qualities = None
+
+
 def load_jobs(jobs: Sequence[WindowJob], workers: Optional[int] = None) -> list:
     """Read and prepare the windows of ``jobs`` (FASTA / qualities -> compact tensors, seeded initial
     states).  This is host work of the same order as the GPU run itself, so it is spread over the host
@@ -441,16 +484,32 @@ def _finish_job(job: WindowJob, batch, i: int, out, histories=None):
     return state, result
 
 
-def run_jobs(jobs: Sequence[WindowJob], device: int = 0, budget_bytes: Optional[int] = None) -> list:
+def run_jobs(jobs: Sequence[WindowJob], device: int = 0, budget_bytes: Optional[int] = None,
+             host_budget: Optional[int] = None) -> list:
     """Load, run and finish a list of windows on one GPU; writes ``<output_name>support.fas``
     and ``<output_name>cor.fas`` per window (run_dpm_mfa.py:119-120).  Returns the best
     restart's state dict (with the summary merged in) per job.  The windows go through the GPU in
     waves bounded by the free HBM (``engine.run_in_waves``: the next wave is uploaded while this
     one runs), the way the reference bounds its pool by ``max_proc`` (shotgun.py:527-538)."""
-    from ..engine import CaviBatch, run_in_waves
+    from ..engine import CaviBatch, plan_waves, run_in_waves
+    jobs = list(jobs)
     for job in jobs:
         if job.write_files:
             os.makedirs(job.output_dir, exist_ok=True)
+    # Host memory is bounded too: when the windows would not fit together (an ONT genome: 120 windows x
+    # 1.6 GB of initial states), they are loaded, run and released group by group
+    sizes = [host_bytes_estimate(j) for j in jobs]
+    budget = host_budget_bytes() if host_budget is None else int(host_budget)
+    if len(jobs) > 1 and sum(sizes) > budget:
+        finished = [None] * len(jobs)
+        for group in plan_waves(sizes, budget):
+            part = load_jobs([jobs[i] for i in group])
+            for i, job, fin in zip(group, part, run_jobs(part, device=device, budget_bytes=budget_bytes, host_budget=1 << 62)):
+                finished[i] = fin
+                jobs[i].ref_seq, jobs[i].prepared = job.ref_seq, job.prepared      # (a process pool returns copies)
+                release_job(job)
+                release_job(jobs[i])
+        return finished
     jobs = load_jobs(jobs)
     finished = [None] * len(jobs)
     plain = [i for i, j in enumerate(jobs) if not j.record_history]

@@ -123,21 +123,26 @@ def run_dpm_batch(runlist, devices: Optional[Sequence[int]] = None, collect: boo
     import torch
     runlist = list(runlist)
     todo = runlist if runlist and isinstance(runlist[0], _common.WindowJob) else jobs_from_runlist(runlist)
-    jobs = _common.load_jobs(todo, workers=load_workers)    # a process pool, like the reference's
-    if not jobs:
+    if not todo:
         return ([], []) if collect else None
+    # windows that fit host memory together are loaded at once (a process pool, like the reference's); a
+    # genome that does not (ONT: 1.6 GB of initial states per window) is loaded group by group inside run_jobs
+    sizes = [_common.host_bytes_estimate(j) for j in todo]
+    lazy = sum(sizes) > _common.host_budget_bytes()
+    jobs = todo if lazy else _common.load_jobs(todo, workers=load_workers)
     if devices is None:
         devices = list(range(torch.cuda.device_count()))
     if not devices:
         raise RuntimeError("no CUDA device: the CAVI engine has no CPU fallback")
-    parts = scheduler.lpt_partition([j.window.cost() for j in jobs], len(devices))
+    parts = scheduler.lpt_partition([float(sz) if lazy else j.window.cost() for j, sz in zip(jobs, sizes)], len(devices))
     errors = []
     finished = [None] * len(jobs)
+    host_share = max(1, _common.host_budget_bytes() // len(devices))     # the device threads load side by side
 
     def work(dev, idx):
         try:
             if idx:
-                for i, fin in zip(idx, _common.run_jobs([jobs[i] for i in idx], device=dev)):
+                for i, fin in zip(idx, _common.run_jobs([jobs[i] for i in idx], device=dev, host_budget=host_share)):
                     finished[i] = fin
         except Exception as exc:                                 # shotgun.py:137-143: log and re-raise
             logging.error(f"Error in process for device {dev}: {exc}")

@@ -153,11 +153,11 @@ void vl_batch_destroy(vl_batch* batch);
  */
 #define VL_OPT_SKIP_DEAD 1
 /*
- * VL_OPT_FUSED_CHUNKS (default 1): vl_batch_run enqueues a whole chunk of updates of a kernel
- * class as ONE launch of persistent worker CTAs that claim tiles from per-restart scheduling words in
- * device memory (launches of different classes side by side on their own streams), instead of two
- * launches per update; 0 restores the per-update launches (vl_batch_step and
- * vl_batch_profile_step always use those).  Same arithmetic, bit-identical results.
+ * VL_OPT_FUSED_CHUNKS (default 1): vl_batch_run enqueues a whole chunk of updates of all running
+ * restarts as ONE launch per variant (mode x split haplotype tiles) of one-tile worker CTAs that claim
+ * tiles from per-restart scheduling words in device memory, instead of two launches per update; 0
+ * restores the per-update launches (vl_batch_step and vl_batch_profile_step always use those).  Same
+ * arithmetic, bit-identical results.
  */
 #define VL_OPT_FUSED_CHUNKS 3
 int vl_batch_set_option(vl_batch* batch, int32_t option, int32_t value);

@@ -419,3 +419,27 @@ def test_host_memory_estimate_of_an_unloaded_window(tmp_path):
     _common.release_job(job)
     assert job.window is None and job.prepared.qualities is None and job.ref_seq
     assert _common.host_budget_bytes() > (1 << 28)
+
+
+def test_bench_workload_description_and_lpt_costs():
+    """bench.py's host logic: both arms print the same `config`; the longest-first cost follows the committed
+    iteration table (profile-guided), the reference arm's genome work is derived from the same table."""
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    import bench
+    spec = synthetic.WORKLOADS["sars_amplicon"]
+    cfg = bench.config_of(spec, spec.n_windows)
+    assert cfg["workload"] == "sars_amplicon" and cfg["windows"] == 98 and "l2" in cfg and "model" not in cfg
+    assert bench.config_of(spec, spec.n_windows) == cfg                      # one function, both arms
+    costs, how = bench.predicted_costs(spec, spec.n_windows)
+    assert how.startswith("profile-guided") and len(costs) == 98
+    table = bench.load_iteration_table("sars_amplicon")
+    assert int(np.argmax(costs)) == int(np.argmax(np.asarray(table["n_updates"]) * np.asarray(table["n_reads"]) * np.asarray(table["length"])))
+    parts, _ = bench.shard_windows(spec, spec.n_windows, 8)
+    assert sorted(i for p in parts for i in p) == list(range(98))
+    heavy = int(np.argmax(costs))
+    assert [p for p in parts if heavy in p][0] == [heavy]                     # the 17 178-update window gets a GPU of its own
+    work, src = bench.genome_work(spec, spec.n_windows)
+    assert work > 0 and "bench_iterations" in src
+    costs_u, how_u = bench.predicted_costs(synthetic.WORKLOADS["sars_ont"], 120)
+    assert how_u.startswith("uniform") and len(set(costs_u)) == 1

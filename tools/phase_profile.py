@@ -20,7 +20,7 @@ def main():
     nw = int(sys.argv[2]) if len(sys.argv) > 2 else None
     wins = synthetic.make_workload(name, nw)
     rows = []
-        with engine.CaviBatch(wins) as b:
+    with engine.CaviBatch(wins) as b:
         b.upload()
         done = 0
         for upto in (0, 8, 32, 128, 512, 1024, 2048, 3072, 4096, 6144):

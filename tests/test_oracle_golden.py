@@ -221,3 +221,23 @@ def test_lep_loop_and_finishing_match_reference(golden_dir, name):
         rows = np.nonzero(member[:, j])[0]
         assert [p.read_ids[n][0] for n in rows] == meta["assigned_unique"][j]
         assert [rid for n in rows for rid in p.read_ids[n]] == meta["assigned_all"][j]
+
+
+def test_oracle_matches_reference_at_full_amplicon_shape(golden_dir):
+    """The oracle at the configs[3] shape (N_raw = 20 000 -> 2 571 unique reads, L = 408, K = 100) against
+    the summary of the UNMODIFIED reference's 12 iterations (oracle/make_golden_fullshape.py): the oracle
+    is pinned at full size too, not only on the small fixtures."""
+    import os
+    import sys
+    path = os.path.join(golden_dir, "fullshape", "amplicon_full.npz")
+    if not os.path.exists(path):
+        pytest.skip("fullshape goldens not generated")
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    import _bridge as br
+    from oracle import make_golden_fullshape as mg
+    g = np.load(path, allow_pickle=True)
+    from viloca_b200 import synthetic
+    win = synthetic.make_window(synthetic.WORKLOADS["sars_amplicon"], 5, max_iter=4)
+    assert (win.n_reads, win.length) == (int(g["n_reads"]), int(g["length"]))
+    traj = br.oracle_run(win, max_iterations=4)                      # the first 4 of the 12 (a few seconds)
+    assert np.array_equal(np.array(traj.history_elbo), g["r0_history"][:4])      # bit for bit, like the small fixtures

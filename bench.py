@@ -420,9 +420,7 @@ def extra_line(name, device, indices=None, steps=2, warmup=1, gen_procs=1, **kw)
     n_problems = sum(w.n_starts for w in windows)
     with engine.CaviBatch(windows, device=device) as batch:
         run_ms, e2e_ms, _, launches_run, outcomes, _ = timed_steps(batch, windows, steps, warmup, torch.cuda.synchronize, device)
-        ops = operand_stats(windows)
         updates = [r.n_updates for o in outcomes for r in o.restarts]
-        ex = sum(2.0 * o["Npad"] * o["NCs"] for o, w in zip(ops, windows) for _ in range(w.n_starts))
         out = {"workload": name, "windows": len(windows), "of_windows": spec.n_windows, "n_starts": spec.n_starts,
                "n_unique_mean": float(np.mean([w.n_reads for w in windows])), "length_mean": float(np.mean([w.length for w in windows])),
                "value": len(windows) * steps / (run_ms * 1e-3), "unit": UNIT, "ms_per_step": run_ms / steps,
@@ -432,7 +430,6 @@ def extra_line(name, device, indices=None, steps=2, warmup=1, gen_procs=1, **kw)
                "steps": steps, "warmup": warmup, "loop_launches_per_step": launches_run / steps,
                "iterations": {"mean": float(np.mean(updates)), "max": int(max(updates)), "min": int(min(updates))},
                "workspace_mb": batch.workspace_bytes / 1e6, "host_generation_s": gen_s}
-        del ex
     return out
 
 
